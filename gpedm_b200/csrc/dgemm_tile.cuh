@@ -1,0 +1,177 @@
+// FP64 tensor-pipe (DMMA) tile contraction for sm_100a.
+//
+// One CTA (256 threads, 8 warps) computes one 128x128 tile
+//     C = (+/-) sum_k Aop[m,k] * Bop[k,n]  (+ Cin)
+// over an arbitrary k range (multiple of 16).  This is the workhorse behind every
+// O(N^3) step that replaces the reference's LAPACK calls (dpotrf / dpotri behind
+// Matrix::chol / chol2inv, reference R/GPfunctions.R:826-829): the Cholesky panel
+// and trailing update, the triangular inverse and the L^-T L^-1 product.
+//
+// Hardware mapping: tcgen05/UMMA has no f64 kind, so the FP64 tensor path on
+// sm_100a is warp-level `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4).  Each warp owns
+// a 64x32 sub-tile = 8x4 DMMA tiles = 64 FP64 accumulators per thread; operands
+// are staged global -> shared with a 4-deep cp.async (LDGSTS) pipeline of
+// 16-wide k slabs, in layouts padded so that every fragment LDS.64 is
+// bank-conflict-free.
+//
+// Operand layouts (all matrices are column-major in global memory):
+//   A "MN-major": element (m,k) at A[m + k*lda]   (m contiguous; plain  "N")
+//   A "K-major" : element (m,k) at A[k + m*lda]   (k contiguous; i.e.   "T")
+//   B "MN-major": element (k,n) at B[n + k*ldb]   (n contiguous; i.e.   "T")
+//   B "K-major" : element (k,n) at B[k + n*ldb]   (k contiguous; plain  "N")
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpedm {
+
+constexpr int TB = 128;            // tile edge
+constexpr int GEMM_THREADS = 256;  // 8 warps: 2 (m) x 4 (n), warp tile 64 x 32
+constexpr int BKK = 16;            // k slab per pipeline stage
+constexpr int GEMM_STAGES = 4;
+constexpr int LD_MN = TB + 4;      // smem row stride (doubles) of an MN-major slab [BKK][LD_MN]
+constexpr int LD_K = BKK + 4;      // smem row stride (doubles) of a  K-major slab [TB][LD_K]
+constexpr int SLAB_ELEMS = (BKK * LD_MN > TB * LD_K) ? BKK * LD_MN : TB * LD_K;  // 2560 doubles
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * SLAB_ELEMS * (int)sizeof(double);  // 160 KB
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Stage one 16-wide k slab of a 128-row operand into shared memory.
+template <bool KMAJOR>
+__device__ __forceinline__ void load_slab(double* __restrict__ s, const double* __restrict__ g, size_t ld,
+                                          int k0, int tid) {
+  if (!KMAJOR) {
+    // global: 16 columns (k) of 128 contiguous doubles.  1024 16-byte chunks, 4 per thread.
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int chunk = tid + r * GEMM_THREADS;
+      int row = chunk >> 6;        // k within slab
+      int c2 = (chunk & 63) << 1;  // m offset
+      cp_async16(s + row * LD_MN + c2, g + (size_t)(k0 + row) * ld + c2);
+    }
+  } else {
+    // global: 128 columns (m) of 16 contiguous doubles (k).
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int chunk = tid + r * GEMM_THREADS;
+      int row = chunk >> 3;       // m
+      int c2 = (chunk & 7) << 1;  // k offset within slab
+      cp_async16(s + row * LD_K + c2, g + (size_t)row * ld + k0 + c2);
+    }
+  }
+}
+
+struct TileAcc {
+  double v[8][4][2];
+};
+
+// Main contraction.  `smem` must provide GEMM_SMEM_BYTES.  kbeg/kend are element
+// indices along k (multiples of 16) applied to both operands' k axes.
+// If Cin != nullptr the accumulator starts from the Cin tile (fetched before the
+// k loop so its latency hides under the first slabs), else from zero.
+template <bool A_KMAJOR, bool B_KMAJOR>
+__device__ __forceinline__ void gemm_tile(const double* __restrict__ A, size_t lda, const double* __restrict__ B,
+                                          size_t ldb, int kbeg, int kend, bool negate, const double* Cin,
+                                          size_t ldcin, double* __restrict__ Cout, size_t ldc, double* smem) {
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = (warp & 1) * 64, n0 = (warp >> 1) * 32;
+
+  double* sA = smem;
+  double* sB = smem + GEMM_STAGES * SLAB_ELEMS;
+
+  const int nk = (kend - kbeg) / BKK;
+  // prologue: first STAGES-1 slabs in flight
+#pragma unroll
+  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+    if (s < nk) {
+      load_slab<A_KMAJOR>(sA + s * SLAB_ELEMS, A, lda, kbeg + s * BKK, tid);
+      load_slab<B_KMAJOR>(sB + s * SLAB_ELEMS, B, ldb, kbeg + s * BKK, tid);
+    }
+    cp_async_commit();
+  }
+
+  TileAcc acc;
+  if (Cin != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          acc.v[i][j][e] = Cin[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ldcin];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc.v[i][j][0] = acc.v[i][j][1] = 0.0;
+  }
+
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<GEMM_STAGES - 2>();
+    __syncthreads();
+    {
+      int nxt = kt + GEMM_STAGES - 1;
+      if (nxt < nk) {
+        int sb = nxt % GEMM_STAGES;
+        load_slab<A_KMAJOR>(sA + sb * SLAB_ELEMS, A, lda, kbeg + nxt * BKK, tid);
+        load_slab<B_KMAJOR>(sB + sb * SLAB_ELEMS, B, ldb, kbeg + nxt * BKK, tid);
+      }
+      cp_async_commit();
+    }
+    const double* a_s = sA + (kt % GEMM_STAGES) * SLAB_ELEMS;
+    const double* b_s = sB + (kt % GEMM_STAGES) * SLAB_ELEMS;
+#pragma unroll
+    for (int k4 = 0; k4 < BKK / 4; ++k4) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double x = A_KMAJOR ? a_s[(m0 + 8 * i + g) * LD_K + k4 * 4 + t] : a_s[(k4 * 4 + t) * LD_MN + m0 + 8 * i + g];
+        a[i] = negate ? -x : x;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        b[j] = B_KMAJOR ? b_s[(n0 + 8 * j + g) * LD_K + k4 * 4 + t] : b_s[(k4 * 4 + t) * LD_MN + n0 + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        Cout[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ldc] = acc.v[i][j][e];
+}
+
+// Decode a linear index into lower-triangle coordinates (i >= j), row-major over rows:
+// t = i*(i+1)/2 + j.
+__device__ __forceinline__ void tri_decode(int t, int& i, int& j) {
+  int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((long long)(r + 1) * (r + 2) / 2 <= t) ++r;
+  while ((long long)r * (r + 1) / 2 > t) --r;
+  i = r;
+  j = t - r * (r + 1) / 2;
+}
+
+}  // namespace gpedm
