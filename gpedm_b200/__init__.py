@@ -1,0 +1,7 @@
+"""gpedm_b200: B200-native (sm_100a, FP64) GP fit / predict hot path of GPEDM behind the
+reference's own API names.  All numerics run in libgpedm_b200.so (hand-written CUDA, C ABI in
+include/gpedm.h); there is no CPU fallback."""
+from ._lib import GPEDMError, build, lib  # noqa: F401
+from .core import (GPModel, fmingrad_Rprop, fp64_peak, getcov, getlikegrad, logit)  # noqa: F401
+from .fitgp import GP, fitGP, getR2, getR2pop, makelags, predict, predict_seq, summary, update  # noqa: F401
+from .batch import fit_batch, fit_grid  # noqa: F401

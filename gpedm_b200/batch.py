@@ -1,0 +1,108 @@
+"""Batched independent fits (E/tau model-selection grids, multistart, per-population models):
+the path that shards across GPUs.  Mirrors the user-level loops of the reference
+(vignettes/choosingE.Rmd:63-86, R/rhomatrix.R:169-182) as one call into `gpedm_fit_batch`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import FitDesc, Result, check, dptr, f64, iptr, lib
+from .core import SIGMA2MAX, SIGMA2MIN, VEMAX, VEMIN, logit, pop_codes
+from .fitgp import _lagmatrix, _mean, _sd, getR2
+
+
+def default_initparst(d, single_pop=True):
+    """Default start of fitGP (R/GPfunctions.R:409, :425-429)."""
+    initpars = np.concatenate([np.full(d, 0.1), [0.001, 1 - 0.001, 0.5]])
+    t = np.concatenate([np.log(initpars[:d]), [logit(initpars[d], VEMIN, VEMAX),
+                                               logit(initpars[d + 1], SIGMA2MIN, SIGMA2MAX),
+                                               logit(initpars[d + 2], 0.0, 1.0)]])
+    if single_pop:
+        t[d + 2] = 0.0
+    return t
+
+
+def fit_batch(problems, ngpus=1, devices=None, want_loo=False):
+    """problems: list of dicts with Y (N), X (N x d), optional pop, rhomatrix, initparst, fixedpars,
+    modeprior, rhofixed.  Returns a list of result dicts (plus loo_mean / loo_var / insamp_mean when
+    want_loo)."""
+    n = len(problems)
+    descs = (FitDesc * n)()
+    results = (Result * n)()
+    keep = []
+    outs = []
+    for i, pr in enumerate(problems):
+        Y = f64(pr["Y"]).ravel()
+        X = np.asarray(pr["X"], dtype=np.float64)
+        if X.ndim == 1:
+            X = X[:, None]
+        X = f64(X)
+        N, d = X.shape
+        pop = pr.get("pop")
+        codes, levels = pop_codes(np.ones(N, dtype=np.int64) if pop is None else pop)
+        rm = pr.get("rhomatrix")
+        rm = None if rm is None else f64(rm)
+        ip = pr.get("initparst")
+        ip = f64(default_initparst(d, len(levels) == 1) if ip is None else ip).ravel()
+        fp = pr.get("fixedpars")
+        fp = None if fp is None else f64(fp).ravel()
+        o = dict(loo_mean=np.empty(N), loo_var=np.empty(N), insamp_mean=np.empty(N), insamp_var=np.empty(N))
+        keep.append((Y, X, codes, rm, ip, fp, o))
+        ds = descs[i]
+        ds.N, ds.d, ds.np = N, d, len(levels)
+        ds.X, ds.Y, ds.pop = dptr(X), dptr(Y), iptr(codes)
+        ds.rhomat, ds.initparst, ds.fixedpars = dptr(rm), dptr(ip), dptr(fp)
+        ds.modeprior = float(pr.get("modeprior", 1.0))
+        rf = pr.get("rhofixed")
+        ds.rhofixed = float("nan") if rf is None else float(rf)
+        ds.want_loo = 1 if want_loo else 0
+        if want_loo:
+            ds.loo_mean, ds.loo_var = dptr(o["loo_mean"]), dptr(o["loo_var"])
+            ds.insamp_mean, ds.insamp_var = dptr(o["insamp_mean"]), dptr(o["insamp_var"])
+        outs.append(o)
+    dev = None if devices is None else np.ascontiguousarray(np.asarray(devices, dtype=np.int32))
+    check(lib().gpedm_fit_batch(n, descs, int(ngpus), iptr(dev), None, results))
+    res = []
+    for i in range(n):
+        r = results[i].to_dict()
+        if want_loo:
+            r.update(outs[i])
+        res.append(r)
+    return res
+
+
+def grid_problems(y, Es, taus, pop=None, scaling="global"):
+    """Training sets of the E x tau model-selection grid of vignettes/choosingE.Rmd:63-86:
+    for each (E, tau) lag y, scale (global), drop incomplete rows.  Returns (problems, meta)."""
+    y = np.asarray(y, dtype=np.float64)
+    popv = np.ones(len(y), dtype=np.int64).astype(object) if pop is None else np.asarray(pop, dtype=object)
+    if scaling != "global":
+        raise NotImplementedError("grid helper supports global scaling")
+    problems, meta = [], []
+    for E in Es:
+        for tau in taus:
+            x = _lagmatrix(y, popv, E, tau)
+            ym, ys = _mean(y), _sd(y)
+            yds = (y - ym) / ys
+            xm = np.array([_mean(x[:, j]) for j in range(x.shape[1])])
+            xs = np.array([_sd(x[:, j]) for j in range(x.shape[1])])
+            xds = (x - xm[None, :]) / xs[None, :]
+            ok = ~(np.isnan(yds) | np.isnan(xds).any(axis=1))
+            problems.append(dict(Y=yds[ok], X=xds[ok], pop=popv[ok]))
+            meta.append(dict(E=E, tau=tau, ymean=ym, ysd=ys, rows=ok, yobs=y[ok]))
+    return problems, meta
+
+
+def fit_grid(y, Es, taus, pop=None, ngpus=1, devices=None):
+    """fitGP(y, E, tau, predictmethod="loo") over an E x tau grid, returning one dict per cell with
+    the fitted modes and the leave-one-out R2 (the model-selection criterion of choosingE.Rmd)."""
+    problems, meta = grid_problems(y, Es, taus, pop)
+    res = fit_batch(problems, ngpus=ngpus, devices=devices, want_loo=True)
+    out = []
+    for r, m in zip(res, meta):
+        loo = r["loo_mean"] * m["ysd"] + m["ymean"]
+        ins = r["insamp_mean"] * m["ysd"] + m["ymean"]
+        out.append(dict(E=m["E"], tau=m["tau"], pars=r["pars"], iter=r["iter"], nevals=r["nevals"],
+                        ln_post=-r["nllpost"], R2_insample=getR2(m["yobs"], ins), R2_loo=getR2(m["yobs"], loo),
+                        status=r["status"]))
+    return out

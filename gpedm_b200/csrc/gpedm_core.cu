@@ -1,0 +1,1297 @@
+// libgpedm_b200: host orchestration + C ABI (include/gpedm.h) for the B200-native GP
+// evaluation pipeline.  The scalar parts of getlikegrad (parameter transforms, priors,
+// chain rule; reference R/GPfunctions.R:590-630, 719-725, 752-777) and the Rprop loop
+// (:522-584) run on the host; everything that touches N x N data runs in the kernels of
+// kernels.cuh.  There is no CPU fallback for any N^2 / N^3 step.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gpedm.h"
+#include "kernels.cuh"
+
+using namespace gpedm;
+
+static_assert(MAXD == GPEDM_MAX_D, "MAXD mismatch");
+
+// ------------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return set_err(GPEDM_ERR_CUDA, "CUDA error '%s' at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, \
+                     __LINE__, #call);                                                               \
+  } while (0)
+
+// Reference bounds (R/GPfunctions.R:591-593)
+static const double VEMIN = 0.0001, SIGMA2MIN = 0.0001, VEMAX = 4.9999, SIGMA2MAX = 4.9999, RHOMIN = 0.0001,
+                    RHOMAX = 1.0;
+static inline double logit3(double x, double lo, double hi) { return log((x - lo) / (hi - x)); }
+
+// ------------------------------------------------------------------------------- handle
+struct gpedm_fit_s {
+  int device = 0;
+  int64_t N = 0;
+  int Np = 0, nb = 0, ntiles = 0;
+  int d = 0, np = 1, p = 0;
+  bool has_rhomat = false;
+  bool single_pop = true;
+  double *dX = nullptr, *dY = nullptr, *drhotab = nullptr;
+  int* dpop = nullptr;
+  double *bufA = nullptr, *bufB = nullptr, *bufC = nullptr;
+  EvalParams* dparams = nullptr;
+  EvalParams* hparams = nullptr;  // pinned
+  double *dz = nullptr, *da = nullptr, *ddiagS = nullptr, *dpart = nullptr, *dlogdet = nullptr,
+         *dtracepart = nullptr, *dscal = nullptr;
+  double* hscal = nullptr;  // pinned
+  int* dinfo = nullptr;
+  int* hinfo = nullptr;  // pinned
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[GPEDM_NPHASE + 1] = {};
+  float phase_ms[GPEDM_NPHASE] = {};
+  int64_t launches = 0;
+  bool have_full = false;  // L (bufA), L^-1 (bufB), Sigma^-1 (bufC), a, diagS valid for `cur`
+  double cur_ve = 0, cur_sigma2 = 0, cur_rho = 0;
+  std::vector<double> hY;  // host copy of Y (N)
+  std::vector<int> hpop;
+};
+
+static const int NSCAL = 8 + MAXD + 3;
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+static bool g_attr_set[64] = {};
+static int ensure_kernel_attrs(int device) {
+  if (device < 64 && g_attr_set[device]) return 0;
+  CU(cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(potrf_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(trtri_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(trtri_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tri_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(diag_potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+  int trace_smem = (4 * MAXD * TB + 2 * TB + 8 * (MAXD + 3)) * 8 + 2 * TB * 4;
+  CU(cudaFuncSetAttribute(grad_trace_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
+  CU(cudaFuncSetAttribute(grad_trace_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
+  CU(cudaFuncSetAttribute(grad_trace_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
+  int asm_smem = 2 * MAXD * TB * 8 + 2 * TB * 4;
+  CU(cudaFuncSetAttribute(assemble_sigma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_smem));
+  CU(cudaFuncSetAttribute(cov_rect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_smem));
+  if (device < 64) g_attr_set[device] = true;
+  return 0;
+}
+
+extern "C" int gpedm_abi_version(void) { return GPEDM_ABI_VERSION; }
+extern "C" const char* gpedm_last_error(void) { return g_err; }
+extern "C" int gpedm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+extern "C" void gpedm_default_rprop_options(gpedm_rprop_options* o) {
+  o->delta0 = 0.1;
+  o->deltamin = 1e-6;
+  o->deltamax = 50.0;
+  o->eta_minus = 0.5;
+  o->eta_plus = 1.2;
+  o->maxiter = 200;
+  o->tol_grad = 1e-4;
+  o->tol_df = 1e-7;
+}
+
+static void free_handle(gpedm_fit_s* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->dX);
+  cudaFree(h->dY);
+  cudaFree(h->drhotab);
+  cudaFree(h->dpop);
+  cudaFree(h->bufA);
+  cudaFree(h->bufB);
+  cudaFree(h->bufC);
+  cudaFree(h->dparams);
+  cudaFree(h->dz);
+  cudaFree(h->da);
+  cudaFree(h->ddiagS);
+  cudaFree(h->dpart);
+  cudaFree(h->dlogdet);
+  cudaFree(h->dtracepart);
+  cudaFree(h->dscal);
+  cudaFree(h->dinfo);
+  if (h->hparams) cudaFreeHost(h->hparams);
+  if (h->hscal) cudaFreeHost(h->hscal);
+  if (h->hinfo) cudaFreeHost(h->hinfo);
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int gpedm_create(int device, int64_t N, int32_t d, int32_t np, const double* X, const double* Y,
+                            const int32_t* pop, const double* rhomat, gpedm_handle* out) {
+  if (!out) return set_err(GPEDM_ERR_ARG, "out handle is NULL");
+  *out = nullptr;
+  if (N < 1 || N > (1 << 20)) return set_err(GPEDM_ERR_ARG, "N=%lld out of range", (long long)N);
+  if (d < 1 || d > GPEDM_MAX_D) return set_err(GPEDM_ERR_ARG, "d=%d out of range 1..%d", d, GPEDM_MAX_D);
+  if (np < 1) return set_err(GPEDM_ERR_ARG, "np=%d must be >= 1", np);
+  if (!X || !Y || !pop) return set_err(GPEDM_ERR_ARG, "X, Y and pop must be non-NULL");
+  for (int64_t i = 0; i < N; ++i)
+    if (pop[i] < 0 || pop[i] >= np) return set_err(GPEDM_ERR_ARG, "pop[%lld]=%d outside 0..np-1", (long long)i, pop[i]);
+  int ndev = gpedm_device_count();
+  if (ndev == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available (libgpedm_b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(GPEDM_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+  CU(cudaSetDevice(device));
+  int rc = ensure_kernel_attrs(device);
+  if (rc) return rc;
+  gpedm_fit_s* h = new gpedm_fit_s();
+  h->device = device;
+  h->N = N;
+  h->nb = ceil_div((int)N, TB);
+  h->Np = h->nb * TB;
+  h->ntiles = h->nb * (h->nb + 1) / 2;
+  h->d = d;
+  h->np = np;
+  h->p = d + 3;
+  h->has_rhomat = rhomat != nullptr;
+  h->hY.assign(Y, Y + N);
+  h->hpop.assign(pop, pop + N);
+  h->single_pop = true;
+  for (int64_t i = 1; i < N; ++i)
+    if (pop[i] != pop[0]) h->single_pop = false;
+  const size_t Np = h->Np, mat = Np * Np * sizeof(double);
+#define ALLOC(ptr, bytes)                                                                         \
+  do {                                                                                            \
+    cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                         \
+    if (e_ != cudaSuccess) {                                                                      \
+      free_handle(h);                                                                             \
+      return set_err(GPEDM_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", (size_t)(bytes),       \
+                     cudaGetErrorString(e_));                                                     \
+    }                                                                                             \
+  } while (0)
+  ALLOC(h->dX, (size_t)N * d * 8);
+  ALLOC(h->dY, Np * 8);
+  ALLOC(h->dpop, (size_t)N * 4);
+  if (rhomat) ALLOC(h->drhotab, (size_t)np * np * 8);
+  ALLOC(h->bufA, mat);
+  ALLOC(h->bufB, mat);
+  ALLOC(h->bufC, mat);
+  ALLOC(h->dparams, sizeof(EvalParams));
+  ALLOC(h->dz, Np * 8);
+  ALLOC(h->da, Np * 8);
+  ALLOC(h->ddiagS, Np * 8);
+  ALLOC(h->dpart, (size_t)h->nb * Np * 8);
+  ALLOC(h->dlogdet, (size_t)h->nb * 8);
+  ALLOC(h->dtracepart, (size_t)h->ntiles * (MAXD + 3) * 8);
+  ALLOC(h->dscal, NSCAL * 8);
+  ALLOC(h->dinfo, 4);
+#undef ALLOC
+  cudaError_t e = cudaMallocHost((void**)&h->hparams, sizeof(EvalParams));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hscal, NSCAL * 8);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hinfo, 4);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  for (int i = 0; i <= GPEDM_NPHASE && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  if (e == cudaSuccess) e = cudaMemcpy(h->dX, X, (size_t)N * d * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->dY, 0, Np * 8);
+  if (e == cudaSuccess) e = cudaMemcpy(h->dY, Y, (size_t)N * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->dpop, pop, (size_t)N * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && rhomat) e = cudaMemcpy(h->drhotab, rhomat, (size_t)np * np * 8, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    free_handle(h);
+    return set_err(GPEDM_ERR_CUDA, "handle setup failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" int gpedm_destroy(gpedm_handle h) {
+  free_handle(h);
+  return 0;
+}
+extern "C" int64_t gpedm_n(gpedm_handle h) { return h ? h->N : -1; }
+extern "C" int64_t gpedm_launch_count(gpedm_handle h) { return h ? h->launches : -1; }
+extern "C" int gpedm_last_phase_ms(gpedm_handle h, float* ms) {
+  if (!h || !ms) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  memcpy(ms, h->phase_ms, sizeof(h->phase_ms));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- pipeline
+// Enqueue the device work of one evaluation on h->stream.  h->hparams must be filled.
+// stages: through z/a (need_inverse_products=false stops after z for the sequential helper).
+static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) {
+  cudaStream_t st = h->stream;
+  const int nb = h->nb, Np = h->Np, N = (int)h->N, d = h->d;
+  const size_t ld = Np;
+  CU(cudaMemcpyAsync(h->dparams, h->hparams, sizeof(EvalParams), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(h->dinfo, 0, 4, st));
+  CU(cudaEventRecord(h->ev[0], st));
+  // --- assemble Sigma (lower tiles) into bufA
+  {
+    int smem = 2 * d * TB * 8 + 2 * TB * 4;
+    assemble_sigma_kernel<<<h->ntiles, 256, smem, st>>>(h->bufA, ld, N, h->dX, h->dpop, h->drhotab, h->dparams);
+    h->launches++;
+  }
+  CU(cudaEventRecord(h->ev[1], st));
+  // --- Cholesky, right-looking over 128-wide block columns
+  for (int k = 0; k < nb; ++k) {
+    diag_potf2_inv_kernel<<<1, 256, DIAG_SMEM_BYTES, st>>>(h->bufA + (size_t)k * TB * (ld + 1), ld,
+                                                            h->bufB + (size_t)k * TB * (ld + 1), ld, k, N,
+                                                            h->dlogdet, h->dinfo);
+    h->launches++;
+    int m = nb - k - 1;
+    if (m > 0) {
+      potrf_panel_kernel<<<m, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->bufA, h->bufB, ld, k);
+      potrf_trail_kernel<<<m*(m + 1) / 2, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->bufA, ld, k, nb, k + 1, nb);
+      h->launches += 2;
+    }
+  }
+  CU(cudaEventRecord(h->ev[2], st));
+  // --- triangular inverse X = L^-1 by recursive doubling (diagonal blocks already in bufB)
+  for (int s = 1; s < nb; s *= 2) {
+    int npairs = ceil_div(nb, 2 * s);
+    int grid = npairs * s * s;
+    trtri_w_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->bufA, h->bufB, h->bufC, ld, nb, s);
+    trtri_x_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->bufB, h->bufC, ld, nb, s);
+    h->launches += 2;
+  }
+  CU(cudaEventRecord(h->ev[3], st));
+  // --- z = X Y
+  trmv_n_part_kernel<<<h->ntiles, 256, 0, st>>>(h->bufB, ld, h->dY, h->dpart, ld);
+  reduce_parts_kernel<<<ceil_div(Np, 256), 256, 0, st>>>(h->dpart, ld, nb, 0, h->dz, Np);
+  h->launches += 2;
+  if (through_z_only) {
+    CU(cudaEventRecord(h->ev[4], st));
+    CU(cudaMemcpyAsync(h->hinfo, h->dinfo, 4, cudaMemcpyDeviceToHost, st));
+    return 0;
+  }
+  // --- a = X^T z
+  trmv_t_part_kernel<<<h->ntiles, 256, 0, st>>>(h->bufB, ld, h->dz, h->dpart, ld);
+  reduce_parts_kernel<<<ceil_div(Np, 256), 256, 0, st>>>(h->dpart, ld, nb, 1, h->da, Np);
+  h->launches += 2;
+  CU(cudaEventRecord(h->ev[4], st));
+  // --- S = Sigma^-1 = X^T X (lower tiles) into bufC
+  lauum_kernel<<<h->ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->bufB, h->bufC, ld, nb);
+  h->launches++;
+  CU(cudaEventRecord(h->ev[5], st));
+  // --- gradient trace terms + scalar reductions
+  {
+    int DC = d <= 8 ? 8 : (d <= 16 ? 16 : 32);
+    int smem = (4 * d * TB + 2 * TB + 8 * (DC + 3)) * 8 + 2 * TB * 4;
+    if (DC == 8)
+      grad_trace_kernel<8><<<h->ntiles, 256, smem, st>>>(h->bufC, ld, N, h->dX, h->dpop, h->drhotab, h->da,
+                                                         h->dparams, h->dtracepart);
+    else if (DC == 16)
+      grad_trace_kernel<16><<<h->ntiles, 256, smem, st>>>(h->bufC, ld, N, h->dX, h->dpop, h->drhotab, h->da,
+                                                          h->dparams, h->dtracepart);
+    else
+      grad_trace_kernel<32><<<h->ntiles, 256, smem, st>>>(h->bufC, ld, N, h->dX, h->dpop, h->drhotab, h->da,
+                                                          h->dparams, h->dtracepart);
+    h->launches++;
+    if (full) {
+      extract_diag_kernel<<<ceil_div(N, 256), 256, 0, st>>>(h->bufC, ld, N, h->ddiagS);
+      h->launches++;
+    }
+    final_reduce_kernel<<<1, 256, 0, st>>>(h->dlogdet, nb, h->dz, h->da, h->ddiagS, N, h->dtracepart, h->ntiles,
+                                           d + 3, full ? 1 : 0, h->dscal);
+    h->launches++;
+  }
+  CU(cudaEventRecord(h->ev[6], st));
+  CU(cudaMemcpyAsync(h->hscal, h->dscal, NSCAL * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->hinfo, h->dinfo, 4, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+static int collect_phase_times(gpedm_fit_s* h) {
+  // ev: 0 start, 1 after assemble, 2 after potrf, 3 after trtri, 4 after vec, 5 after lauum, 6 after trace
+  float t;
+  CU(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+  h->phase_ms[GPEDM_PHASE_ASSEMBLE] = t;
+  CU(cudaEventElapsedTime(&t, h->ev[1], h->ev[2]));
+  h->phase_ms[GPEDM_PHASE_POTRF] = t;
+  CU(cudaEventElapsedTime(&t, h->ev[2], h->ev[3]));
+  h->phase_ms[GPEDM_PHASE_TRTRI] = t;
+  CU(cudaEventElapsedTime(&t, h->ev[3], h->ev[4]));
+  h->phase_ms[GPEDM_PHASE_VEC] = t;
+  CU(cudaEventElapsedTime(&t, h->ev[4], h->ev[5]));
+  h->phase_ms[GPEDM_PHASE_LAUUM] = t;
+  CU(cudaEventElapsedTime(&t, h->ev[5], h->ev[6]));
+  h->phase_ms[GPEDM_PHASE_TRACE] = t;
+  CU(cudaEventElapsedTime(&t, h->ev[0], h->ev[6]));
+  h->phase_ms[GPEDM_PHASE_TOTAL] = t;
+  return 0;
+}
+
+// Host-side scalar head of getlikegrad (reference R/GPfunctions.R:590-630).
+struct HostPars {
+  double phi[MAXD], ve, sigma2, rho;
+  double parst[GPEDM_MAX_P], dpars[GPEDM_MAX_P], dlp[GPEDM_MAX_P];
+  double lp;
+  bool rho_is_fixed;
+  bool fixed[GPEDM_MAX_P];
+};
+
+static void host_transform(const gpedm_fit_s* h, const double* parst_in, double modeprior, const double* fixedpars,
+                           double rhofixed, HostPars& o) {
+  const int d = h->d;
+  for (int i = 0; i < d + 3; ++i) o.parst[i] = parst_in[i];
+  for (int i = 0; i < d; ++i) o.phi[i] = exp(o.parst[i]);
+  o.ve = (VEMAX - VEMIN) / (1 + exp(-o.parst[d])) + VEMIN;
+  o.sigma2 = (SIGMA2MAX - SIGMA2MIN) / (1 + exp(-o.parst[d + 1])) + SIGMA2MIN;
+  o.rho = (RHOMAX - RHOMIN) / (1 + exp(-o.parst[d + 2])) + RHOMIN;
+  // :600-602  one population or rhomatrix  => rho fixed to 0.5
+  if (h->single_pop || h->has_rhomat) rhofixed = 0.5;
+  o.rho_is_fixed = !isnan(rhofixed);
+  if (o.rho_is_fixed) {
+    o.rho = rhofixed;
+    o.parst[d + 2] = logit3(o.rho, RHOMIN, RHOMAX);
+  }
+  for (int i = 0; i < d + 3; ++i) o.fixed[i] = false;
+  if (fixedpars) {
+    bool anyphi = false;
+    for (int i = 0; i < d; ++i)
+      if (!isnan(fixedpars[i])) {
+        o.phi[i] = fixedpars[i];
+        o.fixed[i] = true;
+        anyphi = true;
+      }
+    if (anyphi)
+      for (int i = 0; i < d; ++i) o.parst[i] = log(o.phi[i]);  // :611
+    if (!isnan(fixedpars[d])) {
+      o.ve = fixedpars[d];
+      o.parst[d] = logit3(o.ve, VEMIN, VEMAX);
+      o.fixed[d] = true;
+    }
+    if (!isnan(fixedpars[d + 1])) {
+      o.sigma2 = fixedpars[d + 1];
+      o.parst[d + 1] = logit3(o.sigma2, SIGMA2MIN, SIGMA2MAX);
+      o.fixed[d + 1] = true;
+    }
+  }
+  for (int i = 0; i < d; ++i) o.dpars[i] = o.phi[i];
+  o.dpars[d] = (o.ve - VEMIN) * (1 - (o.ve - VEMIN) / (VEMAX - VEMIN));
+  o.dpars[d + 1] = (o.sigma2 - SIGMA2MIN) * (1 - (o.sigma2 - SIGMA2MIN) / (SIGMA2MAX - SIGMA2MIN));
+  o.dpars[d + 2] = (o.rho - RHOMIN) * (1 - (o.rho - RHOMIN) / (RHOMAX - RHOMIN));
+  // getpriors :752-777
+  const double lam = pow(pow(2.0, modeprior - 1), 2) * M_PI / 2;
+  double sphi2 = 0;
+  for (int i = 0; i < d; ++i) sphi2 += o.phi[i] * o.phi[i];
+  double lp_phi = -0.5 * sphi2 / lam;
+  for (int i = 0; i < d; ++i) o.dlp[i] = -o.phi[i] / lam;
+  double lp_s2 = log(o.sigma2 / SIGMA2MAX) + log(1 - o.sigma2 / SIGMA2MAX);
+  o.dlp[d + 1] = 1.0 / o.sigma2 - 1.0 / (SIGMA2MAX - o.sigma2);
+  double lp_ve = log(o.ve / VEMAX) + log(1 - o.ve / VEMAX);
+  o.dlp[d] = 1.0 / o.ve - 1.0 / (VEMAX - o.ve);
+  double lp_rho = log(o.rho) + log(1 - o.rho);
+  o.dlp[d + 2] = 1.0 / o.rho - 1.0 / (1 - o.rho);
+  o.lp = lp_phi + lp_ve + lp_s2 + lp_rho;
+}
+
+static void fill_params(gpedm_fit_s* h, const HostPars& hp) {
+  EvalParams* P = h->hparams;
+  memset(P, 0, sizeof(*P));
+  for (int i = 0; i < h->d; ++i) {
+    P->phi[i] = hp.phi[i];
+    P->sqphi[i] = sqrt(hp.phi[i]);
+  }
+  P->ve = hp.ve;
+  P->sigma2 = hp.sigma2;
+  P->rho = hp.rho;
+  P->d = h->d;
+  P->np = h->np;
+  P->use_rhotab = h->has_rhomat ? 1 : 0;
+}
+
+static void finish_result(const gpedm_fit_s* h, const HostPars& hp, bool full, gpedm_result* out) {
+  const int d = h->d;
+  const double* sc = h->hscal;
+  double logdet = sc[0], SS = sc[1];
+  double like = -0.5 * SS - logdet;  // :648
+  double dl[GPEDM_MAX_P];
+  for (int i = 0; i < d; ++i) dl[i] = hp.fixed[i] ? 0.0 : 0.5 * sc[8 + i];  // :659-665 (note the extra 0.5)
+  dl[d] = hp.fixed[d] ? 0.0 : sc[8 + d];                                    // :688-692
+  dl[d + 1] = hp.fixed[d + 1] ? 0.0 : sc[8 + d + 1];                        // :694-698
+  dl[d + 2] = hp.rho_is_fixed ? 0.0 : sc[8 + d + 2];                        // :701-709
+  memset(out, 0, sizeof(*out));
+  out->p = d + 3;
+  double g2 = 0;
+  for (int i = 0; i < d + 3; ++i) {
+    double J = dl[i] + hp.dlp[i];
+    out->grad[i] = -J * hp.dpars[i];  // :719-720
+    g2 += out->grad[i] * out->grad[i];
+    out->parst[i] = hp.parst[i];
+  }
+  for (int i = 0; i < d; ++i) out->pars[i] = hp.phi[i];
+  out->pars[d] = hp.ve;
+  out->pars[d + 1] = hp.sigma2;
+  out->pars[d + 2] = hp.rho;
+  out->gradnorm = sqrt(g2);
+  out->lp = hp.lp;
+  out->like = like;
+  out->nllpost = -(like + hp.lp);  // :721
+  out->logdet = logdet;
+  out->SS = SS;
+  if (full) {
+    out->lnL_LOO = 0.5 * sc[2] - 0.5 * sc[3];            // :742
+    out->df = (double)h->N - hp.ve * sc[4];              // :743 via tr(Cd S) = N - ve tr(S)
+  } else {
+    out->lnL_LOO = NAN;
+    out->df = NAN;
+  }
+}
+
+static int eval_internal(gpedm_fit_s* h, const double* parst, double modeprior, const double* fixedpars,
+                         double rhofixed, bool full, gpedm_result* out) {
+  CU(cudaSetDevice(h->device));
+  HostPars hp;
+  host_transform(h, parst, modeprior, fixedpars, rhofixed, hp);
+  fill_params(h, hp);
+  h->have_full = false;
+  int rc = enqueue_eval(h, full);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  rc = collect_phase_times(h);
+  if (rc) return rc;
+  finish_result(h, hp, full, out);
+  out->nevals = 1;
+  int info = *h->hinfo;
+  out->status = info;
+  if (info > 0)
+    return set_err(info, "covariance matrix not positive definite: non-positive pivot at row %d", info);
+  if (full) {
+    h->have_full = true;
+    h->cur_ve = hp.ve;
+    h->cur_sigma2 = hp.sigma2;
+    h->cur_rho = hp.rho;
+  }
+  return 0;
+}
+
+extern "C" int gpedm_likegrad(gpedm_handle h, const double* parst, double modeprior, const double* fixedpars,
+                              double rhofixed, int full, gpedm_result* out) {
+  if (!h || !parst || !out) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  return eval_internal(h, parst, modeprior, fixedpars, rhofixed, full != 0, out);
+}
+
+static inline double sgn(double x) { return (x > 0) - (x < 0); }
+
+extern "C" int gpedm_fit_rprop(gpedm_handle h, const double* initparst, double modeprior, const double* fixedpars,
+                               double rhofixed, const gpedm_rprop_options* opts, gpedm_result* out) {
+  if (!h || !initparst || !out) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  gpedm_rprop_options o;
+  if (opts)
+    o = *opts;
+  else
+    gpedm_default_rprop_options(&o);
+  const int p = h->p;
+  const double eta_minus = o.eta_minus - 1, eta_plus = o.eta_plus - 1;  // :534-535
+  double pa[GPEDM_MAX_P], del[GPEDM_MAX_P], grad[GPEDM_MAX_P], panew[GPEDM_MAX_P];
+  gpedm_result r;
+  int rc = eval_internal(h, initparst, modeprior, fixedpars, rhofixed, false, &r);  // :545
+  if (rc) {
+    *out = r;
+    return rc;
+  }
+  int nevals = 1;
+  double nll = r.nllpost;
+  for (int i = 0; i < p; ++i) {
+    grad[i] = r.grad[i];
+    pa[i] = initparst[i];
+    del[i] = o.delta0;
+  }
+  double s = r.gradnorm;
+  int iter = 0;
+  double df = 10;
+  while (s > o.tol_grad && iter < o.maxiter && df > o.tol_df) {  // :556
+    for (int i = 0; i < p; ++i) panew[i] = pa[i] - sgn(grad[i]) * del[i];  // :559
+    rc = eval_internal(h, panew, modeprior, fixedpars, rhofixed, false, &r);
+    ++nevals;
+    if (rc) {
+      *out = r;
+      out->iter = iter;
+      out->nevals = nevals;
+      return rc;
+    }
+    s = r.gradnorm;
+    df = fabs(r.nllpost / nll - 1);  // :565
+    for (int i = 0; i < p; ++i) {
+      double gc = grad[i] * r.grad[i];
+      double tdel = del[i] * (1 + eta_plus * (gc > 0) + eta_minus * (gc < 0));  // :569
+      del[i] = tdel < o.deltamin ? o.deltamin : (tdel > o.deltamax ? o.deltamax : tdel);
+      pa[i] = panew[i];
+      grad[i] = r.grad[i];
+    }
+    nll = r.nllpost;
+    ++iter;
+  }
+  rc = eval_internal(h, pa, modeprior, fixedpars, rhofixed, true, &r);  // :580
+  ++nevals;
+  *out = r;
+  out->iter = iter;
+  out->nevals = nevals;
+  return rc;
+}
+
+// ------------------------------------------------------------------------------- exports
+extern "C" int gpedm_get_vector(gpedm_handle h, int which, double* outv) {
+  if (!h || !outv) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident (call gpedm_likegrad(full=1) or gpedm_fit_rprop first)");
+  CU(cudaSetDevice(h->device));
+  const int64_t N = h->N;
+  std::vector<double> a(N), ds(N);
+  CU(cudaMemcpy(a.data(), h->da, N * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(ds.data(), h->ddiagS, N * 8, cudaMemcpyDeviceToHost));
+  const double ve = h->cur_ve;
+  for (int64_t i = 0; i < N; ++i) {
+    switch (which) {
+      case GPEDM_VEC_MEAN: outv[i] = h->hY[i] - ve * a[i]; break;            // Cd a = Y - ve a
+      case GPEDM_VEC_VAR: outv[i] = ve - ve * ve * ds[i]; break;             // diag(Cd - Cd S Cd)
+      case GPEDM_VEC_ALPHA: outv[i] = a[i]; break;
+      case GPEDM_VEC_DIAG_IKVS: outv[i] = ds[i]; break;
+      case GPEDM_VEC_LOO_MEAN: outv[i] = h->hY[i] - a[i] / ds[i]; break;
+      case GPEDM_VEC_LOO_VAR: outv[i] = 1.0 / ds[i] - ve; break;
+      default: return set_err(GPEDM_ERR_ARG, "unknown vector id %d", which);
+    }
+  }
+  return 0;
+}
+
+static int launch_cov_rect(gpedm_fit_s* h, double* out, size_t ldo, int rows_alloc, int cols_alloc, int transpose,
+                           int M, const double* dX2, const int* dpop2, int add_ve) {
+  int smem = 2 * h->d * TB * 8 + 2 * TB * 4;
+  dim3 grid(ceil_div(rows_alloc, TB), ceil_div(cols_alloc, TB));
+  cov_rect_kernel<<<grid, 256, smem, h->stream>>>(out, ldo, rows_alloc, cols_alloc, transpose, (int)h->N, h->dX,
+                                                  h->dpop, M, dX2, dpop2, h->drhotab, h->dparams, add_ve);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gpedm_get_matrix(gpedm_handle h, int which, double* outm) {
+  if (!h || !outm) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
+  CU(cudaSetDevice(h->device));
+  const int64_t N = h->N;
+  const size_t ld = h->Np;
+  if (which == GPEDM_MAT_CD || which == GPEDM_MAT_SIGMA || which == GPEDM_MAT_POPSAME) {
+    double* tmp = nullptr;
+    CU(cudaMalloc((void**)&tmp, (size_t)N * N * 8));
+    int rc = 0;
+    if (which == GPEDM_MAT_POPSAME) {
+      size_t tot = (size_t)N * N;
+      popsame_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(tmp, (int)N, h->dpop);
+      h->launches++;
+    } else {
+      rc = launch_cov_rect(h, tmp, (size_t)N, (int)N, (int)N, 0, (int)N, h->dX, h->dpop,
+                           which == GPEDM_MAT_SIGMA ? 1 : 0);
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(outm, tmp, (size_t)N * N * 8, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    if (rc) return rc;
+    if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "export failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  const double* src = which == GPEDM_MAT_IKVS ? h->bufC : (which == GPEDM_MAT_L ? h->bufA : (which == GPEDM_MAT_LINV ? h->bufB : nullptr));
+  if (!src) return set_err(GPEDM_ERR_ARG, "unknown matrix id %d", which);
+  CU(cudaMemcpy2D(outm, (size_t)N * 8, src, ld * 8, (size_t)N * 8, (size_t)N, cudaMemcpyDeviceToHost));
+  for (int64_t j = 0; j < N; ++j)
+    for (int64_t i = 0; i < j; ++i)
+      outm[i + j * N] = which == GPEDM_MAT_IKVS ? outm[j + i * N] : 0.0;
+  return 0;
+}
+
+extern "C" int gpedm_getcov(int device, int32_t d, const double* phi, double sigma2, double rho, int64_t N,
+                            const double* X, const int32_t* pop, int64_t M, const double* X2, const int32_t* pop2,
+                            int32_t np, const double* rhomat, double* Cd_out) {
+  if (!phi || !X || !pop || !X2 || !pop2 || !Cd_out) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  if (d < 1 || d > GPEDM_MAX_D || N < 1 || M < 1) return set_err(GPEDM_ERR_ARG, "bad sizes");
+  int ndev = gpedm_device_count();
+  if (ndev == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available (libgpedm_b200 has no CPU fallback)");
+  CU(cudaSetDevice(device));
+  int rc = ensure_kernel_attrs(device);
+  if (rc) return rc;
+  double *dX = nullptr, *dX2 = nullptr, *dout = nullptr, *drt = nullptr;
+  int *dp = nullptr, *dp2 = nullptr;
+  EvalParams* dP = nullptr;
+  EvalParams P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < d; ++i) {
+    P.phi[i] = phi[i];
+    P.sqphi[i] = sqrt(phi[i]);
+  }
+  P.sigma2 = sigma2;
+  P.rho = rho;
+  P.d = d;
+  P.np = np;
+  P.use_rhotab = rhomat ? 1 : 0;
+  cudaError_t e = cudaMalloc((void**)&dX, (size_t)N * d * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dX2, (size_t)M * d * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dout, (size_t)M * N * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dp, (size_t)N * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dp2, (size_t)M * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dP, sizeof(EvalParams));
+  if (e == cudaSuccess && rhomat) e = cudaMalloc((void**)&drt, (size_t)np * np * 8);
+  if (e == cudaSuccess) e = cudaMemcpy(dX, X, (size_t)N * d * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dX2, X2, (size_t)M * d * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dp, pop, (size_t)N * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dp2, pop2, (size_t)M * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dP, &P, sizeof(P), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && rhomat) e = cudaMemcpy(drt, rhomat, (size_t)np * np * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    int smem = 2 * d * TB * 8 + 2 * TB * 4;
+    dim3 grid(ceil_div((int)M, TB), ceil_div((int)N, TB));
+    cov_rect_kernel<<<grid, 256, smem>>>(dout, (size_t)M, (int)M, (int)N, 0, (int)N, dX, dp, (int)M, dX2, dp2, drt,
+                                         dP, 0);
+    e = cudaDeviceSynchronize();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(Cd_out, dout, (size_t)M * N * 8, cudaMemcpyDeviceToHost);
+  cudaFree(dX);
+  cudaFree(dX2);
+  cudaFree(dout);
+  cudaFree(dp);
+  cudaFree(dp2);
+  cudaFree(dP);
+  cudaFree(drt);
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "gpedm_getcov failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- prediction
+extern "C" int gpedm_predict_new(gpedm_handle h, int64_t M, const double* Xnew, const int32_t* popnew, double* mean,
+                                 double* var, double* gpgrad) {
+  if (!h || !Xnew || !popnew || !mean || !var) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  if (M < 1) return set_err(GPEDM_ERR_ARG, "M must be >= 1");
+  if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
+  for (int64_t i = 0; i < M; ++i)
+    if (popnew[i] < 0 || popnew[i] >= h->np) return set_err(GPEDM_ERR_ARG, "popnew[%lld] outside 0..np-1", (long long)i);
+  CU(cudaSetDevice(h->device));
+  const int d = h->d;
+  const int64_t CH = 4096;  // new points per chunk
+  const int64_t chunk_max = std::min<int64_t>(M, CH);
+  const int Mp_max = ceil_div((int)chunk_max, TB) * TB;
+  const size_t ldv = h->Np;
+  double *dV = nullptr, *dU = nullptr, *dXn = nullptr, *dmean = nullptr, *dvar = nullptr, *dgrad = nullptr;
+  int* dpn = nullptr;
+  cudaError_t e = cudaMalloc((void**)&dV, ldv * Mp_max * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dU, ldv * Mp_max * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dXn, (size_t)chunk_max * d * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dpn, (size_t)chunk_max * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dmean, (size_t)chunk_max * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dvar, (size_t)chunk_max * 8);
+  if (e == cudaSuccess && gpgrad) e = cudaMalloc((void**)&dgrad, (size_t)chunk_max * d * 8);
+  int rc = 0;
+  std::vector<double> xn, gtmp;
+  for (int64_t m0 = 0; m0 < M && e == cudaSuccess && rc == 0; m0 += CH) {
+    const int64_t mc = std::min<int64_t>(CH, M - m0);
+    const int Mp = ceil_div((int)mc, TB) * TB;
+    xn.resize((size_t)mc * d);
+    for (int k = 0; k < d; ++k)
+      for (int64_t i = 0; i < mc; ++i) xn[i + (size_t)k * mc] = Xnew[m0 + i + (size_t)k * M];
+    e = cudaMemcpyAsync(dXn, xn.data(), (size_t)mc * d * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dpn, popnew + m0, (size_t)mc * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) break;
+    rc = launch_cov_rect(h, dV, ldv, h->Np, Mp, 1, (int)mc, dXn, dpn, 0);
+    if (rc) break;
+    dim3 grid(h->nb, Mp / TB);
+    tri_apply_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->bufB, ldv, dV, dU, ldv, h->nb);
+    predict_reduce_kernel<<<(unsigned)mc, 256, 0, h->stream>>>(dV, dU, ldv, (int)h->N, (int)mc, h->da, h->dX, dXn,
+                                                                h->dparams, dmean, dvar, dgrad);
+    h->launches += 2;
+    e = cudaMemcpyAsync(mean + m0, dmean, (size_t)mc * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(var + m0, dvar, (size_t)mc * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && gpgrad) {
+      gtmp.resize((size_t)mc * d);
+      e = cudaMemcpyAsync(gtmp.data(), dgrad, (size_t)mc * d * 8, cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess && gpgrad)
+      for (int k = 0; k < d; ++k)
+        for (int64_t i = 0; i < mc; ++i) gpgrad[m0 + i + (size_t)k * M] = gtmp[i + (size_t)k * mc];
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(dV);
+  cudaFree(dU);
+  cudaFree(dXn);
+  cudaFree(dpn);
+  cudaFree(dmean);
+  cudaFree(dvar);
+  cudaFree(dgrad);
+  if (rc) return rc;
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "gpedm_predict_new failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// Small dense SPD solve on the host for the block leave-out formulas (blocks are the size of the
+// excluded set: 2*exclradius+1 rows, or the rows sharing a time value).
+static bool host_chol(std::vector<double>& A, int n) {
+  for (int j = 0; j < n; ++j) {
+    double s = A[j + (size_t)j * n];
+    for (int k = 0; k < j; ++k) s -= A[j + (size_t)k * n] * A[j + (size_t)k * n];
+    if (!(s > 0)) return false;
+    double dj = sqrt(s);
+    A[j + (size_t)j * n] = dj;
+    for (int i = j + 1; i < n; ++i) {
+      double t = A[i + (size_t)j * n];
+      for (int k = 0; k < j; ++k) t -= A[i + (size_t)k * n] * A[j + (size_t)k * n];
+      A[i + (size_t)j * n] = t / dj;
+    }
+  }
+  return true;
+}
+static void host_chol_solve(const std::vector<double>& L, int n, double* b) {
+  for (int i = 0; i < n; ++i) {
+    double t = b[i];
+    for (int k = 0; k < i; ++k) t -= L[i + (size_t)k * n] * b[k];
+    b[i] = t / L[i + (size_t)i * n];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double t = b[i];
+    for (int k = i + 1; k < n; ++k) t -= L[k + (size_t)i * n] * b[k];
+    b[i] = t / L[i + (size_t)i * n];
+  }
+}
+
+// Shared implementation of loo / lto given the groups (excluded sets) and focal rows.
+//   members/goff : concatenated excluded-row indices per group;  focal[f], fgroup[f].
+static int leaveout_core(gpedm_fit_s* h, const std::vector<int>& members, const std::vector<int>& goff,
+                         const std::vector<int>& focal, const std::vector<int>& fgroup, double* mean, double* var,
+                         double* gpgrad) {
+  CU(cudaSetDevice(h->device));
+  const int64_t N = h->N;
+  const int ng = (int)goff.size() - 1, nf = (int)focal.size();
+  std::vector<double> a(N), ds(N);
+  CU(cudaMemcpy(a.data(), h->da, N * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(ds.data(), h->ddiagS, N * 8, cudaMemcpyDeviceToHost));
+  std::vector<long long> boff(ng + 1, 0);
+  for (int g = 0; g < ng; ++g) {
+    long long nbk = goff[g + 1] - goff[g];
+    boff[g + 1] = boff[g] + nbk * nbk;
+  }
+  std::vector<double> blocks((size_t)boff[ng]);
+  int *didx = nullptr, *dgoff = nullptr;
+  long long* dboff = nullptr;
+  double* dblocks = nullptr;
+  cudaError_t e = cudaMalloc((void**)&didx, std::max<size_t>(1, members.size()) * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dgoff, (size_t)(ng + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dboff, (size_t)(ng + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dblocks, std::max<size_t>(1, blocks.size()) * 8);
+  if (e == cudaSuccess) e = cudaMemcpy(didx, members.data(), members.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dgoff, goff.data(), (size_t)(ng + 1) * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dboff, boff.data(), (size_t)(ng + 1) * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && ng > 0) {
+    gather_blocks_kernel<<<ng, 128, 0, h->stream>>>(h->bufC, (size_t)h->Np, didx, dgoff, dboff, ng, dblocks);
+    h->launches++;
+    e = cudaStreamSynchronize(h->stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(blocks.data(), dblocks, blocks.size() * 8, cudaMemcpyDeviceToHost);
+  // per-group solves: u = S_BB^-1 a_B, and diag(S_BB^-1)
+  std::vector<double> u(members.size()), dinv(members.size());
+  int bad = 0;
+  if (e == cudaSuccess) {
+    std::vector<double> Lb, rhs;
+    for (int g = 0; g < ng; ++g) {
+      int b0 = goff[g], nbk = goff[g + 1] - b0;
+      if (nbk == 0) continue;
+      Lb.assign(blocks.begin() + boff[g], blocks.begin() + boff[g + 1]);
+      if (!host_chol(Lb, nbk)) {
+        bad = g + 1;
+        break;
+      }
+      rhs.resize(nbk);
+      for (int r = 0; r < nbk; ++r) rhs[r] = a[members[b0 + r]];
+      host_chol_solve(Lb, nbk, rhs.data());
+      for (int r = 0; r < nbk; ++r) u[b0 + r] = rhs[r];
+      // diag of inverse: column-wise forward solves  ||L^-1 e_r||^2
+      for (int r = 0; r < nbk; ++r) {
+        std::vector<double> w(nbk, 0.0);
+        w[r] = 1.0;
+        double acc = 0.0;
+        for (int i = r; i < nbk; ++i) {
+          double t = w[i];
+          for (int k = r; k < i; ++k) t -= Lb[i + (size_t)k * nbk] * w[k];
+          w[i] = t / Lb[i + (size_t)i * nbk];
+          acc += w[i] * w[i];
+        }
+        dinv[b0 + r] = acc;
+      }
+    }
+  }
+  if (e == cudaSuccess && !bad) {
+    for (int f = 0; f < nf; ++f) {
+      int g = fgroup[f], b0 = goff[g], nbk = goff[g + 1] - b0;
+      int pos = -1;
+      for (int r = 0; r < nbk; ++r)
+        if (members[b0 + r] == focal[f]) pos = r;
+      if (pos < 0) {
+        mean[f] = NAN;
+        var[f] = NAN;
+        continue;
+      }
+      mean[f] = h->hY[focal[f]] - u[b0 + pos];
+      var[f] = dinv[b0 + pos] - h->cur_ve;
+    }
+    if (gpgrad && nf > 0) {
+      int *dfocal = nullptr, *dfg = nullptr;
+      double *du = nullptr, *dg = nullptr;
+      e = cudaMalloc((void**)&dfocal, (size_t)nf * 4);
+      if (e == cudaSuccess) e = cudaMalloc((void**)&dfg, (size_t)nf * 4);
+      if (e == cudaSuccess) e = cudaMalloc((void**)&du, std::max<size_t>(1, u.size()) * 8);
+      if (e == cudaSuccess) e = cudaMalloc((void**)&dg, (size_t)nf * h->d * 8);
+      if (e == cudaSuccess) e = cudaMemcpy(dfocal, focal.data(), (size_t)nf * 4, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMemcpy(dfg, fgroup.data(), (size_t)nf * 4, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMemcpy(du, u.data(), u.size() * 8, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) {
+        loo_gpgrad_kernel<<<nf, 256, 0, h->stream>>>(h->bufC, (size_t)h->Np, (int)N, h->dX, h->dpop, h->drhotab, h->da,
+                                                     h->dparams, dfocal, dfg, didx, dgoff, du, nf, dg);
+        h->launches++;
+        e = cudaStreamSynchronize(h->stream);
+      }
+      if (e == cudaSuccess) e = cudaMemcpy(gpgrad, dg, (size_t)nf * h->d * 8, cudaMemcpyDeviceToHost);
+      cudaFree(dfocal);
+      cudaFree(dfg);
+      cudaFree(du);
+      cudaFree(dg);
+    }
+  }
+  cudaFree(didx);
+  cudaFree(dgoff);
+  cudaFree(dboff);
+  cudaFree(dblocks);
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "leave-out prediction failed: %s", cudaGetErrorString(e));
+  if (bad) return set_err(GPEDM_ERR_STATE, "leave-out block %d of Sigma^-1 is not positive definite", bad);
+  return 0;
+}
+
+extern "C" int gpedm_predict_loo(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary,
+                                 double* mean, double* var, double* gpgrad) {
+  if (!h || !mean || !var) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
+  if (exclradius < 0) return set_err(GPEDM_ERR_ARG, "exclradius must be >= 0");
+  const int N = (int)h->N;
+  int nd = 0;
+  for (int i = 0; i < N; ++i) nd += primary ? (primary[i] != 0) : 1;
+  // reference :1061, :1067 - primary rows are assumed to come first
+  for (int i = 0; i < nd; ++i)
+    if (primary && !primary[i]) return set_err(GPEDM_ERR_ARG, "primary rows must precede augmentation rows");
+  if (nd < N && !time) return set_err(GPEDM_ERR_ARG, "time is required when augmentation rows are present");
+  std::vector<int> members, goff(1, 0), focal(nd), fgroup(nd);
+  for (int i = 0; i < nd; ++i) {
+    size_t start = members.size();
+    for (int j = i - exclradius; j <= i + exclradius; ++j)  // :1069-1070
+      if (j >= 0 && j < N && h->hpop[j] == h->hpop[i]) members.push_back(j);
+    size_t nex = members.size();
+    for (int q = nd; q < N; ++q) {  // :1072 duplicates among augmentation rows
+      bool dup = false;
+      for (size_t e = start; e < nex && !dup; ++e)
+        dup = (h->hpop[q] == h->hpop[members[e]]) && (time[q] == time[members[e]]);
+      if (dup && std::find(members.begin() + start, members.end(), q) == members.end()) members.push_back(q);
+    }
+    goff.push_back((int)members.size());
+    focal[i] = i;
+    fgroup[i] = i;
+  }
+  return leaveout_core(h, members, goff, focal, fgroup, mean, var, gpgrad);
+}
+
+extern "C" int gpedm_predict_lto(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary,
+                                 double* mean, double* var, double* gpgrad) {
+  if (!h || !mean || !var || !time) return set_err(GPEDM_ERR_ARG, "NULL argument (time is required)");
+  if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
+  if (exclradius < 0) return set_err(GPEDM_ERR_ARG, "exclradius must be >= 0");
+  const int N = (int)h->N;
+  int nd = 0;
+  for (int i = 0; i < N; ++i) nd += primary ? (primary[i] != 0) : 1;
+  for (int i = 0; i < nd; ++i)
+    if (primary && !primary[i]) return set_err(GPEDM_ERR_ARG, "primary rows must precede augmentation rows");
+  // timevals = unique(Time) in order of first appearance (:1142)
+  std::vector<double> timevals;
+  std::vector<int> tcode(N);
+  for (int i = 0; i < N; ++i) {
+    int c = -1;
+    for (size_t q = 0; q < timevals.size(); ++q)
+      if (timevals[q] == time[i]) {
+        c = (int)q;
+        break;
+      }
+    if (c < 0) {
+      c = (int)timevals.size();
+      timevals.push_back(time[i]);
+    }
+    tcode[i] = c;
+  }
+  const int nt = (int)timevals.size();
+  std::vector<int> members, goff(1, 0), focal, fgroup;
+  for (int i = 0; i < nd; ++i) {
+    mean[i] = NAN;
+    var[i] = NAN;
+  }
+  std::vector<int> fpos;
+  for (int t = 0; t < nt; ++t) {
+    int lo = std::max(0, t - exclradius), hi = std::min(nt - 1, t + exclradius);  // :1155-1156
+    for (int j = 0; j < N; ++j)
+      if (tcode[j] >= lo && tcode[j] <= hi) members.push_back(j);  // complement of `train`, :1158
+    goff.push_back((int)members.size());
+    for (int j = 0; j < nd; ++j)
+      if (tcode[j] == t) {  // :1157 focal rows among primary
+        focal.push_back(j);
+        fgroup.push_back(t);
+        fpos.push_back(j);
+      }
+  }
+  const int nf = (int)focal.size();
+  std::vector<double> m(nf), v(nf), g;
+  if (gpgrad) g.resize((size_t)nf * h->d);
+  int rc = leaveout_core(h, members, goff, focal, fgroup, m.data(), v.data(), gpgrad ? g.data() : nullptr);
+  if (rc) return rc;
+  for (int f = 0; f < nf; ++f) {
+    mean[fpos[f]] = m[f];
+    var[fpos[f]] = v[f];
+    if (gpgrad)
+      for (int k = 0; k < h->d; ++k) gpgrad[fpos[f] + (size_t)k * nd] = g[f + (size_t)k * nf];
+  }
+  return 0;
+}
+
+extern "C" int gpedm_predict_sequential(gpedm_handle h, const double* time, double* ymean, double* ysd2) {
+  if (!h || !time || !ymean || !ysd2) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
+  CU(cudaSetDevice(h->device));
+  const int N = (int)h->N, d = h->d;
+  // time-major stable ordering by order of first appearance of each time value (:1201)
+  std::vector<double> timevals;
+  std::vector<int> tcode(N);
+  for (int i = 0; i < N; ++i) {
+    int c = -1;
+    for (size_t q = 0; q < timevals.size(); ++q)
+      if (timevals[q] == time[i]) {
+        c = (int)q;
+        break;
+      }
+    if (c < 0) {
+      c = (int)timevals.size();
+      timevals.push_back(time[i]);
+    }
+    tcode[i] = c;
+  }
+  std::vector<int> perm(N);
+  for (int i = 0; i < N; ++i) perm[i] = i;
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return tcode[a] < tcode[b]; });
+  std::vector<double> Xh((size_t)N * d), Xp((size_t)N * d), Yp(N);
+  std::vector<int> popp(N), bstart(N);
+  CU(cudaMemcpy(Xh.data(), h->dX, (size_t)N * d * 8, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < N; ++r) {
+    int s = perm[r];
+    Yp[r] = h->hY[s];
+    popp[r] = h->hpop[s];
+    for (int k = 0; k < d; ++k) Xp[r + (size_t)k * N] = Xh[s + (size_t)k * N];
+  }
+  for (int r = 0; r < N; ++r) bstart[r] = (r > 0 && tcode[perm[r]] == tcode[perm[r - 1]]) ? bstart[r - 1] : r;
+  std::vector<double> rhomat;
+  if (h->has_rhomat) {
+    rhomat.resize((size_t)h->np * h->np);
+    CU(cudaMemcpy(rhomat.data(), h->drhotab, rhomat.size() * 8, cudaMemcpyDeviceToHost));
+  }
+  gpedm_handle t = nullptr;
+  int rc = gpedm_create(h->device, N, d, h->np, Xp.data(), Yp.data(), popp.data(), h->has_rhomat ? rhomat.data() : nullptr, &t);
+  if (rc) return rc;
+  *t->hparams = *h->hparams;
+  rc = enqueue_eval(t, false, true);
+  int* dbs = nullptr;
+  double *dm = nullptr, *ds = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (!rc) {
+    e = cudaMalloc((void**)&dbs, (size_t)N * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dm, (size_t)N * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ds, (size_t)N * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dbs, bstart.data(), (size_t)N * 4, cudaMemcpyHostToDevice, t->stream);
+    if (e == cudaSuccess) {
+      sequential_kernel<<<ceil_div(N, 8), 256, 0, t->stream>>>(t->bufA, (size_t)t->Np, N, t->dz, dbs, dm, ds);
+      t->launches++;
+      e = cudaStreamSynchronize(t->stream);
+    }
+  }
+  std::vector<double> mp(N), sp(N);
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(mp.data(), dm, (size_t)N * 8, cudaMemcpyDeviceToHost);
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(sp.data(), ds, (size_t)N * 8, cudaMemcpyDeviceToHost);
+  int info = rc ? 0 : *t->hinfo;
+  h->launches += t->launches;
+  cudaFree(dbs);
+  cudaFree(dm);
+  cudaFree(ds);
+  gpedm_destroy(t);
+  if (rc) return rc;
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "sequential prediction failed: %s", cudaGetErrorString(e));
+  if (info > 0) return set_err(info, "time-ordered covariance matrix not positive definite at row %d", info);
+  const double s2ve = h->cur_sigma2 + h->cur_ve;
+  for (int r = 0; r < N; ++r) {
+    int s = perm[r];
+    if (tcode[s] == 0) {  // first time value: never updated (:1215-1216, :1236)
+      ymean[s] = 0.0;
+      ysd2[s] = s2ve;
+    } else {
+      ymean[s] = mp[r];
+      ysd2[s] = sp[r];
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- batched fits
+struct NcclApi {
+  void* lib = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static bool load_nccl(NcclApi& n) {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (n.lib) break;
+  }
+  if (!n.lib) return false;
+  n.CommInitAll = (int (*)(void**, int, const int*))dlsym(n.lib, "ncclCommInitAll");
+  n.CommDestroy = (int (*)(void*))dlsym(n.lib, "ncclCommDestroy");
+  n.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(n.lib, "ncclAllGather");
+  n.GroupStart = (int (*)())dlsym(n.lib, "ncclGroupStart");
+  n.GroupEnd = (int (*)())dlsym(n.lib, "ncclGroupEnd");
+  n.GetErrorString = (const char* (*)(int))dlsym(n.lib, "ncclGetErrorString");
+  return n.CommInitAll && n.CommDestroy && n.AllGather && n.GroupStart && n.GroupEnd;
+}
+
+// Fixed-width record exchanged by the final all-gather.
+struct BatchRecord {
+  int32_t fit_index;
+  int32_t valid;
+  gpedm_result res;
+};
+
+static int run_one_fit(int device, const gpedm_fit_desc& ds, const gpedm_rprop_options* opts, gpedm_result* res) {
+  gpedm_handle h = nullptr;
+  int rc = gpedm_create(device, ds.N, ds.d, ds.np, ds.X, ds.Y, ds.pop, ds.rhomat, &h);
+  if (rc) {
+    memset(res, 0, sizeof(*res));
+    res->status = rc;
+    return rc;
+  }
+  rc = gpedm_fit_rprop(h, ds.initparst, ds.modeprior, ds.fixedpars, ds.rhofixed, opts, res);
+  if (rc == 0) {
+    if (ds.want_loo && ds.loo_mean) rc = gpedm_get_vector(h, GPEDM_VEC_LOO_MEAN, ds.loo_mean);
+    if (rc == 0 && ds.want_loo && ds.loo_var) rc = gpedm_get_vector(h, GPEDM_VEC_LOO_VAR, ds.loo_var);
+    if (rc == 0 && ds.insamp_mean) rc = gpedm_get_vector(h, GPEDM_VEC_MEAN, ds.insamp_mean);
+    if (rc == 0 && ds.insamp_var) rc = gpedm_get_vector(h, GPEDM_VEC_VAR, ds.insamp_var);
+  }
+  res->status = rc;
+  gpedm_destroy(h);
+  return rc;
+}
+
+extern "C" int gpedm_fit_batch(int32_t nfits, const gpedm_fit_desc* descs, int32_t ngpus, const int32_t* devices,
+                               const gpedm_rprop_options* opts, gpedm_result* results) {
+  if (nfits < 0 || (nfits > 0 && (!descs || !results))) return set_err(GPEDM_ERR_ARG, "bad arguments");
+  if (nfits == 0) return 0;
+  int ndev = gpedm_device_count();
+  if (ndev == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available (libgpedm_b200 has no CPU fallback)");
+  if (ngpus < 1 || ngpus > ndev) return set_err(GPEDM_ERR_ARG, "ngpus=%d out of range (have %d devices)", ngpus, ndev);
+  std::vector<int> devs(ngpus);
+  for (int g = 0; g < ngpus; ++g) {
+    devs[g] = devices ? devices[g] : g;
+    if (devs[g] < 0 || devs[g] >= ndev) return set_err(GPEDM_ERR_ARG, "device %d out of range", devs[g]);
+  }
+  // queue ordered by descending estimated cost ~ N^3 (+ d N^2)
+  std::vector<int> order(nfits);
+  for (int i = 0; i < nfits; ++i) order[i] = i;
+  auto cost = [&](int i) {
+    double n = (double)descs[i].N;
+    return n * n * n + 40.0 * descs[i].d * n * n;
+  };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+  std::atomic<int> next(0);
+  std::vector<std::vector<BatchRecord>> per_gpu(ngpus);
+  std::vector<std::string> errs(ngpus);
+  auto worker = [&](int g) {
+    cudaSetDevice(devs[g]);
+    for (;;) {
+      int q = next.fetch_add(1);
+      if (q >= nfits) break;
+      int i = order[q];
+      BatchRecord rec;
+      memset(&rec, 0, sizeof(rec));
+      rec.fit_index = i;
+      rec.valid = 1;
+      int rc = run_one_fit(devs[g], descs[i], opts, &rec.res);
+      if (rc != 0 && errs[g].empty()) errs[g] = gpedm_last_error();
+      per_gpu[g].push_back(rec);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int g = 0; g < ngpus; ++g) th.emplace_back(worker, g);
+  for (auto& t : th) t.join();
+
+  if (ngpus == 1) {
+    for (auto& r : per_gpu[0]) results[r.fit_index] = r.res;
+  } else {
+    // Exchange the fixed-width records with ONE NCCL all-gather (single process, one
+    // communicator per GPU).  Every GPU contributes `slab` records (padded with valid=0).
+    NcclApi nc;
+    if (!load_nccl(nc)) return set_err(GPEDM_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+    size_t slab = 0;
+    for (int g = 0; g < ngpus; ++g) slab = std::max(slab, per_gpu[g].size());
+    if (slab == 0) slab = 1;
+    const size_t slab_bytes = slab * sizeof(BatchRecord);
+    std::vector<void*> comms(ngpus, nullptr);
+    int nrc = nc.CommInitAll(comms.data(), ngpus, devs.data());
+    if (nrc != 0)
+      return set_err(GPEDM_ERR_NCCL, "ncclCommInitAll failed: %s", nc.GetErrorString ? nc.GetErrorString(nrc) : "?");
+    std::vector<char*> dsend(ngpus, nullptr), drecv(ngpus, nullptr);
+    std::vector<cudaStream_t> sts(ngpus, nullptr);
+    cudaError_t e = cudaSuccess;
+    for (int g = 0; g < ngpus && e == cudaSuccess; ++g) {
+      e = cudaSetDevice(devs[g]);
+      if (e == cudaSuccess) e = cudaStreamCreate(&sts[g]);
+      if (e == cudaSuccess) e = cudaMalloc((void**)&dsend[g], slab_bytes);
+      if (e == cudaSuccess) e = cudaMalloc((void**)&drecv[g], slab_bytes * ngpus);
+      std::vector<BatchRecord> pad(slab);
+      memset(pad.data(), 0, slab_bytes);
+      for (size_t q = 0; q < per_gpu[g].size(); ++q) pad[q] = per_gpu[g][q];
+      if (e == cudaSuccess) e = cudaMemcpy(dsend[g], pad.data(), slab_bytes, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+      nc.GroupStart();
+      for (int g = 0; g < ngpus; ++g) {
+        cudaSetDevice(devs[g]);
+        nrc = nc.AllGather(dsend[g], drecv[g], slab_bytes, /*ncclChar*/ 0, comms[g], sts[g]);
+        if (nrc != 0) break;
+      }
+      int nrc2 = nc.GroupEnd();
+      if (nrc == 0) nrc = nrc2;
+      for (int g = 0; g < ngpus && e == cudaSuccess; ++g) {
+        cudaSetDevice(devs[g]);
+        e = cudaStreamSynchronize(sts[g]);
+      }
+    }
+    std::vector<BatchRecord> all(slab * ngpus);
+    if (e == cudaSuccess && nrc == 0) {
+      cudaSetDevice(devs[0]);
+      e = cudaMemcpy(all.data(), drecv[0], slab_bytes * ngpus, cudaMemcpyDeviceToHost);
+    }
+    for (int g = 0; g < ngpus; ++g) {
+      cudaSetDevice(devs[g]);
+      cudaFree(dsend[g]);
+      cudaFree(drecv[g]);
+      if (sts[g]) cudaStreamDestroy(sts[g]);
+      if (comms[g]) nc.CommDestroy(comms[g]);
+    }
+    if (nrc != 0) return set_err(GPEDM_ERR_NCCL, "ncclAllGather failed: %s", nc.GetErrorString ? nc.GetErrorString(nrc) : "?");
+    if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "batch gather failed: %s", cudaGetErrorString(e));
+    int got = 0;
+    for (auto& r : all)
+      if (r.valid && r.fit_index >= 0 && r.fit_index < nfits) {
+        results[r.fit_index] = r.res;
+        ++got;
+      }
+    if (got != nfits) return set_err(GPEDM_ERR_STATE, "batch gather returned %d of %d records", got, nfits);
+  }
+  for (int g = 0; g < ngpus; ++g)
+    if (!errs[g].empty()) {
+      int first_bad = 0;
+      for (int i = 0; i < nfits; ++i)
+        if (results[i].status != 0) {
+          first_bad = results[i].status;
+          break;
+        }
+      return set_err(first_bad ? first_bad : GPEDM_ERR_STATE, "at least one fit failed: %s", errs[g].c_str());
+    }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- measurement
+extern "C" int gpedm_fp64_peak(int device, int which, double* tflops) {
+  if (!tflops) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  if (gpedm_device_count() == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int nsm = prop.multiProcessorCount;
+  double* dout = nullptr;
+  CU(cudaMalloc((void**)&dout, (size_t)nsm * 4 * 256 * 8));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  float best = 1e30f;
+  const int iters = which == 0 ? 4000 : 20000;
+  const int ctas = which == 0 ? nsm : nsm * 4;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(e0));
+    if (which == 0)
+      probe_dmma_kernel<<<ctas, 256>>>(dout, iters);
+    else
+      probe_dfma_kernel<<<ctas, 256>>>(dout, iters);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  CU(cudaGetLastError());
+  double fl = which == 0 ? (double)ctas * 8 * 32.0 * iters * 512.0 : (double)ctas * 256 * 16.0 * iters * 2.0;
+  *tflops = fl / best * 1e-9;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dout);
+  return 0;
+}
+
+extern "C" int gpedm_bench_evals(gpedm_handle h, const double* parst, double modeprior, int steps, float* ms_per_eval) {
+  if (!h || !parst || !ms_per_eval || steps < 1) return set_err(GPEDM_ERR_ARG, "bad arguments");
+  CU(cudaSetDevice(h->device));
+  HostPars hp;
+  host_transform(h, parst, modeprior, nullptr, NAN, hp);
+  fill_params(h, hp);
+  h->have_full = false;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, h->stream));
+  for (int s = 0; s < steps; ++s) {
+    int rc = enqueue_eval(h, false);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(e1, h->stream));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaGetLastError());
+  float ms;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_per_eval = ms / steps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  collect_phase_times(h);
+  if (*h->hinfo > 0) return set_err(*h->hinfo, "covariance matrix not positive definite at row %d", *h->hinfo);
+  return 0;
+}

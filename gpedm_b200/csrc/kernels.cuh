@@ -1,0 +1,771 @@
+// CUDA kernels of the GP evaluation pipeline (sm_100a, FP64).
+// Matrices are Np x Np column-major with Np = N rounded up to a multiple of 128; the padded
+// rows/columns carry an identity so they are inert in every factorisation step.
+//   bufA : Sigma (lower, full diagonal tiles)  -> L   (in-place Cholesky)
+//   bufB : X = L^-1 (lower; diagonal tiles carry explicit zeros above the diagonal)
+//   bufC : scratch W during the triangular inverse, then S = Sigma^-1 (lower)
+#pragma once
+#include "dgemm_tile.cuh"
+
+namespace gpedm {
+
+constexpr int MAXD = 32;
+
+// Per-evaluation hyper-parameters, resident in device memory so that every kernel reads the
+// current values (keeps launches replayable).
+struct EvalParams {
+  double sqphi[MAXD];
+  double phi[MAXD];
+  double ve, sigma2, rho;
+  int d, np, use_rhotab, pad;
+};
+
+// -----------------------------------------------------------------------------------------
+// Covariance entry, arithmetic order of getcov (reference R/GPfunctions.R:787-811):
+//   lC0 = -sum_k (sqrt(phi_k) x2_ik - sqrt(phi_k) x_jk)^2   (laGP::distance: difference, square,
+//         accumulate in coordinate order; no fused multiply-add so rounding matches a CPU)
+//   Cd  = (sigma2 * exp(lC0)) * R,  R = 1 (same pop) | rho | rhomat[pop2_i, pop_j]
+// xi / xj point at pre-scaled coordinates with stride `sx` between coordinates.
+__device__ __forceinline__ double cov_entry(const double* xi, const double* xj, int sx, int d, double sigma2,
+                                            double rho, int pi, int pj, const double* rhotab, int np) {
+  double dist = 0.0;
+  for (int k = 0; k < d; ++k) {
+    double diff = __dsub_rn(xi[k * sx], xj[k * sx]);
+    dist = __dadd_rn(dist, __dmul_rn(diff, diff));
+  }
+  double v = __dmul_rn(sigma2, exp(-dist));
+  if (rhotab != nullptr)
+    v = __dmul_rn(v, rhotab[pi + pj * np]);
+  else if (pi != pj)
+    v = __dmul_rn(v, rho);
+  return v;
+}
+
+// Sigma = Cd + ve*I on the lower tiles (reference R/GPfunctions.R:633-641; the symmetrisation
+// at :641 is a no-op because each entry is computed once).  grid = nb*(nb+1)/2 tiles.
+__global__ void __launch_bounds__(256) assemble_sigma_kernel(double* __restrict__ A, size_t ld, int N,
+                                                              const double* __restrict__ X,
+                                                              const int* __restrict__ pop,
+                                                              const double* __restrict__ rhotab,
+                                                              const EvalParams* __restrict__ P) {
+  extern __shared__ double sm[];
+  const int d = P->d;
+  double* xi = sm;             // [d][128]
+  double* xj = sm + d * TB;    // [d][128]
+  int* pi_s = (int*)(xj + d * TB);
+  int* pj_s = pi_s + TB;
+  int ti, tj;
+  tri_decode(blockIdx.x, ti, tj);
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < d * TB; idx += 256) {
+    int k = idx >> 7, r = idx & 127;
+    int gi = ti * TB + r, gj = tj * TB + r;
+    double s = P->sqphi[k];
+    xi[idx] = gi < N ? __dmul_rn(X[(size_t)gi + (size_t)k * N], s) : 0.0;
+    xj[idx] = gj < N ? __dmul_rn(X[(size_t)gj + (size_t)k * N], s) : 0.0;
+  }
+  if (tid < TB) {
+    int gi = ti * TB + tid, gj = tj * TB + tid;
+    pi_s[tid] = gi < N ? pop[gi] : -1;
+    pj_s[tid] = gj < N ? pop[gj] : -1;
+  }
+  __syncthreads();
+  const double sigma2 = P->sigma2, rho = P->rho, ve = P->ve;
+  const int np = P->np;
+  const double* rt = P->use_rhotab ? rhotab : nullptr;
+  const int r = tid & 127, half = tid >> 7;
+  const int gi = ti * TB + r;
+  for (int c = half * 64; c < half * 64 + 64; ++c) {
+    int gj = tj * TB + c;
+    double v;
+    if (gi < N && gj < N) {
+      v = cov_entry(xi + r, xj + c, TB, d, sigma2, rho, pi_s[r], pj_s[c], rt, np);
+      if (gi == gj) v = __dadd_rn(v, ve);
+    } else {
+      v = (gi == gj) ? 1.0 : 0.0;
+    }
+    A[(size_t)gi + (size_t)gj * ld] = v;
+  }
+}
+
+// General rectangular covariance (getcov with X2 != X): out[(row) + (col)*ldo] where
+// transpose == 0: rows = new points (M), cols = training points (N)   -> Cd as R returns it
+// transpose == 1: rows = training points, cols = new points            -> Cs^T for the solves
+// Entries outside M x N (padding up to the allocated extents rows_alloc x cols_alloc) are zero.
+__global__ void __launch_bounds__(256) cov_rect_kernel(double* __restrict__ out, size_t ldo, int rows_alloc,
+                                                        int cols_alloc, int transpose, int N,
+                                                        const double* __restrict__ X, const int* __restrict__ pop,
+                                                        int M, const double* __restrict__ X2,
+                                                        const int* __restrict__ pop2,
+                                                        const double* __restrict__ rhotab,
+                                                        const EvalParams* __restrict__ P, int add_ve_diag) {
+  extern __shared__ double sm[];
+  const int d = P->d;
+  double* xr = sm;
+  double* xc = sm + d * TB;
+  int* pr_s = (int*)(xc + d * TB);
+  int* pc_s = pr_s + TB;
+  const int tr = blockIdx.x, tc = blockIdx.y;
+  const int tid = threadIdx.x;
+  // row-side / col-side sources
+  const double* Xr = transpose ? X : X2;
+  const double* Xc = transpose ? X2 : X;
+  const int* popr = transpose ? pop : pop2;
+  const int* popc = transpose ? pop2 : pop;
+  const int nr = transpose ? N : M, nc = transpose ? M : N;
+  for (int idx = tid; idx < d * TB; idx += 256) {
+    int k = idx >> 7, r = idx & 127;
+    int gr = tr * TB + r, gc = tc * TB + r;
+    double s = P->sqphi[k];
+    xr[idx] = gr < nr ? __dmul_rn(Xr[(size_t)gr + (size_t)k * nr], s) : 0.0;
+    xc[idx] = gc < nc ? __dmul_rn(Xc[(size_t)gc + (size_t)k * nc], s) : 0.0;
+  }
+  if (tid < TB) {
+    int gr = tr * TB + tid, gc = tc * TB + tid;
+    pr_s[tid] = gr < nr ? popr[gr] : -1;
+    pc_s[tid] = gc < nc ? popc[gc] : -1;
+  }
+  __syncthreads();
+  const double sigma2 = P->sigma2, rho = P->rho, ve = P->ve;
+  const int np = P->np;
+  const double* rt = P->use_rhotab ? rhotab : nullptr;
+  const int r = tid & 127, half = tid >> 7;
+  const int gr = tr * TB + r;
+  if (gr >= rows_alloc) return;
+  for (int c = half * 64; c < half * 64 + 64; ++c) {
+    int gc = tc * TB + c;
+    if (gc >= cols_alloc) break;
+    double v = 0.0;
+    if (gr < nr && gc < nc) {
+      // rhomat is addressed [pop2 (new), pop (train)] (reference :806)
+      int p_new = transpose ? pc_s[c] : pr_s[r];
+      int p_trn = transpose ? pr_s[r] : pc_s[c];
+      // the squared distance is symmetric in its arguments term by term, so xr/xc order is free
+      v = cov_entry(xr + r, xc + c, TB, d, sigma2, rho, p_new, p_trn, rt, np);
+      if (add_ve_diag && gr == gc) v = __dadd_rn(v, ve);
+    }
+    out[(size_t)gr + (size_t)gc * ldo] = v;
+  }
+}
+
+// popsame (reference :796) for export.
+__global__ void popsame_kernel(double* out, int N, const int* pop) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * N) return;
+  int i = (int)(idx % N), j = (int)(idx / N);
+  out[idx] = pop[i] == pop[j] ? 1.0 : 0.0;
+}
+
+// -----------------------------------------------------------------------------------------
+// Diagonal block: Cholesky of the 128x128 tile A_kk (lower, in place) and its inverse
+// D_k = L_kk^-1 written as a full tile (zeros above the diagonal) into bufB's diagonal tile.
+// Also emits sum(log L_ii) of this block and flags the first non-positive pivot.
+// One CTA; the tile lives in shared memory with stride 129.
+constexpr int DIAG_LD = TB + 1;
+constexpr int DIAG_SMEM_BYTES = (TB * DIAG_LD + 2 * TB) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256) diag_potf2_inv_kernel(double* __restrict__ Akk, size_t lda,
+                                                              double* __restrict__ Dkk, size_t ldd, int kblock,
+                                                              int n_valid, double* __restrict__ logdet_part,
+                                                              int* __restrict__ info) {
+  extern __shared__ double sm[];
+  double* s = sm;                     // [128][129] column-major: s[r + c*129]
+  double* dvec = sm + TB * DIAG_LD;   // pivots
+  double* xv = dvec + TB;             // column scratch for the inverse
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < TB * TB; idx += 256) {
+    int r = idx & 127, c = idx >> 7;
+    s[r + c * DIAG_LD] = Akk[(size_t)r + (size_t)c * lda];
+  }
+  __syncthreads();
+  // ---- left-looking Cholesky, one column per step ----
+  for (int j = 0; j < TB; ++j) {
+    double sum = 0.0;
+    if (tid >= j && tid < TB) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = 0;
+      for (; c + 3 < j; c += 4) {
+        s0 = fma(s[tid + c * DIAG_LD], s[j + c * DIAG_LD], s0);
+        s1 = fma(s[tid + (c + 1) * DIAG_LD], s[j + (c + 1) * DIAG_LD], s1);
+        s2 = fma(s[tid + (c + 2) * DIAG_LD], s[j + (c + 2) * DIAG_LD], s2);
+        s3 = fma(s[tid + (c + 3) * DIAG_LD], s[j + (c + 3) * DIAG_LD], s3);
+      }
+      for (; c < j; ++c) s0 = fma(s[tid + c * DIAG_LD], s[j + c * DIAG_LD], s0);
+      sum = s[tid + j * DIAG_LD] - ((s0 + s1) + (s2 + s3));
+      if (tid == j) {
+        if (!(sum > 0.0)) {
+          if (kblock * TB + j < n_valid) atomicCAS(info, 0, kblock * TB + j + 1);
+        }
+        dvec[j] = sqrt(sum);
+      }
+    }
+    __syncthreads();
+    if (tid >= j && tid < TB) {
+      double dj = dvec[j];
+      s[tid + j * DIAG_LD] = (tid == j) ? dj : sum / dj;
+    }
+    __syncthreads();
+  }
+  // write L back (lower part; upper part of the tile zeroed so later full-tile reads are clean)
+  for (int idx = tid; idx < TB * TB; idx += 256) {
+    int r = idx & 127, c = idx >> 7;
+    Akk[(size_t)r + (size_t)c * lda] = (r >= c) ? s[r + c * DIAG_LD] : 0.0;
+  }
+  // log-determinant contribution (fixed-order reduction -> deterministic)
+  if (tid < TB) xv[tid] = (kblock * TB + tid < n_valid) ? log(dvec[tid]) : 0.0;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if (tid < off) xv[tid] += xv[tid + off];
+    __syncthreads();
+  }
+  if (tid == 0) logdet_part[kblock] = xv[0];
+  __syncthreads();
+  // ---- in-place inverse of the lower-triangular block (unblocked, columns right to left) ----
+  for (int j = TB - 1; j >= 0; --j) {
+    if (tid > j && tid < TB) xv[tid] = s[tid + j * DIAG_LD];  // L[r][j], r > j
+    __syncthreads();
+    double val = 0.0;
+    if (tid > j && tid < TB) {
+      double s0 = 0.0, s1 = 0.0;
+      int c = j + 1;
+      for (; c + 1 <= tid; c += 2) {
+        s0 = fma(s[tid + c * DIAG_LD], xv[c], s0);
+        s1 = fma(s[tid + (c + 1) * DIAG_LD], xv[c + 1], s1);
+      }
+      for (; c <= tid; ++c) s0 = fma(s[tid + c * DIAG_LD], xv[c], s0);
+      val = -(s0 + s1) / dvec[j];
+    }
+    __syncthreads();
+    if (tid > j && tid < TB) s[tid + j * DIAG_LD] = val;
+    if (tid == j) s[j + j * DIAG_LD] = 1.0 / dvec[j];
+    __syncthreads();
+  }
+  for (int idx = tid; idx < TB * TB; idx += 256) {
+    int r = idx & 127, c = idx >> 7;
+    Dkk[(size_t)r + (size_t)c * ldd] = (r >= c) ? s[r + c * DIAG_LD] : 0.0;
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// DMMA tile kernels (all launched with GEMM_THREADS threads and GEMM_SMEM_BYTES dynamic smem)
+
+// Panel: L_ik = A_ik * D_k^T for i > k (in place; each CTA is the only reader of its tile).
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    potrf_panel_kernel(double* __restrict__ A, const double* __restrict__ Bx, size_t ld, int k) {
+  extern __shared__ double smem[];
+  const int i = k + 1 + blockIdx.x;
+  double* At = A + (size_t)i * TB + (size_t)k * TB * ld;
+  const double* Dk = Bx + (size_t)k * TB + (size_t)k * TB * ld;
+  gemm_tile<false, false>(At, ld, Dk, ld, 0, TB, false, nullptr, 0, At, ld, smem);
+}
+
+// Trailing update: A_ij -= L_ik L_jk^T for jlo <= j <= i < nb, j < jhi (lower tiles).
+// Tiles are enumerated column-block by column-block so that a look-ahead launch can take
+// just the first column (jhi = jlo + 1).
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    potrf_trail_kernel(double* __restrict__ A, size_t ld, int k, int nb, int jlo, int jhi) {
+  extern __shared__ double smem[];
+  // decode blockIdx.x -> (i, j): columns j = jlo..jhi-1, each with (nb - j) tiles
+  int t = blockIdx.x;
+  int j = jlo;
+  while (t >= nb - j) {
+    t -= nb - j;
+    ++j;
+  }
+  (void)jhi;
+  const int i = j + t;
+  const double* Pi = A + (size_t)i * TB + (size_t)k * TB * ld;
+  const double* Pj = A + (size_t)j * TB + (size_t)k * TB * ld;
+  double* Ct = A + (size_t)i * TB + (size_t)j * TB * ld;
+  gemm_tile<false, false>(Pi, ld, Pj, ld, 0, TB, true, Ct, ld, Ct, ld, smem);
+}
+
+// Triangular inverse, recursive doubling level with block size s (in tiles):
+//   W  = L21 * X11      (into bufC at the position of block (2,1))
+//   X21 = -X22 * W      (into bufB)
+// for every pair p covering tile rows/cols [2ps, 2ps+2s).
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    trtri_w_kernel(const double* __restrict__ L, const double* __restrict__ X, double* __restrict__ W, size_t ld,
+                   int nb, int s) {
+  extern __shared__ double smem[];
+  const int per = s * s;
+  const int p = blockIdx.x / per, rem = blockIdx.x % per;
+  const int j = rem / s, i = rem % s;  // ascending j first: longest k range first
+  const int o = p * 2 * s;
+  if (o + s >= nb) return;
+  const int s2 = min(s, nb - (o + s));
+  if (i >= s2) return;
+  const double* At = L + (size_t)(o + s + i) * TB + (size_t)o * TB * ld;
+  const double* Bt = X + (size_t)o * TB + (size_t)(o + j) * TB * ld;
+  double* Ct = W + (size_t)(o + s + i) * TB + (size_t)(o + j) * TB * ld;
+  gemm_tile<false, true>(At, ld, Bt, ld, j * TB, s * TB, false, nullptr, 0, Ct, ld, smem);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    trtri_x_kernel(double* __restrict__ X, const double* __restrict__ W, size_t ld, int nb, int s) {
+  extern __shared__ double smem[];
+  const int per = s * s;
+  const int p = blockIdx.x / per, rem = blockIdx.x % per;
+  const int i = s - 1 - rem / s, j = rem % s;  // descending i first: longest k range first
+  const int o = p * 2 * s;
+  if (o + s >= nb) return;
+  const int s2 = min(s, nb - (o + s));
+  if (i >= s2) return;
+  const double* At = X + (size_t)(o + s + i) * TB + (size_t)(o + s) * TB * ld;
+  const double* Bt = W + (size_t)(o + s) * TB + (size_t)(o + j) * TB * ld;
+  double* Ct = X + (size_t)(o + s + i) * TB + (size_t)(o + j) * TB * ld;
+  gemm_tile<false, true>(At, ld, Bt, ld, 0, (i + 1) * TB, true, nullptr, 0, Ct, ld, smem);
+}
+
+// S = X^T X on the lower tiles (X lower triangular): S_ij = sum_{k >= i} X_ki^T X_kj.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    lauum_kernel(const double* __restrict__ X, double* __restrict__ S, size_t ld, int nb) {
+  extern __shared__ double smem[];
+  int i, j;
+  tri_decode(blockIdx.x, i, j);  // ascending i: longest k range first
+  const double* At = X + (size_t)i * TB * ld;
+  const double* Bt = X + (size_t)j * TB * ld;
+  double* Ct = S + (size_t)i * TB + (size_t)j * TB * ld;
+  gemm_tile<true, true>(At, ld, Bt, ld, i * TB, nb * TB, false, nullptr, 0, Ct, ld, smem);
+}
+
+// U = X * V for prediction (X = L^-1 lower, V = Cs^T padded to Np x Mp): tile (i, jt),
+// k range [0, (i+1)*128).
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    tri_apply_kernel(const double* __restrict__ X, size_t ldx, const double* __restrict__ V, double* __restrict__ U,
+                     size_t ldv, int nb) {
+  extern __shared__ double smem[];
+  const int i = nb - 1 - blockIdx.x, jt = blockIdx.y;
+  const double* At = X + (size_t)i * TB;
+  const double* Bt = V + (size_t)jt * TB * ldv;
+  double* Ct = U + (size_t)i * TB + (size_t)jt * TB * ldv;
+  gemm_tile<false, true>(At, ldx, Bt, ldv, 0, (i + 1) * TB, false, nullptr, 0, Ct, ldv, smem);
+}
+
+// -----------------------------------------------------------------------------------------
+// Vector work on the lower-triangular X = L^-1:  z = X Y,  a = X^T z  (so a = Sigma^-1 Y,
+// reference R/GPfunctions.R:647, and Y'a = ||z||^2).  Tile partials + fixed-order reduction
+// keep the result deterministic.
+
+// zpart[tj][row] = sum_{c in tile tj} X[row, c] * y[c]      for lower tiles (ti >= tj)
+__global__ void __launch_bounds__(256) trmv_n_part_kernel(const double* __restrict__ X, size_t ld,
+                                                           const double* __restrict__ y,
+                                                           double* __restrict__ part, size_t np_ld) {
+  __shared__ double ys[TB];
+  __shared__ double red[TB];
+  int ti, tj;
+  tri_decode(blockIdx.x, ti, tj);
+  const int tid = threadIdx.x, r = tid & 127, half = tid >> 7;
+  if (tid < TB) ys[tid] = y[(size_t)tj * TB + tid];
+  __syncthreads();
+  const double* xp = X + (size_t)ti * TB + r + (size_t)tj * TB * ld;
+  double s0 = 0.0, s1 = 0.0;
+  for (int c = half * 64; c < half * 64 + 64; c += 2) {
+    s0 = fma(xp[(size_t)c * ld], ys[c], s0);
+    s1 = fma(xp[(size_t)(c + 1) * ld], ys[c + 1], s1);
+  }
+  double s = s0 + s1;
+  if (half == 1) red[r] = s;
+  __syncthreads();
+  if (half == 0) part[(size_t)tj * np_ld + (size_t)ti * TB + r] = s + red[r];
+}
+
+// apart[ti][col] = sum_{r in tile ti} X[r, col] * z[r]       for lower tiles (ti >= tj)
+__global__ void __launch_bounds__(256) trmv_t_part_kernel(const double* __restrict__ X, size_t ld,
+                                                           const double* __restrict__ z,
+                                                           double* __restrict__ part, size_t np_ld) {
+  __shared__ double zs[TB];
+  int ti, tj;
+  tri_decode(blockIdx.x, ti, tj);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < TB) zs[tid] = z[(size_t)ti * TB + tid];
+  __syncthreads();
+  for (int c = warp; c < TB; c += 8) {
+    const double* xp = X + (size_t)ti * TB + (size_t)(tj * TB + c) * ld;
+    double s = xp[lane] * zs[lane];
+    s = fma(xp[lane + 32], zs[lane + 32], s);
+    s = fma(xp[lane + 64], zs[lane + 64], s);
+    s = fma(xp[lane + 96], zs[lane + 96], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) part[(size_t)ti * np_ld + (size_t)tj * TB + c] = s;
+  }
+}
+
+// out[i] = sum over the tile partials that exist for i, in fixed order.
+// mode 0: partial index tj runs 0..tile(i)   (z);  mode 1: ti runs tile(i)..nb-1   (a)
+__global__ void reduce_parts_kernel(const double* __restrict__ part, size_t np_ld, int nb, int mode,
+                                    double* __restrict__ out, int n_alloc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_alloc) return;
+  int t = i / TB;
+  double s = 0.0;
+  if (mode == 0)
+    for (int q = 0; q <= t; ++q) s += part[(size_t)q * np_ld + i];
+  else
+    for (int q = t; q < nb; ++q) s += part[(size_t)q * np_ld + i];
+  out[i] = s;
+}
+
+__global__ void extract_diag_kernel(const double* __restrict__ S, size_t ld, int n, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = S[(size_t)i + (size_t)i * ld];
+}
+
+// -----------------------------------------------------------------------------------------
+// Gradient trace terms (reference R/GPfunctions.R:652-709):  with vQ = 0.5 (a a' - Sigma^-1),
+//   T_k   = <vQ, -D_k o Cd>          (dl_k = 0.5 T_k, the reference's extra one half, :663)
+//   T_ve  = <vQ, I>, T_s2 = <vQ, Cd/sigma2>, T_rho = <vQ, Cd o (1-popsame) / rho>
+// Reads Sigma^-1 (lower tiles) once; Cd and the per-coordinate squared distances D_k are
+// recomputed from the staged predictor tiles instead of being stored (the reference keeps d
+// dense N x N matrices, :539-542).  Off-diagonal entries count twice (symmetry).
+// tracepart[tile][q], q = 0..d-1 (phi), d (ve), d+1 (sigma2), d+2 (rho).
+template <int DC>
+__global__ void __launch_bounds__(256) grad_trace_kernel(const double* __restrict__ S, size_t ld, int N,
+                                                          const double* __restrict__ X,
+                                                          const int* __restrict__ pop,
+                                                          const double* __restrict__ rhotab,
+                                                          const double* __restrict__ avec,
+                                                          const EvalParams* __restrict__ P,
+                                                          double* __restrict__ tracepart) {
+  extern __shared__ double sm[];
+  const int d = P->d;
+  double* xi = sm;                  // scaled  [d][128]
+  double* xj = xi + d * TB;
+  double* ri = xj + d * TB;         // raw     [d][128]
+  double* rj = ri + d * TB;
+  double* ai = rj + d * TB;         // [128]
+  double* aj = ai + TB;
+  double* red = aj + TB;            // [8][DC+3]
+  int* pi_s = (int*)(red + 8 * (DC + 3));
+  int* pj_s = pi_s + TB;
+  int ti, tj;
+  tri_decode(blockIdx.x, ti, tj);
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < d * TB; idx += 256) {
+    int k = idx >> 7, r = idx & 127;
+    int gi = ti * TB + r, gj = tj * TB + r;
+    double s = P->sqphi[k];
+    double vi = gi < N ? X[(size_t)gi + (size_t)k * N] : 0.0;
+    double vj = gj < N ? X[(size_t)gj + (size_t)k * N] : 0.0;
+    ri[idx] = vi;
+    rj[idx] = vj;
+    xi[idx] = __dmul_rn(vi, s);
+    xj[idx] = __dmul_rn(vj, s);
+  }
+  if (tid < TB) {
+    int gi = ti * TB + tid, gj = tj * TB + tid;
+    pi_s[tid] = gi < N ? pop[gi] : -1;
+    pj_s[tid] = gj < N ? pop[gj] : -1;
+    ai[tid] = gi < N ? avec[gi] : 0.0;
+    aj[tid] = gj < N ? avec[gj] : 0.0;
+  }
+  __syncthreads();
+  const double sigma2 = P->sigma2, rho = P->rho;
+  const int np = P->np;
+  const double* rt = P->use_rhotab ? rhotab : nullptr;
+  const int r = tid & 127, half = tid >> 7;
+  const int gi = ti * TB + r;
+  double acc[DC + 3];
+#pragma unroll
+  for (int q = 0; q < DC + 3; ++q) acc[q] = 0.0;
+  if (gi < N) {
+    const double a_i = ai[r];
+    const int p_i = pi_s[r];
+    const double* Sp = S + (size_t)gi + (size_t)tj * TB * ld;
+    for (int c = half * 64; c < half * 64 + 64; ++c) {
+      int gj = tj * TB + c;
+      if (gj >= N || gj > gi) continue;
+      double sij = Sp[(size_t)c * ld];
+      double q = 0.5 * (a_i * aj[c] - sij);
+      double cd = cov_entry(xi + r, xj + c, TB, d, sigma2, rho, p_i, pj_s[c], rt, np);
+      double w = (gi == gj) ? 1.0 : 2.0;
+      double qc = w * q * cd;
+#pragma unroll
+      for (int k = 0; k < DC; ++k) {
+        if (k < d) {
+          double df = ri[k * TB + r] - rj[k * TB + c];
+          acc[k] -= qc * (df * df);
+        }
+      }
+      if (gi == gj) acc[DC] += q;
+      acc[DC + 1] += qc / sigma2;
+      if (p_i != pj_s[c]) acc[DC + 2] += qc / rho;
+    }
+  }
+  // block reduction in fixed order: warp shuffle tree, then 8 warp partials summed by warp 0
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int q = 0; q < DC + 3; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) red[warp * (DC + 3) + q] = v;
+  }
+  __syncthreads();
+  if (tid < DC + 3) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red[w * (DC + 3) + tid];
+    int qo = tid < DC ? tid : d + (tid - DC);
+    if (tid >= DC || tid < d) tracepart[(size_t)blockIdx.x * (MAXD + 3) + qo] = v;
+  }
+}
+
+// Final scalar reductions of one evaluation (single CTA, fixed order => deterministic):
+//  scal[0]        = logdet = sum log L_ii                (:648, :729)
+//  scal[1]        = SS = ||z||^2 = Y' a                   (:728)
+//  scal[2]        = sum log diag(S)      \  lnL_LOO (:742)
+//  scal[3]        = sum a_i^2 / S_ii     /
+//  scal[4]        = tr(S)                 -> df = N - ve tr(S)  (:743)
+//  scal[8 + q]    = trace terms q = 0..d+2
+__global__ void __launch_bounds__(256) final_reduce_kernel(const double* __restrict__ logdet_part, int nb,
+                                                            const double* __restrict__ z,
+                                                            const double* __restrict__ avec,
+                                                            const double* __restrict__ diagS, int N,
+                                                            const double* __restrict__ tracepart, int ntiles,
+                                                            int nq, int have_S, double* __restrict__ scal) {
+  __shared__ double red[256];
+  const int tid = threadIdx.x;
+  auto block_sum = [&](double v) -> double {
+    red[tid] = v;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (tid < off) red[tid] += red[tid + off];
+      __syncthreads();
+    }
+    double r = red[0];
+    __syncthreads();
+    return r;
+  };
+  double v = 0.0;
+  for (int i = tid; i < nb; i += 256) v += logdet_part[i];
+  double logdet = block_sum(v);
+  v = 0.0;
+  for (int i = tid; i < N; i += 256) v = fma(z[i], z[i], v);
+  double ss = block_sum(v);
+  double sl = 0.0, sq = 0.0, tr = 0.0;
+  if (have_S) {
+    double v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    for (int i = tid; i < N; i += 256) {
+      double sii = diagS[i];
+      v1 += log(sii);
+      v2 += avec[i] * avec[i] / sii;
+      v3 += sii;
+    }
+    sl = block_sum(v1);
+    sq = block_sum(v2);
+    tr = block_sum(v3);
+  }
+  if (tid == 0) {
+    scal[0] = logdet;
+    scal[1] = ss;
+    scal[2] = sl;
+    scal[3] = sq;
+    scal[4] = tr;
+  }
+  for (int q = 0; q < nq; ++q) {
+    v = 0.0;
+    for (int t = tid; t < ntiles; t += 256) v += tracepart[(size_t)t * (MAXD + 3) + q];
+    double s = block_sum(v);
+    if (tid == 0) scal[8 + q] = s;
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// Prediction helpers.  V = Cs^T (Np x Mp, zero padded), U = L^-1 V.
+// mean[m] = sum_n V[n,m] a[n]  (reference :1017);  gpgrad[m,k] = -2 phi_k sum_n (xnew_mk - x_nk) V[n,m] a[n]
+// (getGPgrad :1863-1865, unscaled coordinates);  var[m] = sigma2 - sum_n U[n,m]^2 (:1020, evaluated as
+// sigma2 - ||L^-1 c||^2).  One CTA per new point.
+__global__ void __launch_bounds__(256) predict_reduce_kernel(const double* __restrict__ V,
+                                                              const double* __restrict__ U, size_t ldv, int N,
+                                                              int M, const double* __restrict__ avec,
+                                                              const double* __restrict__ X,
+                                                              const double* __restrict__ Xnew,
+                                                              const EvalParams* __restrict__ P,
+                                                              double* __restrict__ mean, double* __restrict__ var,
+                                                              double* __restrict__ gpgrad) {
+  __shared__ double red[256];
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const int d = P->d;
+  auto block_sum = [&](double v) -> double {
+    red[tid] = v;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (tid < off) red[tid] += red[tid + off];
+      __syncthreads();
+    }
+    double r = red[0];
+    __syncthreads();
+    return r;
+  };
+  const double* v = V + (size_t)m * ldv;
+  double s = 0.0;
+  for (int n = tid; n < N; n += 256) s = fma(v[n], avec[n], s);
+  s = block_sum(s);
+  if (tid == 0) mean[m] = s;
+  if (U != nullptr) {
+    const double* u = U + (size_t)m * ldv;
+    double q = 0.0;
+    for (int n = tid; n < N; n += 256) q = fma(u[n], u[n], q);
+    q = block_sum(q);
+    if (tid == 0) var[m] = P->sigma2 - q;
+  }
+  if (gpgrad != nullptr) {
+    for (int k = 0; k < d; ++k) {
+      double xk = Xnew[(size_t)m + (size_t)k * M];
+      double g = 0.0;
+      for (int n = tid; n < N; n += 256) g = fma((xk - X[(size_t)n + (size_t)k * N]) * v[n], avec[n], g);
+      g = block_sum(g);
+      if (tid == 0) gpgrad[(size_t)m + (size_t)k * M] = -2.0 * P->phi[k] * g;
+    }
+  }
+}
+
+// Gather the (symmetric) sub-blocks S[B_g, B_g] of Sigma^-1 for the block leave-out formulas.
+// idx: concatenated member indices; goff[g]: start of group g in idx; boff[g]: start of its
+// |B|x|B| block in out (column-major).
+__global__ void gather_blocks_kernel(const double* __restrict__ S, size_t ld, const int* __restrict__ idx,
+                                     const int* __restrict__ goff, const long long* __restrict__ boff, int ngroups,
+                                     double* __restrict__ out) {
+  int g = blockIdx.x;
+  if (g >= ngroups) return;
+  int b0 = goff[g], nbk = goff[g + 1] - b0;
+  double* o = out + boff[g];
+  for (int e = threadIdx.x; e < nbk * nbk; e += blockDim.x) {
+    int r = e % nbk, c = e / nbk;
+    int ir = idx[b0 + r], ic = idx[b0 + c];
+    int hi = max(ir, ic), lo = min(ir, ic);
+    o[e] = S[(size_t)hi + (size_t)lo * ld];
+  }
+}
+
+// Sequential (leave-future-out) prediction from the Cholesky factor of the time-major ordered
+// matrix (reference :1196-1245, identities in SURVEY appendix B):
+//   mean_r = sum_{c < bstart(r)} L[r,c] z_c,   sd_r = sqrt( sum_{bstart(r) <= c <= r} L[r,c]^2 )
+// One warp per row.
+__global__ void __launch_bounds__(256) sequential_kernel(const double* __restrict__ L, size_t ld, int N,
+                                                          const double* __restrict__ z,
+                                                          const int* __restrict__ bstart,
+                                                          double* __restrict__ mean, double* __restrict__ sd) {
+  int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (r >= N) return;
+  int b0 = bstart[r];
+  double m = 0.0, q = 0.0;
+  for (int c = lane; c <= r; c += 32) {
+    double l = L[(size_t)r + (size_t)c * ld];
+    if (c < b0)
+      m = fma(l, z[c], m);
+    else
+      q = fma(l, l, q);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    m += __shfl_xor_sync(0xffffffffu, m, off);
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+  }
+  if (lane == 0) {
+    mean[r] = m;
+    sd[r] = sqrt(q);
+  }
+}
+
+// LOO / LTO GP-gradient (getGPgrad with the focal group's rows removed, reference :1081-1085,
+// :1168-1175).  For focal row i with excluded set B and u = (S_BB)^-1 a_B:
+//   a^(-B)_j = a_j - sum_{b in B} S[j,b] u_b  (j not in B),
+//   grad_k = -2 phi_k sum_{j not in B} (x_ik - x_jk) Cd[i,j] a^(-B)_j.
+// One CTA per focal row.  members/u are the group's concatenated arrays.
+__global__ void __launch_bounds__(256) loo_gpgrad_kernel(const double* __restrict__ S, size_t ld, int N,
+                                                          const double* __restrict__ X,
+                                                          const int* __restrict__ pop,
+                                                          const double* __restrict__ rhotab,
+                                                          const double* __restrict__ avec,
+                                                          const EvalParams* __restrict__ P,
+                                                          const int* __restrict__ focal,
+                                                          const int* __restrict__ fgroup,
+                                                          const int* __restrict__ idx,
+                                                          const int* __restrict__ goff,
+                                                          const double* __restrict__ uvec, int nfocal,
+                                                          double* __restrict__ gpgrad) {
+  __shared__ double red[256];
+  __shared__ double xis[MAXD], xir[MAXD];
+  const int f = blockIdx.x, tid = threadIdx.x;
+  if (f >= nfocal) return;
+  const int i = focal[f], g = fgroup[f];
+  const int b0 = goff[g], nbk = goff[g + 1] - b0;
+  const int d = P->d;
+  if (tid < d) {
+    xir[tid] = X[(size_t)i + (size_t)tid * N];
+    xis[tid] = __dmul_rn(xir[tid], P->sqphi[tid]);
+  }
+  __syncthreads();
+  double acc[MAXD];
+  for (int k = 0; k < d; ++k) acc[k] = 0.0;
+  const double* rt = P->use_rhotab ? rhotab : nullptr;
+  for (int j = tid; j < N; j += 256) {
+    bool inB = false;
+    double corr = 0.0;
+    for (int b = 0; b < nbk; ++b) {
+      int ib = idx[b0 + b];
+      if (ib == j) inB = true;
+      int hi = max(j, ib), lo = min(j, ib);
+      corr = fma(S[(size_t)hi + (size_t)lo * ld], uvec[b0 + b], corr);
+    }
+    if (inB) continue;
+    double aj = avec[j] - corr;
+    double dist = 0.0;
+    for (int k = 0; k < d; ++k) {
+      double diff = __dsub_rn(xis[k], __dmul_rn(X[(size_t)j + (size_t)k * N], P->sqphi[k]));
+      dist = __dadd_rn(dist, __dmul_rn(diff, diff));
+    }
+    double v = __dmul_rn(P->sigma2, exp(-dist));
+    if (rt != nullptr)
+      v = __dmul_rn(v, rt[pop[i] + pop[j] * P->np]);
+    else if (pop[i] != pop[j])
+      v = __dmul_rn(v, P->rho);
+    double w = v * aj;
+    for (int k = 0; k < d; ++k) acc[k] = fma(xir[k] - X[(size_t)j + (size_t)k * N], w, acc[k]);
+  }
+  for (int k = 0; k < d; ++k) {
+    red[tid] = acc[k];
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (tid < off) red[tid] += red[tid + off];
+      __syncthreads();
+    }
+    if (tid == 0) gpgrad[(size_t)f + (size_t)k * nfocal] = -2.0 * P->phi[k] * red[0];
+    __syncthreads();
+  }
+}
+
+// FP64 issue-rate probes (roofline denominators).
+__global__ void __launch_bounds__(256) probe_dmma_kernel(double* out, int iters) {
+  double c[32][2];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) c[i][0] = c[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) probe_dfma_kernel(double* out, int iters) {
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = i;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace gpedm
