@@ -25,14 +25,27 @@
 
 namespace gpedm {
 
-constexpr int TB = 128;            // tile edge
-constexpr int GEMM_THREADS = 256;  // 8 warps: 2 (m) x 4 (n), warp tile 64 x 32
-constexpr int BKK = 16;            // k slab per pipeline stage
-constexpr int GEMM_STAGES = 4;
-constexpr int LD_MN = TB + 4;      // smem row stride (doubles) of an MN-major slab [BKK][LD_MN]
-constexpr int LD_K = BKK + 4;      // smem row stride (doubles) of a  K-major slab [TB][LD_K]
-constexpr int SLAB_ELEMS = (BKK * LD_MN > TB * LD_K) ? BKK * LD_MN : TB * LD_K;  // 2560 doubles
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * SLAB_ELEMS * (int)sizeof(double);  // 160 KB
+constexpr int TB = 128;  // tile edge
+
+// Compile-time shape of the contraction kernel.  WM x WN warps, each owning a
+// (128/WM) x (128/WN) sub-tile; k slabs of BK columns, NSTAGE-deep cp.async pipeline.
+template <int WM_, int WN_, int BK_, int NSTAGE_>
+struct GemmCfgT {
+  static constexpr int WM = WM_, WN = WN_, BK = BK_, NSTAGE = NSTAGE_;
+  static constexpr int THREADS = WM * WN * 32;
+  static constexpr int MT = TB / WM / 8;  // 8-row DMMA tiles per warp along m
+  static constexpr int NT = TB / WN / 8;  // 8-col DMMA tiles per warp along n
+  static constexpr int LD_MN = TB + 4;    // smem row stride (doubles) of an MN-major slab [BK][LD_MN]
+  static constexpr int LD_K = BK + 4;     // smem row stride (doubles) of a  K-major slab [TB][LD_K]
+  static constexpr int SLAB = (BK * LD_MN > TB * LD_K) ? BK * LD_MN : TB * LD_K;
+  static constexpr int SMEM_BYTES = NSTAGE * 2 * SLAB * (int)sizeof(double);
+};
+#ifndef GPEDM_GEMM_CFG
+#define GPEDM_GEMM_CFG GemmCfgT<2, 4, 16, 4>
+#endif
+using GemmCfg = GPEDM_GEMM_CFG;
+constexpr int GEMM_THREADS = GemmCfg::THREADS;
+constexpr int GEMM_SMEM_BYTES = GemmCfg::SMEM_BYTES;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -50,118 +63,126 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// Stage one 16-wide k slab of a 128-row operand into shared memory.
-template <bool KMAJOR>
+__device__ __forceinline__ double flip_sign(double x, unsigned mask) {
+  return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+}
+
+// Stage one BK-wide k slab of a 128-row operand into shared memory.
+template <class Cfg, bool KMAJOR>
 __device__ __forceinline__ void load_slab(double* __restrict__ s, const double* __restrict__ g, size_t ld,
                                           int k0, int tid) {
+  constexpr int CHUNKS = TB * Cfg::BK / 2;  // 16-byte chunks per slab
   if (!KMAJOR) {
-    // global: 16 columns (k) of 128 contiguous doubles.  1024 16-byte chunks, 4 per thread.
+    // global: BK columns (k) of 128 contiguous doubles.
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int chunk = tid + r * GEMM_THREADS;
-      int row = chunk >> 6;        // k within slab
-      int c2 = (chunk & 63) << 1;  // m offset
-      cp_async16(s + row * LD_MN + c2, g + (size_t)(k0 + row) * ld + c2);
+    for (int r = 0; r < (CHUNKS + Cfg::THREADS - 1) / Cfg::THREADS; ++r) {
+      int chunk = tid + r * Cfg::THREADS;
+      if (CHUNKS % Cfg::THREADS == 0 || chunk < CHUNKS) {
+        int row = chunk >> 6;        // k within slab
+        int c2 = (chunk & 63) << 1;  // m offset
+        cp_async16(s + row * Cfg::LD_MN + c2, g + (size_t)(k0 + row) * ld + c2);
+      }
     }
   } else {
-    // global: 128 columns (m) of 16 contiguous doubles (k).
+    // global: 128 columns (m) of BK contiguous doubles (k).
+    constexpr int CPR = Cfg::BK / 2;  // chunks per row
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int chunk = tid + r * GEMM_THREADS;
-      int row = chunk >> 3;       // m
-      int c2 = (chunk & 7) << 1;  // k offset within slab
-      cp_async16(s + row * LD_K + c2, g + (size_t)row * ld + k0 + c2);
+    for (int r = 0; r < (CHUNKS + Cfg::THREADS - 1) / Cfg::THREADS; ++r) {
+      int chunk = tid + r * Cfg::THREADS;
+      if (CHUNKS % Cfg::THREADS == 0 || chunk < CHUNKS) {
+        int row = chunk / CPR;         // m
+        int c2 = (chunk % CPR) << 1;   // k offset within slab
+        cp_async16(s + row * Cfg::LD_K + c2, g + (size_t)row * ld + k0 + c2);
+      }
     }
   }
 }
 
-struct TileAcc {
-  double v[8][4][2];
-};
-
-// Main contraction.  `smem` must provide GEMM_SMEM_BYTES.  kbeg/kend are element
-// indices along k (multiples of 16) applied to both operands' k axes.
+// Main contraction.  `smem` must provide Cfg::SMEM_BYTES.  kbeg/kend are element
+// indices along k (multiples of BK) applied to both operands' k axes.
 // If Cin != nullptr the accumulator starts from the Cin tile (fetched before the
 // k loop so its latency hides under the first slabs), else from zero.
-template <bool A_KMAJOR, bool B_KMAJOR>
+template <bool A_KMAJOR, bool B_KMAJOR, class Cfg = GemmCfg>
 __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, size_t lda, const double* __restrict__ B,
                                           size_t ldb, int kbeg, int kend, bool negate, const double* Cin,
                                           size_t ldcin, double* __restrict__ Cout, size_t ldc, double* smem) {
+  constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, SLAB = Cfg::SLAB;
+  constexpr int LD_MN = Cfg::LD_MN, LD_K = Cfg::LD_K;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int m0 = (warp & 1) * 64, n0 = (warp >> 1) * 32;
+  const int m0 = (warp % Cfg::WM) * (MT * 8), n0 = (warp / Cfg::WM) * (NT * 8);
 
   double* sA = smem;
-  double* sB = smem + GEMM_STAGES * SLAB_ELEMS;
+  double* sB = smem + NS * SLAB;
 
-  const int nk = (kend - kbeg) / BKK;
-  // prologue: first STAGES-1 slabs in flight
+  const int nk = (kend - kbeg) / BK;
+  const unsigned sgn = negate ? 0x80000000u : 0u;  // sign flip on the integer pipe, not the FP64 pipe
 #pragma unroll
-  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+  for (int s = 0; s < NS - 1; ++s) {
     if (s < nk) {
-      load_slab<A_KMAJOR>(sA + s * SLAB_ELEMS, A, lda, kbeg + s * BKK, tid);
-      load_slab<B_KMAJOR>(sB + s * SLAB_ELEMS, B, ldb, kbeg + s * BKK, tid);
+      load_slab<Cfg, A_KMAJOR>(sA + s * SLAB, A, lda, kbeg + s * BK, tid);
+      load_slab<Cfg, B_KMAJOR>(sB + s * SLAB, B, ldb, kbeg + s * BK, tid);
     }
     cp_async_commit();
   }
 
-  TileAcc acc;
+  double acc[MT][NT][2];
   if (Cin != nullptr) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NT; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e)
-          acc.v[i][j][e] = Cin[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ldcin];
+          acc[i][j][e] = Cin[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ldcin];
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc.v[i][j][0] = acc.v[i][j][1] = 0.0;
+      for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   }
 
   for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<GEMM_STAGES - 2>();
+    cp_async_wait<NS - 2>();
     __syncthreads();
     {
-      int nxt = kt + GEMM_STAGES - 1;
+      int nxt = kt + NS - 1;
       if (nxt < nk) {
-        int sb = nxt % GEMM_STAGES;
-        load_slab<A_KMAJOR>(sA + sb * SLAB_ELEMS, A, lda, kbeg + nxt * BKK, tid);
-        load_slab<B_KMAJOR>(sB + sb * SLAB_ELEMS, B, ldb, kbeg + nxt * BKK, tid);
+        int sb = nxt % NS;
+        load_slab<Cfg, A_KMAJOR>(sA + sb * SLAB, A, lda, kbeg + nxt * BK, tid);
+        load_slab<Cfg, B_KMAJOR>(sB + sb * SLAB, B, ldb, kbeg + nxt * BK, tid);
       }
       cp_async_commit();
     }
-    const double* a_s = sA + (kt % GEMM_STAGES) * SLAB_ELEMS;
-    const double* b_s = sB + (kt % GEMM_STAGES) * SLAB_ELEMS;
+    const double* a_s = sA + (kt % NS) * SLAB;
+    const double* b_s = sB + (kt % NS) * SLAB;
 #pragma unroll
-    for (int k4 = 0; k4 < BKK / 4; ++k4) {
-      double a[8], b[4];
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      double a[MT], b[NT];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < MT; ++i) {
         double x = A_KMAJOR ? a_s[(m0 + 8 * i + g) * LD_K + k4 * 4 + t] : a_s[(k4 * 4 + t) * LD_MN + m0 + 8 * i + g];
-        a[i] = negate ? -x : x;
+        a[i] = flip_sign(x, sgn);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NT; ++j)
         b[j] = B_KMAJOR ? b_s[(n0 + 8 * j + g) * LD_K + k4 * 4 + t] : b_s[(k4 * 4 + t) * LD_MN + n0 + 8 * j + g];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
   cp_async_wait<0>();
 
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NT; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e)
-        Cout[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ldc] = acc.v[i][j][e];
+        Cout[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ldc] = acc[i][j][e];
 }
 
 // Decode a linear index into lower-triangle coordinates (i >= j), row-major over rows:

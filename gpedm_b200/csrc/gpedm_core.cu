@@ -20,6 +20,7 @@
 
 #include "../../include/gpedm.h"
 #include "kernels.cuh"
+#include "diag_block.cuh"
 
 using namespace gpedm;
 
@@ -65,7 +66,11 @@ struct gpedm_fit_s {
   double* hscal = nullptr;  // pinned
   int* dinfo = nullptr;
   int* hinfo = nullptr;  // pinned
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux = nullptr;  // high-priority stream for the look-ahead chain (diag, panel, next column)
+  std::vector<cudaEvent_t> evPanel, evTrail;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaEvent_t ev[GPEDM_NPHASE + 1] = {};
   float phase_ms[GPEDM_NPHASE] = {};
   int64_t launches = 0;
@@ -80,15 +85,22 @@ static const int NSCAL = 8 + MAXD + 3;
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 static bool g_attr_set[64] = {};
+static int g_num_sms[64] = {};
+// GPEDM_DIAG_REF=1 selects the simple (slow) reference diagonal-block kernel, for A/B debugging.
+static const bool g_no_lookahead = getenv("GPEDM_NO_LOOKAHEAD") != nullptr && atoi(getenv("GPEDM_NO_LOOKAHEAD")) != 0;
+static const bool g_diag_ref = getenv("GPEDM_DIAG_REF") != nullptr && atoi(getenv("GPEDM_DIAG_REF")) != 0;
 static int ensure_kernel_attrs(int device) {
   if (device < 64 && g_attr_set[device]) return 0;
-  CU(cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(potrf_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(trtri_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(trtri_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(tri_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (device < 64) g_num_sms[device] = prop.multiProcessorCount;
+  }
   CU(cudaFuncSetAttribute(diag_potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_BYTES));
   int trace_smem = (4 * MAXD * TB + 2 * TB + 8 * (MAXD + 3)) * 8 + 2 * TB * 4;
   CU(cudaFuncSetAttribute(grad_trace_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
   CU(cudaFuncSetAttribute(grad_trace_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
@@ -145,6 +157,11 @@ static void free_handle(gpedm_fit_s* h) {
   if (h->hinfo) cudaFreeHost(h->hinfo);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : h->evPanel) cudaEventDestroy(e);
+  for (auto& e : h->evTrail) cudaEventDestroy(e);
+  if (h->evFork) cudaEventDestroy(h->evFork);
+  if (h->evJoin) cudaEventDestroy(h->evJoin);
+  if (h->aux) cudaStreamDestroy(h->aux);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -206,11 +223,25 @@ extern "C" int gpedm_create(int device, int64_t N, int32_t d, int32_t np, const 
   ALLOC(h->dtracepart, (size_t)h->ntiles * (MAXD + 3) * 8);
   ALLOC(h->dscal, NSCAL * 8);
   ALLOC(h->dinfo, 4);
+  h->num_sms = (device < 64 && g_num_sms[device] > 0) ? g_num_sms[device] : 148;
 #undef ALLOC
   cudaError_t e = cudaMallocHost((void**)&h->hparams, sizeof(EvalParams));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hscal, NSCAL * 8);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hinfo, 4);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    e = cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming);
+  h->evPanel.resize(h->nb, nullptr);
+  h->evTrail.resize(h->nb, nullptr);
+  for (int i = 0; i < h->nb && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&h->evPanel[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evTrail[i], cudaEventDisableTiming);
+  }
   for (int i = 0; i <= GPEDM_NPHASE && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
   if (e == cudaSuccess) e = cudaMemcpy(h->dX, X, (size_t)N * d * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(h->dY, 0, Np * 8);
@@ -237,6 +268,30 @@ extern "C" int gpedm_last_phase_ms(gpedm_handle h, float* ms) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------- tile launches
+// layout: 0 = (MN, MN), 1 = (MN, K), 2 = (K, K) operand layouts (see dgemm_tile.cuh).
+static int launch_tiles(gpedm_fit_s* h, cudaStream_t st, const TileOp& op, int layout) {
+  if (op.ntiles <= 0) return 0;
+  if (layout == 0)
+    tile_once_kernel<false, false><<<op.ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op);
+  else if (layout == 1)
+    tile_once_kernel<false, true><<<op.ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op);
+  else
+    tile_once_kernel<true, true><<<op.ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op);
+  h->launches++;
+  return 0;
+}
+
+static TileOp make_op(int type, int ntiles, int nb) {
+  TileOp op;
+  memset(&op, 0, sizeof(op));
+  op.type = type;
+  op.ntiles = ntiles;
+  op.nb = nb;
+  return op;
+}
+
 // ------------------------------------------------------------------------------- pipeline
 // Enqueue the device work of one evaluation on h->stream.  h->hparams must be filled.
 // stages: through z/a (need_inverse_products=false stops after z for the sequential helper).
@@ -254,27 +309,82 @@ static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) 
     h->launches++;
   }
   CU(cudaEventRecord(h->ev[1], st));
-  // --- Cholesky, right-looking over 128-wide block columns
-  for (int k = 0; k < nb; ++k) {
-    diag_potf2_inv_kernel<<<1, 256, DIAG_SMEM_BYTES, st>>>(h->bufA + (size_t)k * TB * (ld + 1), ld,
-                                                            h->bufB + (size_t)k * TB * (ld + 1), ld, k, N,
-                                                            h->dlogdet, h->dinfo);
-    h->launches++;
-    int m = nb - k - 1;
-    if (m > 0) {
-      potrf_panel_kernel<<<m, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->bufA, h->bufB, ld, k);
-      potrf_trail_kernel<<<m*(m + 1) / 2, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->bufA, ld, k, nb, k + 1, nb);
-      h->launches += 2;
+  // --- Cholesky, right-looking over 128-wide block columns, with look-ahead:
+  //   aux (high priority): diag(k) -> panel(k) -> update of column k+1 (needs trailing(k-1))
+  //   main               : trailing update of columns >= k+2 with panel k (needs panel(k))
+  // so the serial chain diag/panel/next-column of step k+1 overlaps the bulk update of step k.
+  {
+    cudaStream_t ax = g_no_lookahead ? st : h->aux;
+    CU(cudaEventRecord(h->evFork, st));
+    CU(cudaStreamWaitEvent(ax, h->evFork, 0));
+    for (int k = 0; k < nb; ++k) {
+      if (g_diag_ref)
+        diag_potf2_inv_kernel<<<1, 256, DIAG_SMEM_BYTES, ax>>>(h->bufA + (size_t)k * TB * (ld + 1), ld,
+                                                                h->bufB + (size_t)k * TB * (ld + 1), ld, k, N,
+                                                                h->dlogdet, h->dinfo);
+      else
+        diag_block_kernel<<<1, DG_THREADS, DG_SMEM_BYTES, ax>>>(h->bufA + (size_t)k * TB * (ld + 1), ld,
+                                                                h->bufB + (size_t)k * TB * (ld + 1), ld, k, N,
+                                                                h->dlogdet, h->dinfo);
+      h->launches++;
+      int m = nb - k - 1;
+      if (m > 0) {
+        TileOp pan = make_op(OP_PANEL, m, nb);
+        pan.k = k;
+        pan.P1 = h->bufB;
+        pan.P2 = h->bufA;
+        pan.ld1 = pan.ld2 = ld;
+        int rc = launch_tiles(h, ax, pan, 0);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->evPanel[k], ax));
+        if (k > 0) CU(cudaStreamWaitEvent(ax, h->evTrail[k - 1], 0));
+        TileOp t1 = make_op(OP_TRAIL, m, nb);  // next block column only
+        t1.k = k;
+        t1.jlo = k + 1;
+        t1.jhi = k + 2;
+        t1.P2 = h->bufA;
+        t1.ld2 = ld;
+        rc = launch_tiles(h, ax, t1, 0);
+        if (rc) return rc;
+        CU(cudaStreamWaitEvent(st, h->evPanel[k], 0));
+        if (m > 1) {
+          TileOp t2 = make_op(OP_TRAIL, m * (m - 1) / 2, nb);
+          t2.k = k;
+          t2.jlo = k + 2;
+          t2.jhi = nb;
+          t2.P2 = h->bufA;
+          t2.ld2 = ld;
+          rc = launch_tiles(h, st, t2, 0);
+          if (rc) return rc;
+        }
+        CU(cudaEventRecord(h->evTrail[k], st));
+      }
     }
+    CU(cudaEventRecord(h->evJoin, ax));
+    CU(cudaStreamWaitEvent(st, h->evJoin, 0));
   }
   CU(cudaEventRecord(h->ev[2], st));
   // --- triangular inverse X = L^-1 by recursive doubling (diagonal blocks already in bufB)
   for (int s = 1; s < nb; s *= 2) {
-    int npairs = ceil_div(nb, 2 * s);
-    int grid = npairs * s * s;
-    trtri_w_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->bufA, h->bufB, h->bufC, ld, nb, s);
-    trtri_x_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->bufB, h->bufC, ld, nb, s);
-    h->launches += 2;
+    const int pf = nb / (2 * s);
+    const int rem = nb - 2 * s * pf;
+    const int ntl = pf * s * s + (rem > s ? (rem - s) * s : 0);
+    TileOp w = make_op(OP_TRTRI_W, ntl, nb);
+    w.s = s;
+    w.P0 = h->bufA;
+    w.P1 = h->bufB;
+    w.P2 = h->bufC;
+    w.ld0 = w.ld1 = w.ld2 = ld;
+    int rc = launch_tiles(h, st, w, 1);
+    if (rc) return rc;
+    TileOp x = make_op(OP_TRTRI_X, ntl, nb);
+    x.s = s;
+    x.P0 = h->bufB;
+    x.P1 = h->bufC;
+    x.P2 = h->bufB;
+    x.ld0 = x.ld1 = x.ld2 = ld;
+    rc = launch_tiles(h, st, x, 1);
+    if (rc) return rc;
   }
   CU(cudaEventRecord(h->ev[3], st));
   // --- z = X Y
@@ -292,8 +402,14 @@ static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) 
   h->launches += 2;
   CU(cudaEventRecord(h->ev[4], st));
   // --- S = Sigma^-1 = X^T X (lower tiles) into bufC
-  lauum_kernel<<<h->ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->bufB, h->bufC, ld, nb);
-  h->launches++;
+  {
+    TileOp lu = make_op(OP_LAUUM, h->ntiles, nb);
+    lu.P0 = h->bufB;
+    lu.P2 = h->bufC;
+    lu.ld0 = lu.ld2 = ld;
+    int rc = launch_tiles(h, st, lu, 2);
+    if (rc) return rc;
+  }
   CU(cudaEventRecord(h->ev[5], st));
   // --- gradient trace terms + scalar reductions
   {
@@ -715,11 +831,20 @@ extern "C" int gpedm_predict_new(gpedm_handle h, int64_t M, const double* Xnew, 
     if (e != cudaSuccess) break;
     rc = launch_cov_rect(h, dV, ldv, h->Np, Mp, 1, (int)mc, dXn, dpn, 0);
     if (rc) break;
-    dim3 grid(h->nb, Mp / TB);
-    tri_apply_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->bufB, ldv, dV, dU, ldv, h->nb);
+    {
+      TileOp ta = make_op(OP_TRI_APPLY, h->nb * (Mp / TB), h->nb);
+      ta.mt = Mp / TB;
+      ta.P0 = h->bufB;
+      ta.P1 = dV;
+      ta.P2 = dU;
+      ta.ld0 = ldv;
+      ta.ld1 = ta.ld2 = ldv;
+      rc = launch_tiles(h, h->stream, ta, 1);
+      if (rc) break;
+    }
     predict_reduce_kernel<<<(unsigned)mc, 256, 0, h->stream>>>(dV, dU, ldv, (int)h->N, (int)mc, h->da, h->dX, dXn,
                                                                 h->dparams, dmean, dvar, dgrad);
-    h->launches += 2;
+    h->launches += 1;
     e = cudaMemcpyAsync(mean + m0, dmean, (size_t)mc * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(var + m0, dvar, (size_t)mc * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && gpgrad) {
@@ -1295,3 +1420,10 @@ extern "C" int gpedm_bench_evals(gpedm_handle h, const double* parst, double mod
   if (*h->hinfo > 0) return set_err(*h->hinfo, "covariance matrix not positive definite at row %d", *h->hinfo);
   return 0;
 }
+
+#ifdef GPEDM_DIAG_TIMING
+extern "C" int gpedm_debug_diag_timing(long long* out) {
+  CU(cudaMemcpyFromSymbol(out, g_diag_ts, sizeof(long long) * 32));
+  return 0;
+}
+#endif

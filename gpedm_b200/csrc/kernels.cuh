@@ -6,6 +6,7 @@
 //   bufC : scratch W during the triangular inverse, then S = Sigma^-1 (lower)
 #pragma once
 #include "dgemm_tile.cuh"
+#include "tile_stream.cuh"
 
 namespace gpedm {
 
@@ -244,102 +245,6 @@ __global__ void __launch_bounds__(256) diag_potf2_inv_kernel(double* __restrict_
     int r = idx & 127, c = idx >> 7;
     Dkk[(size_t)r + (size_t)c * ldd] = (r >= c) ? s[r + c * DIAG_LD] : 0.0;
   }
-}
-
-// -----------------------------------------------------------------------------------------
-// DMMA tile kernels (all launched with GEMM_THREADS threads and GEMM_SMEM_BYTES dynamic smem)
-
-// Panel: L_ik = A_ik * D_k^T for i > k (in place; each CTA is the only reader of its tile).
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-    potrf_panel_kernel(double* __restrict__ A, const double* __restrict__ Bx, size_t ld, int k) {
-  extern __shared__ double smem[];
-  const int i = k + 1 + blockIdx.x;
-  double* At = A + (size_t)i * TB + (size_t)k * TB * ld;
-  const double* Dk = Bx + (size_t)k * TB + (size_t)k * TB * ld;
-  gemm_tile<false, false>(At, ld, Dk, ld, 0, TB, false, nullptr, 0, At, ld, smem);
-}
-
-// Trailing update: A_ij -= L_ik L_jk^T for jlo <= j <= i < nb, j < jhi (lower tiles).
-// Tiles are enumerated column-block by column-block so that a look-ahead launch can take
-// just the first column (jhi = jlo + 1).
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-    potrf_trail_kernel(double* __restrict__ A, size_t ld, int k, int nb, int jlo, int jhi) {
-  extern __shared__ double smem[];
-  // decode blockIdx.x -> (i, j): columns j = jlo..jhi-1, each with (nb - j) tiles
-  int t = blockIdx.x;
-  int j = jlo;
-  while (t >= nb - j) {
-    t -= nb - j;
-    ++j;
-  }
-  (void)jhi;
-  const int i = j + t;
-  const double* Pi = A + (size_t)i * TB + (size_t)k * TB * ld;
-  const double* Pj = A + (size_t)j * TB + (size_t)k * TB * ld;
-  double* Ct = A + (size_t)i * TB + (size_t)j * TB * ld;
-  gemm_tile<false, false>(Pi, ld, Pj, ld, 0, TB, true, Ct, ld, Ct, ld, smem);
-}
-
-// Triangular inverse, recursive doubling level with block size s (in tiles):
-//   W  = L21 * X11      (into bufC at the position of block (2,1))
-//   X21 = -X22 * W      (into bufB)
-// for every pair p covering tile rows/cols [2ps, 2ps+2s).
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-    trtri_w_kernel(const double* __restrict__ L, const double* __restrict__ X, double* __restrict__ W, size_t ld,
-                   int nb, int s) {
-  extern __shared__ double smem[];
-  const int per = s * s;
-  const int p = blockIdx.x / per, rem = blockIdx.x % per;
-  const int j = rem / s, i = rem % s;  // ascending j first: longest k range first
-  const int o = p * 2 * s;
-  if (o + s >= nb) return;
-  const int s2 = min(s, nb - (o + s));
-  if (i >= s2) return;
-  const double* At = L + (size_t)(o + s + i) * TB + (size_t)o * TB * ld;
-  const double* Bt = X + (size_t)o * TB + (size_t)(o + j) * TB * ld;
-  double* Ct = W + (size_t)(o + s + i) * TB + (size_t)(o + j) * TB * ld;
-  gemm_tile<false, true>(At, ld, Bt, ld, j * TB, s * TB, false, nullptr, 0, Ct, ld, smem);
-}
-
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-    trtri_x_kernel(double* __restrict__ X, const double* __restrict__ W, size_t ld, int nb, int s) {
-  extern __shared__ double smem[];
-  const int per = s * s;
-  const int p = blockIdx.x / per, rem = blockIdx.x % per;
-  const int i = s - 1 - rem / s, j = rem % s;  // descending i first: longest k range first
-  const int o = p * 2 * s;
-  if (o + s >= nb) return;
-  const int s2 = min(s, nb - (o + s));
-  if (i >= s2) return;
-  const double* At = X + (size_t)(o + s + i) * TB + (size_t)(o + s) * TB * ld;
-  const double* Bt = W + (size_t)(o + s) * TB + (size_t)(o + j) * TB * ld;
-  double* Ct = X + (size_t)(o + s + i) * TB + (size_t)(o + j) * TB * ld;
-  gemm_tile<false, true>(At, ld, Bt, ld, 0, (i + 1) * TB, true, nullptr, 0, Ct, ld, smem);
-}
-
-// S = X^T X on the lower tiles (X lower triangular): S_ij = sum_{k >= i} X_ki^T X_kj.
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-    lauum_kernel(const double* __restrict__ X, double* __restrict__ S, size_t ld, int nb) {
-  extern __shared__ double smem[];
-  int i, j;
-  tri_decode(blockIdx.x, i, j);  // ascending i: longest k range first
-  const double* At = X + (size_t)i * TB * ld;
-  const double* Bt = X + (size_t)j * TB * ld;
-  double* Ct = S + (size_t)i * TB + (size_t)j * TB * ld;
-  gemm_tile<true, true>(At, ld, Bt, ld, i * TB, nb * TB, false, nullptr, 0, Ct, ld, smem);
-}
-
-// U = X * V for prediction (X = L^-1 lower, V = Cs^T padded to Np x Mp): tile (i, jt),
-// k range [0, (i+1)*128).
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-    tri_apply_kernel(const double* __restrict__ X, size_t ldx, const double* __restrict__ V, double* __restrict__ U,
-                     size_t ldv, int nb) {
-  extern __shared__ double smem[];
-  const int i = nb - 1 - blockIdx.x, jt = blockIdx.y;
-  const double* At = X + (size_t)i * TB;
-  const double* Bt = V + (size_t)jt * TB * ldv;
-  double* Ct = U + (size_t)i * TB + (size_t)jt * TB * ldv;
-  gemm_tile<false, true>(At, ldx, Bt, ldv, 0, (i + 1) * TB, false, nullptr, 0, Ct, ldv, smem);
 }
 
 // -----------------------------------------------------------------------------------------

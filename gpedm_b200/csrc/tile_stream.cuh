@@ -1,0 +1,172 @@
+// Tile operations of the evaluation pipeline.  Every O(N^3) step (Cholesky panel and trailing
+// update, triangular inverse, L^-T L^-1 product, prediction solve) is a set of independent
+// 128x128 output tiles  C = (+/-) sum_k Aop Bop (+ C)  with tile-dependent k ranges.  One launch =
+// one such set, described by a POD `TileOp`; `decode_tile` maps a tile index to operand origins
+// (longest k range first, so the hardware block scheduler balances the tail) and `tile_once_kernel`
+// runs the DMMA contraction of dgemm_tile.cuh on it.
+#pragma once
+#include "dgemm_tile.cuh"
+
+namespace gpedm {
+
+enum TileOpType {
+  OP_PANEL = 0,     // L_ik = A_ik D_k^T, i > k                         (MN, MN)
+  OP_TRAIL = 1,     // A_ij -= L_ik L_jk^T, jlo <= j < jhi, i >= j      (MN, MN)
+  OP_TRTRI_W = 2,   // W = L21 X11   (pairs of size s)                  (MN, K)
+  OP_TRTRI_X = 3,   // X21 = -X22 W                                     (MN, K)
+  OP_LAUUM = 4,     // S_ij = sum_{k>=i} X_ki^T X_kj, i >= j            (K, K)
+  OP_TRI_APPLY = 5  // U = X V  (X lower triangular, V = N x M)         (MN, K)
+};
+
+struct TileOp {
+  int type;
+  int ntiles;
+  int nb;        // tiles per matrix edge
+  int k;         // block column (panel / trail)
+  int s;         // trtri block size in tiles
+  int jlo, jhi;  // trail column range
+  int mt;        // tri_apply: number of column tiles of V
+  const double* P0;  // operand matrices (meaning depends on type)
+  const double* P1;
+  double* P2;
+  size_t ld0, ld1, ld2;
+};
+
+// What the kernel needs to know about one tile.  Strides are per-launch constants (TileOp) so
+// they stay out of the per-tile register state.
+struct TileWork {
+  const double* A;  // operand tile origins, already advanced to the first k slab
+  const double* B;
+  double* C;        // output tile (also the accumulate-from tile when flags & 2)
+  int nslab;        // number of BK-wide k slabs
+  int flags;        // bit0: negate the product, bit1: accumulate onto C
+};
+
+// tiles of the lower triangle of an m x m tile grid enumerated column by column:
+// column c holds rows c..m-1; returns (row, col) of linear index t.
+__device__ __forceinline__ void colmajor_tri_decode(int t, int m, int& row, int& col) {
+  double b = 2.0 * m + 1.0;
+  int c = (int)((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
+  if (c < 0) c = 0;
+  if (c > m - 1) c = m - 1;
+  while (c > 0 && (long long)c * m - (long long)c * (c - 1) / 2 > t) --c;
+  while (c < m - 1 && (long long)(c + 1) * m - (long long)(c + 1) * c / 2 <= t) ++c;
+  col = c;
+  row = c + (t - (c * m - c * (c - 1) / 2));
+}
+
+// Operand strides of a launch: lda/ldb apply to the A/B operands, ldc to the output.
+__device__ __forceinline__ void op_strides(const TileOp& op, size_t& lda, size_t& ldb, size_t& ldc) {
+  switch (op.type) {
+    case OP_PANEL: lda = op.ld2; ldb = op.ld1; ldc = op.ld2; break;
+    case OP_TRAIL: lda = ldb = ldc = op.ld2; break;
+    case OP_LAUUM: lda = ldb = op.ld0; ldc = op.ld2; break;
+    default: lda = op.ld0; ldb = op.ld1; ldc = op.ld2; break;
+  }
+}
+
+// Tile t of a launch -> operand origins and k range.  A_KMAJOR/B_KMAJOR say how a k offset moves
+// the operand pointers.  Kept out of line: it runs once per tile, not per slab.
+template <bool A_KMAJOR, bool B_KMAJOR, int BK>
+__device__ __forceinline__ bool decode_tile(const TileOp& op, int t, TileWork& w) {
+  if (t >= op.ntiles) {
+    w.nslab = 0;
+    return false;
+  }
+  const double *A, *B;
+  double* C;
+  size_t lda, ldb, ldc;
+  op_strides(op, lda, ldb, ldc);
+  int kbeg = 0, kend = TB, flags = 0;
+  switch (op.type) {
+    case OP_PANEL: {
+      const int i = op.k + 1 + t;
+      C = op.P2 + (size_t)i * TB + (size_t)op.k * TB * ldc;
+      A = C;
+      B = op.P1 + (size_t)op.k * TB + (size_t)op.k * TB * ldb;  // D_k
+      break;
+    }
+    case OP_TRAIL: {
+      int r, c;
+      colmajor_tri_decode(t, op.nb - op.jlo, r, c);
+      const int i = op.jlo + r, j = op.jlo + c;
+      A = op.P2 + (size_t)i * TB + (size_t)op.k * TB * ldc;
+      B = op.P2 + (size_t)j * TB + (size_t)op.k * TB * ldc;
+      C = op.P2 + (size_t)i * TB + (size_t)j * TB * ldc;
+      flags = 3;
+      break;
+    }
+    case OP_TRTRI_W:
+    case OP_TRTRI_X: {
+      // pairs p cover tile rows/cols [2ps, 2ps+2s); all but possibly the last are full (s x s
+      // tiles), the last may have only s2 < s rows (ragged nb).  No empty tiles are enumerated.
+      const int s = op.s, per = s * s;
+      const int pf = op.nb / (2 * s);
+      int p, rem, s2;
+      if (t < pf * per) {
+        p = t / per;
+        rem = t % per;
+        s2 = s;
+      } else {
+        p = pf;
+        rem = t - pf * per;
+        s2 = op.nb - 2 * s * pf - s;
+      }
+      const int o = p * 2 * s;
+      if (op.type == OP_TRTRI_W) {
+        const int j = rem / s2, i = rem % s2;  // ascending j: longest k range first
+        A = op.P0 + (size_t)(o + s + i) * TB + (size_t)o * TB * lda;   // L21 row block
+        B = op.P1 + (size_t)o * TB + (size_t)(o + j) * TB * ldb;       // X11 column block
+        C = op.P2 + (size_t)(o + s + i) * TB + (size_t)(o + j) * TB * ldc;
+        kbeg = j * TB;
+        kend = s * TB;
+      } else {
+        const int i = s2 - 1 - rem / s, j = rem % s;  // descending i: longest k range first
+        A = op.P0 + (size_t)(o + s + i) * TB + (size_t)(o + s) * TB * lda;  // X22 row block
+        B = op.P1 + (size_t)(o + s) * TB + (size_t)(o + j) * TB * ldb;      // W column block
+        C = op.P2 + (size_t)(o + s + i) * TB + (size_t)(o + j) * TB * ldc;
+        kend = (i + 1) * TB;
+        flags = 1;
+      }
+      break;
+    }
+    case OP_LAUUM: {
+      int i, j;
+      tri_decode(t, i, j);  // ascending i: longest k range first
+      A = op.P0 + (size_t)i * TB * lda;
+      B = op.P0 + (size_t)j * TB * ldb;
+      C = op.P2 + (size_t)i * TB + (size_t)j * TB * ldc;
+      kbeg = i * TB;
+      kend = op.nb * TB;
+      break;
+    }
+    default: {  // OP_TRI_APPLY
+      const int i = op.nb - 1 - t / op.mt, jt = t % op.mt;
+      A = op.P0 + (size_t)i * TB;
+      B = op.P1 + (size_t)jt * TB * ldb;
+      C = op.P2 + (size_t)i * TB + (size_t)jt * TB * ldc;
+      kend = (i + 1) * TB;
+      break;
+    }
+  }
+  w.A = A + (A_KMAJOR ? (size_t)kbeg : (size_t)kbeg * lda);
+  w.B = B + (B_KMAJOR ? (size_t)kbeg : (size_t)kbeg * ldb);
+  w.C = C;
+  w.nslab = (kend - kbeg) / BK;
+  w.flags = flags;
+  return true;
+}
+
+// One tile per CTA (grid = ntiles, hardware block scheduler hands out tiles in launch order).
+template <bool A_KMAJOR, bool B_KMAJOR, class Cfg = GemmCfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) tile_once_kernel(const TileOp op) {
+  extern __shared__ double smem[];
+  TileWork w;
+  if (!decode_tile<A_KMAJOR, B_KMAJOR, Cfg::BK>(op, blockIdx.x, w)) return;
+  size_t lda, ldb, ldc;
+  op_strides(op, lda, ldb, ldc);
+  gemm_tile<A_KMAJOR, B_KMAJOR, Cfg>(w.A, lda, w.B, ldb, 0, w.nslab * Cfg::BK, (w.flags & 1) != 0,
+                                     (w.flags & 2) ? w.C : nullptr, ldc, w.C, ldc, smem);
+}
+
+}  // namespace gpedm
