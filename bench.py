@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the GP log-posterior + gradient hot path.
+
+Metric (BASELINE.json): GP log-posterior+gradient evaluations / second at the N=8192, E=10 member
+of the model-selection grid (series length 8192, E=10, tau=1 -> N=8182 complete rows, d=10),
+synthetic Ricker series, FP64.  A "step" is one evaluation (getlikegrad with returngradonly=TRUE,
+reference R/GPfunctions.R:586-725) at fitGP's default start.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid]
+
+N > 1 is launched by the driver with torchrun (one process per GPU); every rank evaluates its own
+independent grid member (weak scaling: the path shards across fits with no data-path collective),
+rank 0 prints one JSON line with the whole-job evaluation rate (max-over-ranks device time).
+`--grid` additionally times the full batched fitGP grid (E=1..10 x tau=1..4, 40 fits, LOO
+predictions) sharded over the ranks, with one all-gather of the result records.
+`--impl reference` times the CPU restatement of the reference (oracle/, LAPACK dpotrf + dpotri
+with all host threads) on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SERIES_LEN, E, TAU, SEED = 8192, 10, 1, 1004
+METRIC = "gp_logpost_grad_evals_per_sec"
+UNIT = "evals/s"
+
+
+def workload(rank=0):
+    from gpedm_b200 import synth
+    from gpedm_b200.batch import default_initparst
+    Y, X = synth.embed(synth.ricker(SERIES_LEN, SEED + 17 * rank), E, TAU)
+    return Y, X, default_initparst(E, True)
+
+
+def config(N):
+    return {"workload": "C4 grid member: synthetic Ricker series len %d, E=%d, tau=%d -> N=%d rows, d=%d, "
+                        "default initpars (R/GPfunctions.R:409); inputs %.0f MB per matrix > L2"
+                        % (SERIES_LEN, E, TAU, N, E, N * N * 8 / 1e6),
+            "N": int(N), "d": E, "series_len": SERIES_LEN, "tau": TAU, "seed": SEED,
+            "l2": "inputs larger than L2 (3 N x N FP64 work matrices of %.0f MB each)" % (N * N * 8 / 1e6),
+            "parallelism": "independent fits sharded across GPUs; no data-path collective"}
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [s.split(", ") for t, s in self.samples if t0 <= t <= t1 + 0.15] or [s.split(", ") for _, s in self.samples]
+        mhz, reasons, mx, pw = [], set(), None, []
+        for r in rows:
+            try:
+                mhz.append(float(r[0]))
+                mx = float(r[1])
+                pw.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "samples": len(mhz),
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------- reference arm
+def time_reference_eval(Y, X, p0, D=None):
+    """One gradient-only evaluation of the CPU restatement (oracle.getlikegrad: LAPACK dpotrf+dpotri via
+    scipy, the per-coordinate distance matrices precomputed once as fmingrad_Rprop does, :539-542)."""
+    from oracle import gpedm_oracle as O
+    d = X.shape[1]
+    if D is None:
+        D = [O.distance(X[:, i]) for i in range(d)]
+    t = time.perf_counter()
+    out = O.getlikegrad(p0, Y, X, np.ones(len(Y), dtype=int), 1, np.full(d + 2, np.nan), None, None, D, True)
+    return time.perf_counter() - t, out, D
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Y, X, p0 = workload(0)
+    N = len(Y)
+    cores = os.cpu_count()
+    budget = 200.0
+    t_start = time.perf_counter()
+    t_first, out, D = time_reference_eval(Y, X, p0)  # first evaluation = warm-up (builds the distance list)
+    warm = 1
+    while warm < args.warmup and t_first * (warm + 2) < 0.25 * budget:
+        time_reference_eval(Y, X, p0, D)
+        warm += 1
+    times = []
+    while len(times) < max(1, args.steps) and (not times or time.perf_counter() - t_start + times[-1] < budget):
+        t, out, _ = time_reference_eval(Y, X, p0, D)
+        times.append(t)
+    ms = 1e3 * float(np.mean(times))
+    val = 1e3 / ms
+    sample = ("%d full-size evaluations (N=%d, d=%d) after %d warm-up; numpy/scipy OpenBLAS on all %d host threads; "
+              "time budget capped the run" % (len(times), N, E, warm, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(times), "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(N),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "nll": out["nllpost"]}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import gpedm_b200 as G
+    from gpedm_b200 import _lib, dist as gd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    Y, X, p0 = workload(rank)
+    N = len(Y)
+    model = G.GPModel(Y, X, device=local)
+    sampler = ClockSampler(local)
+
+    # ---- warm-up (untimed), then K device-timed steps with inputs resident in HBM
+    for _ in range(max(3, args.warmup)):
+        model.likegrad(p0, 1.0, None, None, True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    l0 = model.launch_count()
+    barrier()
+    t0 = time.time()
+    ms_per_eval = model.bench_evals(p0, 1.0, args.steps)  # CUDA events on the library's stream
+    barrier()
+    t1 = time.time()
+    launches = model.launch_count() - l0
+    phases = model.phase_ms()
+    step_ms = torch.tensor([ms_per_eval], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
+    step_ms = float(step_ms.item())
+    value = world * 1e3 / step_ms
+
+    # ---- end to end through the public API with HOST buffers: every step re-uploads Y, X, pop and
+    # the parameters from host memory and reads the result record back
+    codes = model.codes
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.set_data(Y, X, codes)
+        res = model.likegrad(p0, 1.0, None, None, True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - te0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = world * args.steps / float(e2e_t.item())
+    h2d = N * E * 8 + N * 8 + N * 4 + 544  # X, Y, pop codes, parameter block
+    d2h = (8 + 35) * 8 + 4                 # scalar/trace reductions + pivot flag
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+
+    grid = None
+    if args.grid:
+        grid = run_grid(G, gd, world, rank, local, barrier)
+
+    if rank == 0:
+        peak_dmma = G.fp64_peak(0, local)
+        peak_dfma = G.fp64_peak(1, local)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        n3 = float(N) ** 3
+        lauum_tf = n3 / 3 / (phases["lauum"] * 1e-3) * 1e-12
+        roof = {"bound": "tensor", "kernel": "tile_once_kernel<K,K> (lauum: Sigma^-1 = L^-T L^-1, one launch, N^3/3 flop)",
+                "achieved": lauum_tf, "peak": peak_dmma, "unit": "TFLOP/s", "frac": lauum_tf / peak_dmma,
+                "traffic": None,
+                "peak_source": "live FP64 DMMA m8n8k4 issue-rate probe (gpedm_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "eval": {"flops_per_eval": n3, "achieved": n3 / (step_ms * 1e-3) * 1e-12, "frac": n3 / (step_ms * 1e-3) * 1e-12 / peak_dmma},
+                "phases_ms": phases,
+                "phase_tflops": {"potrf": n3 / 3 / (phases["potrf"] * 1e-3) * 1e-12,
+                                 "trtri": n3 / 3 / (phases["trtri"] * 1e-3) * 1e-12,
+                                 "lauum": lauum_tf},
+                "hbm_kernels": {"assemble_GBs": 4.0 * N * (N + 1) / (phases["assemble"] * 1e-3) * 1e-9,
+                                "trace_GBs": 4.0 * N * (N + 1) / (phases["trace"] * 1e-3) * 1e-9,
+                                "hbm_peak_GBs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+                "dfma_peak": peak_dfma}
+        cpu = None
+        if not args.no_cpu_baseline:
+            t, out, _ = time_reference_eval(Y, X, p0)
+            cpu = {"value": 1.0 / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": "1 full-size evaluation (N=%d, d=%d) of oracle.getlikegrad (LAPACK dpotrf+dpotri, OpenBLAS, "
+                             "all host threads), distance matrices precomputed as in fmingrad_Rprop" % (N, E),
+                   "nll_rel_diff_vs_gpu": abs(out["nllpost"] - res["nllpost"]) / abs(out["nllpost"])}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(N),
+                "roofline": roof, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "clocks": clocks, "nll": res["nllpost"]}
+        if grid is not None:
+            line["grid"] = grid
+        print(json.dumps(line))
+    model.close()
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_grid(G, gd, world, rank, local, barrier):
+    """Batched fitGP over E=1..10 x tau=1..4 at series length 8192 (40 independent fits with
+    closed-form LOO), sharded over the ranks; one all-gather of the fixed-width result records."""
+    import torch
+    from gpedm_b200 import batch, synth
+    from gpedm_b200.fitgp import getR2
+    y = synth.ricker(SERIES_LEN, SEED)
+    probs, meta = batch.grid_problems(y, list(range(1, 11)), [1, 2, 3, 4])
+    costs = [float(len(p["Y"])) ** 3 for p in probs]
+    mine = gd.shard_indices(len(probs), world, rank, costs)
+    barrier()
+    t0 = time.perf_counter()
+    res = G.fit_batch([probs[i] for i in mine], ngpus=1, devices=[local], want_loo=True)
+    torch.cuda.synchronize()
+    local_s = time.perf_counter() - t0
+    allres = gd.gather_records(list(zip(mine, res)), len(probs), device=torch.device("cuda", local))
+    barrier()
+    wall = time.perf_counter() - t0
+    r2 = {}
+    for i, r in zip(mine, res):
+        m = meta[i]
+        r2[i] = getR2(m["yobs"], r["loo_mean"] * m["ysd"] + m["ymean"])
+    if rank != 0:
+        return None
+    best = max(r2, key=r2.get) if r2 else None
+    return {"fits": len(probs), "wall_s": wall, "rank0_local_s": local_s,
+            "total_evals": int(sum(r["nevals"] for r in allres)),
+            "iters": [int(r["iter"]) for r in allres], "status_ok": all(r["status"] == 0 for r in allres),
+            "rank0_best": None if best is None else {"E": meta[best]["E"], "tau": meta[best]["tau"], "R2_loo": r2[best]}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", action="store_true", help="also time the 40-fit E x tau grid")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

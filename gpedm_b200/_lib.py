@@ -65,7 +65,7 @@ class FitDesc(C.Structure):
 # every symbol include/gpedm.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "gpedm_abi_version", "gpedm_last_error", "gpedm_device_count", "gpedm_default_rprop_options",
-    "gpedm_create", "gpedm_destroy", "gpedm_n", "gpedm_likegrad", "gpedm_fit_rprop", "gpedm_get_vector",
+    "gpedm_create", "gpedm_set_data", "gpedm_destroy", "gpedm_n", "gpedm_likegrad", "gpedm_fit_rprop", "gpedm_get_vector",
     "gpedm_get_matrix", "gpedm_getcov", "gpedm_predict_new", "gpedm_predict_loo", "gpedm_predict_lto",
     "gpedm_predict_sequential", "gpedm_fit_batch", "gpedm_last_phase_ms", "gpedm_launch_count",
     "gpedm_fp64_peak", "gpedm_bench_evals",
@@ -108,6 +108,7 @@ def lib():
     L.gpedm_device_count.restype = C.c_int
     L.gpedm_default_rprop_options.argtypes = [C.POINTER(RpropOptions)]
     L.gpedm_create.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_int32, dp, dp, ip, dp, C.POINTER(C.c_void_p)]
+    L.gpedm_set_data.argtypes = [C.c_void_p, dp, dp, ip]
     L.gpedm_destroy.argtypes = [C.c_void_p]
     L.gpedm_n.argtypes = [C.c_void_p]
     L.gpedm_n.restype = C.c_int64

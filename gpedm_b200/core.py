@@ -87,6 +87,14 @@ class GPModel:
         check(lib().gpedm_create(device, self.N, self.d, self.np_, dptr(X), dptr(Y), iptr(self.codes),
                                  dptr(self.rhomat), C.byref(self._h)))
 
+    def set_data(self, Y, X, codes=None):
+        """Re-upload host Y / X (/ population codes) into the resident handle (same shapes)."""
+        Y = f64(Y).ravel()
+        X = f64(np.asarray(X, dtype=np.float64).reshape(self.N, self.d))
+        codes = self.codes if codes is None else np.ascontiguousarray(codes, dtype=np.int32)
+        check(lib().gpedm_set_data(self._h, dptr(X), dptr(Y), iptr(codes)))
+        self.Y, self.X, self.codes = Y, X, codes
+
     # -- lifetime
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

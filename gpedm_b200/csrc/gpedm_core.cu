@@ -256,6 +256,24 @@ extern "C" int gpedm_create(int device, int64_t N, int32_t d, int32_t np, const 
   return 0;
 }
 
+extern "C" int gpedm_set_data(gpedm_handle h, const double* X, const double* Y, const int32_t* pop) {
+  if (!h || !X || !Y || !pop) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  for (int64_t i = 0; i < h->N; ++i)
+    if (pop[i] < 0 || pop[i] >= h->np) return set_err(GPEDM_ERR_ARG, "pop[%lld]=%d outside 0..np-1", (long long)i, pop[i]);
+  CU(cudaSetDevice(h->device));
+  h->have_full = false;
+  CU(cudaMemcpyAsync(h->dX, X, (size_t)h->N * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->dY, Y, (size_t)h->N * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->dpop, pop, (size_t)h->N * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->hY.assign(Y, Y + h->N);
+  h->hpop.assign(pop, pop + h->N);
+  h->single_pop = true;
+  for (int64_t i = 1; i < h->N; ++i)
+    if (pop[i] != pop[0]) h->single_pop = false;
+  return 0;
+}
+
 extern "C" int gpedm_destroy(gpedm_handle h) {
   free_handle(h);
   return 0;

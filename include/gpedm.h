@@ -87,6 +87,10 @@ void gpedm_default_rprop_options(gpedm_rprop_options* opts);
  * like the codes; NULL = single rho).  N >= 1, 1 <= d <= GPEDM_MAX_D. */
 int gpedm_create(int device, int64_t N, int32_t d, int32_t np, const double* X, const double* Y,
                  const int32_t* pop, const double* rhomat, gpedm_handle* out);
+/* Replace the training set of an existing handle (same N, d, np) without reallocating: the
+ * host->device copy a caller pays when it re-enters with fresh host buffers, as every R-level
+ * call of getlikegrad does (reference R/GPfunctions.R:545, :560, :580). */
+int gpedm_set_data(gpedm_handle h, const double* X, const double* Y, const int32_t* pop);
 int gpedm_destroy(gpedm_handle h);
 int64_t gpedm_n(gpedm_handle h);
 
