@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -94,6 +94,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- reference arm
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is entitled to every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+
+
 def time_reference_eval(Y, X, p0, D=None):
     """One gradient-only evaluation of the CPU restatement (oracle.getlikegrad: LAPACK dpotrf+dpotri via
     scipy, the per-coordinate distance matrices precomputed once as fmingrad_Rprop does, :539-542)."""
@@ -110,6 +119,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     Y, X, p0 = workload(0)
     N = len(Y)
     cores = os.cpu_count()
@@ -202,7 +212,7 @@ def run_ours(args):
     e2e_val = world * args.steps / float(e2e_t.item())
     h2d = N * E * 8 + N * 8 + N * 4 + 544  # X, Y, pop codes, parameter block
     d2h = (8 + 35) * 8 + 4                 # scalar/trace reductions + pivot flag
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    clocks = sampler.stop(t0, time.time()) if rank == 0 else None
 
     grid = None
     if args.grid:
@@ -234,6 +244,7 @@ def run_ours(args):
                 "dfma_peak": peak_dfma}
         cpu = None
         if not args.no_cpu_baseline:
+            use_all_host_threads()
             t, out, _ = time_reference_eval(Y, X, p0)
             cpu = {"value": 1.0 / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                    "sample": "1 full-size evaluation (N=%d, d=%d) of oracle.getlikegrad (LAPACK dpotrf+dpotri, OpenBLAS, "

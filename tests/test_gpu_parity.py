@@ -372,3 +372,15 @@ def test_phi_gradient_half_quirk(gpu_lib):
         dlp = (a["lp"] - b["lp"]) / (2 * h)
         assert -(0.5 * dlike + dlp) == pytest.approx(r["grad"][k], rel=1e-5)
     m.close()
+
+
+def test_batch_two_gpus_nccl_gather(gpu_lib):
+    """In-library multi-GPU batch: worker thread per GPU + ONE ncclAllGather of the result records."""
+    if gpu_lib.gpedm_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    y = synth.ricker(400, 5)
+    probs, _ = batch.grid_problems(y, [1, 2, 3, 4], [1, 2])
+    one = G.fit_batch(probs, ngpus=1)
+    two = G.fit_batch(probs, ngpus=2)
+    for a, b in zip(one, two):
+        assert a["iter"] == b["iter"] and a["nllpost"] == b["nllpost"] and np.array_equal(a["pars"], b["pars"])
