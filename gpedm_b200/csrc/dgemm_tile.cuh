@@ -27,23 +27,31 @@ namespace gpedm {
 
 constexpr int TB = 128;  // tile edge
 
-// Compile-time shape of the contraction kernel.  WM x WN warps, each owning a
-// (128/WM) x (128/WN) sub-tile; k slabs of BK columns, NSTAGE-deep cp.async pipeline.
-template <int WM_, int WN_, int BK_, int NSTAGE_>
+// Compile-time shape of the contraction kernel: a TM x 128 output tile computed by WM x WN warps,
+// each owning a (TM/WM) x (128/WN) sub-tile; k slabs of BK columns, NSTAGE-deep cp.async pipeline.
+// TM = 128 is the bulk shape; TM = 32 splits one 128 x 128 tile over four CTAs for the
+// latency-critical chain of the Cholesky (panel + next-column update), where there are fewer
+// tiles than SMs.
+template <int WM_, int WN_, int BK_, int NSTAGE_, int TM_ = 128>
 struct GemmCfgT {
-  static constexpr int WM = WM_, WN = WN_, BK = BK_, NSTAGE = NSTAGE_;
+  static constexpr int WM = WM_, WN = WN_, BK = BK_, NSTAGE = NSTAGE_, TM = TM_;
   static constexpr int THREADS = WM * WN * 32;
-  static constexpr int MT = TB / WM / 8;  // 8-row DMMA tiles per warp along m
+  static constexpr int MT = TM / WM / 8;  // 8-row DMMA tiles per warp along m
   static constexpr int NT = TB / WN / 8;  // 8-col DMMA tiles per warp along n
-  static constexpr int LD_MN = TB + 4;    // smem row stride (doubles) of an MN-major slab [BK][LD_MN]
-  static constexpr int LD_K = BK + 4;     // smem row stride (doubles) of a  K-major slab [TB][LD_K]
-  static constexpr int SLAB = (BK * LD_MN > TB * LD_K) ? BK * LD_MN : TB * LD_K;
-  static constexpr int SMEM_BYTES = NSTAGE * 2 * SLAB * (int)sizeof(double);
+  static constexpr int LD_MN_A = TM + 4;  // smem row stride (doubles) of an MN-major A slab [BK][TM+4]
+  static constexpr int LD_MN_B = TB + 4;  // ... of an MN-major B slab [BK][132]
+  static constexpr int LD_K = BK + 4;     // smem row stride of a K-major slab [rows][BK+4]
+  static constexpr int SLAB_A = (BK * LD_MN_A > TM * LD_K) ? BK * LD_MN_A : TM * LD_K;
+  static constexpr int SLAB_B = (BK * LD_MN_B > TB * LD_K) ? BK * LD_MN_B : TB * LD_K;
+  static constexpr int SMEM_BYTES = NSTAGE * (SLAB_A + SLAB_B) * (int)sizeof(double);
+  static_assert(TM % (WM * 8) == 0 && TB % (WN * 8) == 0, "warp grid must tile the output");
+  static_assert((TM + 4) % 16 == 4 && (BK + 4) % 16 == 4, "strides must be 4 mod 16 for conflict-free LDS.64");
 };
 #ifndef GPEDM_GEMM_CFG
 #define GPEDM_GEMM_CFG GemmCfgT<2, 4, 16, 4>
 #endif
 using GemmCfg = GPEDM_GEMM_CFG;
+using GemmCfgSplit = GemmCfgT<1, 8, 16, 4, 32>;  // 32 x 128 tiles, 8 warps of 32 x 16
 constexpr int GEMM_THREADS = GemmCfg::THREADS;
 constexpr int GEMM_SMEM_BYTES = GemmCfg::SMEM_BYTES;
 
@@ -67,27 +75,30 @@ __device__ __forceinline__ double flip_sign(double x, unsigned mask) {
   return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
 }
 
-// Stage one BK-wide k slab of a 128-row operand into shared memory.
-template <class Cfg, bool KMAJOR>
+// Stage one BK-wide k slab of a ROWS-row operand into shared memory.
+template <class Cfg, bool KMAJOR, int ROWS>
 __device__ __forceinline__ void load_slab(double* __restrict__ s, const double* __restrict__ g, size_t ld,
                                           int k0, int tid) {
-  constexpr int CHUNKS = TB * Cfg::BK / 2;  // 16-byte chunks per slab
+  constexpr int CHUNKS = ROWS * Cfg::BK / 2;  // 16-byte chunks per slab
+  constexpr int ITERS = (CHUNKS + Cfg::THREADS - 1) / Cfg::THREADS;
   if (!KMAJOR) {
-    // global: BK columns (k) of 128 contiguous doubles.
+    // global: BK columns (k) of ROWS contiguous doubles.
+    constexpr int CPR = ROWS / 2;  // chunks per k row
+    constexpr int LDS = ROWS + 4;
 #pragma unroll
-    for (int r = 0; r < (CHUNKS + Cfg::THREADS - 1) / Cfg::THREADS; ++r) {
+    for (int r = 0; r < ITERS; ++r) {
       int chunk = tid + r * Cfg::THREADS;
       if (CHUNKS % Cfg::THREADS == 0 || chunk < CHUNKS) {
-        int row = chunk >> 6;        // k within slab
-        int c2 = (chunk & 63) << 1;  // m offset
-        cp_async16(s + row * Cfg::LD_MN + c2, g + (size_t)(k0 + row) * ld + c2);
+        int row = chunk / CPR;         // k within slab
+        int c2 = (chunk % CPR) << 1;   // m offset
+        cp_async16(s + row * LDS + c2, g + (size_t)(k0 + row) * ld + c2);
       }
     }
   } else {
-    // global: 128 columns (m) of BK contiguous doubles (k).
-    constexpr int CPR = Cfg::BK / 2;  // chunks per row
+    // global: ROWS columns (m) of BK contiguous doubles (k).
+    constexpr int CPR = Cfg::BK / 2;  // chunks per m row
 #pragma unroll
-    for (int r = 0; r < (CHUNKS + Cfg::THREADS - 1) / Cfg::THREADS; ++r) {
+    for (int r = 0; r < ITERS; ++r) {
       int chunk = tid + r * Cfg::THREADS;
       if (CHUNKS % Cfg::THREADS == 0 || chunk < CHUNKS) {
         int row = chunk / CPR;         // m
@@ -98,31 +109,32 @@ __device__ __forceinline__ void load_slab(double* __restrict__ s, const double* 
   }
 }
 
-// Main contraction.  `smem` must provide Cfg::SMEM_BYTES.  kbeg/kend are element
-// indices along k (multiples of BK) applied to both operands' k axes.
+// Main contraction of one TM x 128 tile.  `smem` must provide Cfg::SMEM_BYTES.  kbeg/kend are
+// element indices along k (multiples of BK) applied to both operands' k axes.
 // If Cin != nullptr the accumulator starts from the Cin tile (fetched before the
 // k loop so its latency hides under the first slabs), else from zero.
 template <bool A_KMAJOR, bool B_KMAJOR, class Cfg = GemmCfg>
 __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, size_t lda, const double* __restrict__ B,
                                           size_t ldb, int kbeg, int kend, bool negate, const double* Cin,
                                           size_t ldcin, double* __restrict__ Cout, size_t ldc, double* smem) {
-  constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, SLAB = Cfg::SLAB;
-  constexpr int LD_MN = Cfg::LD_MN, LD_K = Cfg::LD_K;
+  constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE;
+  constexpr int SLAB_A = Cfg::SLAB_A, SLAB_B = Cfg::SLAB_B;
+  constexpr int LD_A = Cfg::LD_MN_A, LD_B = Cfg::LD_MN_B, LD_K = Cfg::LD_K;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = (warp % Cfg::WM) * (MT * 8), n0 = (warp / Cfg::WM) * (NT * 8);
 
   double* sA = smem;
-  double* sB = smem + NS * SLAB;
+  double* sB = smem + NS * SLAB_A;
 
   const int nk = (kend - kbeg) / BK;
   const unsigned sgn = negate ? 0x80000000u : 0u;  // sign flip on the integer pipe, not the FP64 pipe
 #pragma unroll
   for (int s = 0; s < NS - 1; ++s) {
     if (s < nk) {
-      load_slab<Cfg, A_KMAJOR>(sA + s * SLAB, A, lda, kbeg + s * BK, tid);
-      load_slab<Cfg, B_KMAJOR>(sB + s * SLAB, B, ldb, kbeg + s * BK, tid);
+      load_slab<Cfg, A_KMAJOR, Cfg::TM>(sA + s * SLAB_A, A, lda, kbeg + s * BK, tid);
+      load_slab<Cfg, B_KMAJOR, TB>(sB + s * SLAB_B, B, ldb, kbeg + s * BK, tid);
     }
     cp_async_commit();
   }
@@ -150,24 +162,24 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, size_t l
       int nxt = kt + NS - 1;
       if (nxt < nk) {
         int sb = nxt % NS;
-        load_slab<Cfg, A_KMAJOR>(sA + sb * SLAB, A, lda, kbeg + nxt * BK, tid);
-        load_slab<Cfg, B_KMAJOR>(sB + sb * SLAB, B, ldb, kbeg + nxt * BK, tid);
+        load_slab<Cfg, A_KMAJOR, Cfg::TM>(sA + sb * SLAB_A, A, lda, kbeg + nxt * BK, tid);
+        load_slab<Cfg, B_KMAJOR, TB>(sB + sb * SLAB_B, B, ldb, kbeg + nxt * BK, tid);
       }
       cp_async_commit();
     }
-    const double* a_s = sA + (kt % NS) * SLAB;
-    const double* b_s = sB + (kt % NS) * SLAB;
+    const double* a_s = sA + (kt % NS) * SLAB_A;
+    const double* b_s = sB + (kt % NS) * SLAB_B;
 #pragma unroll
     for (int k4 = 0; k4 < BK / 4; ++k4) {
       double a[MT], b[NT];
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
-        double x = A_KMAJOR ? a_s[(m0 + 8 * i + g) * LD_K + k4 * 4 + t] : a_s[(k4 * 4 + t) * LD_MN + m0 + 8 * i + g];
+        double x = A_KMAJOR ? a_s[(m0 + 8 * i + g) * LD_K + k4 * 4 + t] : a_s[(k4 * 4 + t) * LD_A + m0 + 8 * i + g];
         a[i] = flip_sign(x, sgn);
       }
 #pragma unroll
       for (int j = 0; j < NT; ++j)
-        b[j] = B_KMAJOR ? b_s[(n0 + 8 * j + g) * LD_K + k4 * 4 + t] : b_s[(k4 * 4 + t) * LD_MN + n0 + 8 * j + g];
+        b[j] = B_KMAJOR ? b_s[(n0 + 8 * j + g) * LD_K + k4 * 4 + t] : b_s[(k4 * 4 + t) * LD_B + n0 + 8 * j + g];
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll

@@ -88,12 +88,17 @@ static bool g_attr_set[64] = {};
 static int g_num_sms[64] = {};
 // GPEDM_DIAG_REF=1 selects the simple (slow) reference diagonal-block kernel, for A/B debugging.
 static const bool g_no_lookahead = getenv("GPEDM_NO_LOOKAHEAD") != nullptr && atoi(getenv("GPEDM_NO_LOOKAHEAD")) != 0;
+static const int g_group = getenv("GPEDM_POTRF_GROUP") ? std::max(1, atoi(getenv("GPEDM_POTRF_GROUP"))) : 2;
+static const int g_group_min = getenv("GPEDM_POTRF_GROUP_MIN") ? atoi(getenv("GPEDM_POTRF_GROUP_MIN")) : 24;
+static const bool g_no_split = getenv("GPEDM_NO_SPLIT") != nullptr && atoi(getenv("GPEDM_NO_SPLIT")) != 0;
 static const bool g_diag_ref = getenv("GPEDM_DIAG_REF") != nullptr && atoi(getenv("GPEDM_DIAG_REF")) != 0;
 static int ensure_kernel_attrs(int device) {
   if (device < 64 && g_attr_set[device]) return 0;
   CU(cudaFuncSetAttribute(tile_once_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CU(cudaFuncSetAttribute(tile_once_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CU(cudaFuncSetAttribute(tile_once_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<false, false, GemmCfgSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          GemmCfgSplit::SMEM_BYTES));
   {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -289,9 +294,12 @@ extern "C" int gpedm_last_phase_ms(gpedm_handle h, float* ms) {
 
 // ------------------------------------------------------------------------------- tile launches
 // layout: 0 = (MN, MN), 1 = (MN, K), 2 = (K, K) operand layouts (see dgemm_tile.cuh).
-static int launch_tiles(gpedm_fit_s* h, cudaStream_t st, const TileOp& op, int layout) {
+static int launch_tiles(gpedm_fit_s* h, cudaStream_t st, const TileOp& op, int layout, bool split = false) {
   if (op.ntiles <= 0) return 0;
-  if (layout == 0)
+  if (split && layout == 0)  // latency-critical launch with fewer tiles than SMs: 4 row strips per tile
+    tile_once_kernel<false, false, GemmCfgSplit>
+        <<<op.ntiles * (TB / GemmCfgSplit::TM), GemmCfgSplit::THREADS, GemmCfgSplit::SMEM_BYTES, st>>>(op);
+  else if (layout == 0)
     tile_once_kernel<false, false><<<op.ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op);
   else if (layout == 1)
     tile_once_kernel<false, true><<<op.ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op);
@@ -327,56 +335,78 @@ static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) 
     h->launches++;
   }
   CU(cudaEventRecord(h->ev[1], st));
-  // --- Cholesky, right-looking over 128-wide block columns, with look-ahead:
-  //   aux (high priority): diag(k) -> panel(k) -> update of column k+1 (needs trailing(k-1))
-  //   main               : trailing update of columns >= k+2 with panel k (needs panel(k))
-  // so the serial chain diag/panel/next-column of step k+1 overlaps the bulk update of step k.
+  // --- Cholesky, right-looking over 128-wide block columns, with look-ahead and grouped updates.
+  // Steps are processed in groups [g0, g1) of G block columns (G = GPEDM_POTRF_GROUP while the
+  // trailing matrix is large, 1 near the end); [g1, g2) is the next group.
+  //   aux (high priority): for q in [g0, g1):
+  //        column q <- pending updates of the group's earlier steps (rank 128 (q-g0))
+  //        diag(q) -> panel(q)
+  //      then columns [g1, g2) <- all G steps of the group (rank 128 G), so the next group's whole
+  //      chain depends only on this stream;
+  //   main: columns >= g2 <- all G steps in ONE rank-128G update: each trailing tile is read and
+  //        written once per group instead of once per step and the k loop is G times longer.
+  // The chain of group g+1 overlaps the bulk update of group g.
   {
     cudaStream_t ax = g_no_lookahead ? st : h->aux;
     CU(cudaEventRecord(h->evFork, st));
     CU(cudaStreamWaitEvent(ax, h->evFork, 0));
-    for (int k = 0; k < nb; ++k) {
-      if (g_diag_ref)
-        diag_potf2_inv_kernel<<<1, 256, DIAG_SMEM_BYTES, ax>>>(h->bufA + (size_t)k * TB * (ld + 1), ld,
-                                                                h->bufB + (size_t)k * TB * (ld + 1), ld, k, N,
-                                                                h->dlogdet, h->dinfo);
-      else
-        diag_block_kernel<<<1, DG_THREADS, DG_SMEM_BYTES, ax>>>(h->bufA + (size_t)k * TB * (ld + 1), ld,
-                                                                h->bufB + (size_t)k * TB * (ld + 1), ld, k, N,
-                                                                h->dlogdet, h->dinfo);
-      h->launches++;
-      int m = nb - k - 1;
-      if (m > 0) {
-        TileOp pan = make_op(OP_PANEL, m, nb);
-        pan.k = k;
-        pan.P1 = h->bufB;
-        pan.P2 = h->bufA;
-        pan.ld1 = pan.ld2 = ld;
-        int rc = launch_tiles(h, ax, pan, 0);
-        if (rc) return rc;
-        CU(cudaEventRecord(h->evPanel[k], ax));
-        if (k > 0) CU(cudaStreamWaitEvent(ax, h->evTrail[k - 1], 0));
-        TileOp t1 = make_op(OP_TRAIL, m, nb);  // next block column only
-        t1.k = k;
-        t1.jlo = k + 1;
-        t1.jhi = k + 2;
-        t1.P2 = h->bufA;
-        t1.ld2 = ld;
-        rc = launch_tiles(h, ax, t1, 0);
-        if (rc) return rc;
-        CU(cudaStreamWaitEvent(st, h->evPanel[k], 0));
-        if (m > 1) {
-          TileOp t2 = make_op(OP_TRAIL, m * (m - 1) / 2, nb);
-          t2.k = k;
-          t2.jlo = k + 2;
-          t2.jhi = nb;
-          t2.P2 = h->bufA;
-          t2.ld2 = ld;
-          rc = launch_tiles(h, st, t2, 0);
+    auto trail = [&](cudaStream_t s_, int k0, int kc, int jlo, int ntl) -> int {
+      TileOp t = make_op(OP_TRAIL, ntl, nb);
+      t.k = k0;
+      t.kcount = kc;
+      t.jlo = jlo;
+      t.P2 = h->bufA;
+      t.ld2 = ld;
+      return launch_tiles(h, s_, t, 0, s_ == ax && !g_no_split && ntl * 4 <= 2 * h->num_sms);
+    };
+    auto group_size = [&](int start) { return (nb - start - 1 >= g_group_min) ? g_group : 1; };
+    int prev_bulk = -1;  // index of the event recorded after the previous group's bulk update
+    int g0 = 0, G = group_size(0);
+    while (g0 < nb) {
+      const int g1 = std::min(nb, g0 + G);
+      for (int q = g0; q < g1; ++q) {
+        if (q > g0) {
+          int rc = trail(ax, g0, q - g0, q, nb - q);  // column q only
           if (rc) return rc;
         }
-        CU(cudaEventRecord(h->evTrail[k], st));
+        if (g_diag_ref)
+          diag_potf2_inv_kernel<<<1, 256, DIAG_SMEM_BYTES, ax>>>(h->bufA + (size_t)q * TB * (ld + 1), ld,
+                                                                  h->bufB + (size_t)q * TB * (ld + 1), ld, q, N,
+                                                                  h->dlogdet, h->dinfo);
+        else
+          diag_block_kernel<<<1, DG_THREADS, DG_SMEM_BYTES, ax>>>(h->bufA + (size_t)q * TB * (ld + 1), ld,
+                                                                  h->bufB + (size_t)q * TB * (ld + 1), ld, q, N,
+                                                                  h->dlogdet, h->dinfo);
+        h->launches++;
+        if (nb - q - 1 > 0) {
+          TileOp pan = make_op(OP_PANEL, nb - q - 1, nb);
+          pan.k = q;
+          pan.P1 = h->bufB;
+          pan.P2 = h->bufA;
+          pan.ld1 = pan.ld2 = ld;
+          int rc = launch_tiles(h, ax, pan, 0, !g_no_split && pan.ntiles * 4 <= 2 * h->num_sms);
+          if (rc) return rc;
+        }
       }
+      if (g1 >= nb) break;
+      const int Gn = group_size(g1);
+      const int g2 = std::min(nb, g1 + Gn);
+      CU(cudaEventRecord(h->evPanel[g1 - 1], ax));
+      if (prev_bulk >= 0) CU(cudaStreamWaitEvent(ax, h->evTrail[prev_bulk], 0));
+      int next_cols_tiles = 0;
+      for (int c = g1; c < g2; ++c) next_cols_tiles += nb - c;
+      int rc = trail(ax, g0, g1 - g0, g1, next_cols_tiles);  // columns [g1, g2)
+      if (rc) return rc;
+      CU(cudaStreamWaitEvent(st, h->evPanel[g1 - 1], 0));
+      if (g2 < nb) {
+        const int m = nb - g2;
+        rc = trail(st, g0, g1 - g0, g2, m * (m + 1) / 2);  // columns >= g2
+        if (rc) return rc;
+      }
+      CU(cudaEventRecord(h->evTrail[g1 - 1], st));
+      prev_bulk = g1 - 1;
+      g0 = g1;
+      G = Gn;
     }
     CU(cudaEventRecord(h->evJoin, ax));
     CU(cudaStreamWaitEvent(st, h->evJoin, 0));

@@ -11,7 +11,7 @@ namespace gpedm {
 
 enum TileOpType {
   OP_PANEL = 0,     // L_ik = A_ik D_k^T, i > k                         (MN, MN)
-  OP_TRAIL = 1,     // A_ij -= L_ik L_jk^T, jlo <= j < jhi, i >= j      (MN, MN)
+  OP_TRAIL = 1,     // A_ij -= sum_{q=k}^{k+kcount-1} L_iq L_jq^T, j >= jlo, i >= j   (MN, MN)
   OP_TRTRI_W = 2,   // W = L21 X11   (pairs of size s)                  (MN, K)
   OP_TRTRI_X = 3,   // X21 = -X22 W                                     (MN, K)
   OP_LAUUM = 4,     // S_ij = sum_{k>=i} X_ki^T X_kj, i >= j            (K, K)
@@ -22,7 +22,8 @@ struct TileOp {
   int type;
   int ntiles;
   int nb;        // tiles per matrix edge
-  int k;         // block column (panel / trail)
+  int k;         // block column (panel) / first block column of the update (trail)
+  int kcount;    // trail: number of consecutive block columns applied (rank = 128 * kcount)
   int s;         // trtri block size in tiles
   int jlo, jhi;  // trail column range
   int mt;        // tri_apply: number of column tiles of V
@@ -93,6 +94,7 @@ __device__ __forceinline__ bool decode_tile(const TileOp& op, int t, TileWork& w
       A = op.P2 + (size_t)i * TB + (size_t)op.k * TB * ldc;
       B = op.P2 + (size_t)j * TB + (size_t)op.k * TB * ldc;
       C = op.P2 + (size_t)i * TB + (size_t)j * TB * ldc;
+      kend = op.kcount * TB;
       flags = 3;
       break;
     }
@@ -158,15 +160,21 @@ __device__ __forceinline__ bool decode_tile(const TileOp& op, int t, TileWork& w
 }
 
 // One tile per CTA (grid = ntiles, hardware block scheduler hands out tiles in launch order).
+// With Cfg::TM < 128 each 128 x 128 tile is split into 128/TM row strips handled by consecutive
+// CTAs (grid = ntiles * 128/TM).  Row strips keep the in-place panel update safe: a CTA reads
+// only the rows of A it overwrites.
 template <bool A_KMAJOR, bool B_KMAJOR, class Cfg = GemmCfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1) tile_once_kernel(const TileOp op) {
   extern __shared__ double smem[];
+  constexpr int SPLIT = TB / Cfg::TM;
+  static_assert(SPLIT == 1 || !A_KMAJOR, "row-strip split is implemented for MN-major A only");
   TileWork w;
-  if (!decode_tile<A_KMAJOR, B_KMAJOR, Cfg::BK>(op, blockIdx.x, w)) return;
+  if (!decode_tile<A_KMAJOR, B_KMAJOR, Cfg::BK>(op, blockIdx.x / SPLIT, w)) return;
   size_t lda, ldb, ldc;
   op_strides(op, lda, ldb, ldc);
-  gemm_tile<A_KMAJOR, B_KMAJOR, Cfg>(w.A, lda, w.B, ldb, 0, w.nslab * Cfg::BK, (w.flags & 1) != 0,
-                                     (w.flags & 2) ? w.C : nullptr, ldc, w.C, ldc, smem);
+  const int roff = (blockIdx.x % SPLIT) * Cfg::TM;
+  gemm_tile<A_KMAJOR, B_KMAJOR, Cfg>(w.A + roff, lda, w.B, ldb, 0, w.nslab * Cfg::BK, (w.flags & 1) != 0,
+                                     (w.flags & 2) ? w.C + roff : nullptr, ldc, w.C + roff, ldc, smem);
 }
 
 }  // namespace gpedm
