@@ -197,6 +197,128 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, size_t l
         Cout[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ldc] = acc[i][j][e];
 }
 
+// ---- mbarrier helpers (shared::cta) -------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+// arrive-on-completion of all cp.async issued so far by this thread (does not change the pending count)
+__device__ __forceinline__ void mbar_cp_async_arrive(uint64_t* bar) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @!p bra WAIT_%=;\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+
+// Same contraction as gemm_tile, but the CTA-wide __syncthreads per k slab is replaced by per-stage
+// mbarriers: full[s] completes when every thread's cp.async copies of the slab have landed, empty[s]
+// when every warp has finished reading it.  Slabs are prefetched NS-2 ahead into a ring of NS
+// stages, so warps may drift up to two slabs apart instead of meeting at a barrier every slab:
+// a warp that waits (LDS latency, copy not landed yet) no longer stops the other warp on its
+// scheduler from feeding the DMMA pipe.
+template <bool A_KMAJOR, bool B_KMAJOR, class Cfg = GemmCfg>
+__device__ __forceinline__ void gemm_tile_mb(const double* __restrict__ A, size_t lda, const double* __restrict__ B,
+                                             size_t ldb, int kbeg, int kend, bool negate, const double* Cin,
+                                             size_t ldcin, double* __restrict__ Cout, size_t ldc, double* smem) {
+  constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, PREF = NS - 2;
+  constexpr int SLAB_A = Cfg::SLAB_A, SLAB_B = Cfg::SLAB_B;
+  constexpr int LD_A = Cfg::LD_MN_A, LD_B = Cfg::LD_MN_B, LD_K = Cfg::LD_K;
+  static_assert(NS >= 3, "need at least 3 stages");
+  __shared__ uint64_t full_bar[NS], empty_bar[NS];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = (warp % Cfg::WM) * (MT * 8), n0 = (warp / Cfg::WM) * (NT * 8);
+  double* sA = smem;
+  double* sB = smem + NS * SLAB_A;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], Cfg::THREADS);
+      mbar_init(&empty_bar[s], Cfg::THREADS / 32);
+    }
+  }
+  __syncthreads();
+
+  const int nk = (kend - kbeg) / BK;
+  const unsigned sgn = negate ? 0x80000000u : 0u;
+  auto issue = [&](int j) {  // copy slab j into stage j % NS
+    const int s = j % NS, r = j / NS;
+    if (r > 0) mbar_wait(&empty_bar[s], (unsigned)((r - 1) & 1));
+    load_slab<Cfg, A_KMAJOR, Cfg::TM>(sA + s * SLAB_A, A, lda, kbeg + j * BK, tid);
+    load_slab<Cfg, B_KMAJOR, TB>(sB + s * SLAB_B, B, ldb, kbeg + j * BK, tid);
+    mbar_cp_async_arrive(&full_bar[s]);
+  };
+#pragma unroll
+  for (int j = 0; j < PREF; ++j)
+    if (j < nk) issue(j);
+
+  double acc[MT][NT][2];
+  if (Cin != nullptr) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          acc[i][j][e] = Cin[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ldcin];
+  } else {
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  }
+
+  for (int kt = 0; kt < nk; ++kt) {
+    if (kt + PREF < nk) issue(kt + PREF);
+    const int s = kt % NS;
+    mbar_wait(&full_bar[s], (unsigned)((kt / NS) & 1));
+    const double* a_s = sA + s * SLAB_A;
+    const double* b_s = sB + s * SLAB_B;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      double a[MT], b[NT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        double x = A_KMAJOR ? a_s[(m0 + 8 * i + g) * LD_K + k4 * 4 + t] : a_s[(k4 * 4 + t) * LD_A + m0 + 8 * i + g];
+        a[i] = flip_sign(x, sgn);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        b[j] = B_KMAJOR ? b_s[(n0 + 8 * j + g) * LD_K + k4 * 4 + t] : b_s[(k4 * 4 + t) * LD_B + n0 + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        Cout[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ldc] = acc[i][j][e];
+}
+
 // Decode a linear index into lower-triangle coordinates (i >= j), row-major over rows:
 // t = i*(i+1)/2 + j.
 __device__ __forceinline__ void tri_decode(int t, int& i, int& j) {

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) tile_once_kernel(const TileOp
   size_t lda, ldb, ldc;
   op_strides(op, lda, ldb, ldc);
   const int roff = (blockIdx.x % SPLIT) * Cfg::TM;
-  gemm_tile<A_KMAJOR, B_KMAJOR, Cfg>(w.A + roff, lda, w.B, ldb, 0, w.nslab * Cfg::BK, (w.flags & 1) != 0,
+  gemm_tile_mb<A_KMAJOR, B_KMAJOR, Cfg>(w.A + roff, lda, w.B, ldb, 0, w.nslab * Cfg::BK, (w.flags & 1) != 0,
                                      (w.flags & 2) ? w.C + roff : nullptr, ldc, w.C + roff, ldc, smem);
 }
 
