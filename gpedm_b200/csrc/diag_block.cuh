@@ -3,13 +3,15 @@
 // (one launch per 128-wide block column), so it is organised for latency:
 //   * the tile lives in shared memory (column-major, stride 132 => conflict-free DMMA fragments);
 //   * it is factored as 4 block columns of width 32:
-//       - the 32x32 diagonal block by ONE warp in registers (lane = row), right-looking, with the
-//         pivot broadcast and the rank-1 update done by warp shuffles;  1/L_jj comes from rsqrt so
-//         the per-column dependency chain is shuffle -> rsqrt -> multiply -> fma;
-//       - the sub-diagonal 32x32 blocks by forward substitution (lane = row, L_kk broadcast from smem);
-//       - the trailing 32x32 blocks by DMMA 8x8x4 tiles spread over the 16 warps;
-//   * D = L^-1 is then built by recursive doubling: four 32x32 inverses (one warp each, lane =
-//     column), then X21 = -X22 (L21 X11) at block sizes 32 and 64 with DMMA tiles.
+//       - the 32x32 diagonal block by ONE warp in registers (lane = row), right-looking; the
+//         pivot column is broadcast through a double-buffered shared-memory vector read back with
+//         LDS.128, 1/L_jj comes from rsqrt, and the next pivot (own-lane fma -> shuffle -> rsqrt)
+//         is started before the rank-1 update so its latency hides under the update;
+//       - the sub-diagonal 32x32 blocks by forward substitution (lane = row, L_kk broadcast);
+//       - the trailing 32x32 blocks by DMMA 8x8x4 tiles; the next diagonal block is updated
+//         first so that its factorisation (warp 0) overlaps the rest of the update (warps 1-15);
+//   * D = L^-1 is built by recursive doubling X21 = -X22 (L21 X11) from 8x8 diagonal inverses
+//     (one thread per column) through block sizes 8, 16, 32, 64, all products on DMMA tiles.
 // Replaces (for one diagonal block) LAPACK dpotrf / dtrtri behind Matrix::chol / chol2inv
 // (reference R/GPfunctions.R:826-829).
 #pragma once
@@ -26,19 +28,73 @@ __device__ long long g_diag_ts[32];
 #endif
 constexpr int DG_LD = 132;   // stride of the 128x128 tile in smem  (== 4 mod 16)
 constexpr int DG_WLD = 68;   // stride of the 64x64 scratch          (== 4 mod 16)
-constexpr int DG_SMEM_BYTES = (TB * DG_LD + 64 * DG_WLD + 2 * TB) * (int)sizeof(double);
+constexpr int DG_SMEM_BYTES = (TB * DG_LD + 64 * DG_WLD + 2 * TB + 64) * (int)sizeof(double);
 
-// One 8x8 output tile: c += (+/-) A[8 x K] * op(B).  Abase -> A[row0][k0] (column-major, lda).
-// B_TRANS: element (k,n) = Bm[n][k], Bbase -> Bm[col0][k0];  else element (k,n) = Bm[k][n],
-// Bbase -> Bm[k0][col0].
+// One 8x8 output tile: c += (+/-) A[8 x K] * op(B), K a multiple of 8.  Abase -> A[row0][k0]
+// (column-major, lda).  B_TRANS: element (k,n) = Bm[n][k], Bbase -> Bm[col0][k0]; else element
+// (k,n) = Bm[k][n], Bbase -> Bm[k0][col0].  Fragments of the next 8 k are fetched while the
+// current two DMMAs issue.
 template <bool B_TRANS>
 __device__ __forceinline__ void tile_mma(double& c0, double& c1, const double* Abase, int lda, const double* Bbase,
-                                         int ldb, int K, bool negate, int g, int t) {
-  for (int k = 0; k < K; k += 4) {
-    double a = Abase[g + (k + t) * lda];
-    double b = B_TRANS ? Bbase[g + (k + t) * ldb] : Bbase[(k + t) + g * ldb];
-    dmma884(c0, c1, negate ? -a : a, b);
+                                         int ldb, int K, unsigned sgn, int g, int t) {
+  const double* ap = Abase + g + t * lda;
+  const double* bp = B_TRANS ? Bbase + g + t * ldb : Bbase + t + g * ldb;
+  const int astep = 4 * lda, bstep = B_TRANS ? 4 * ldb : 4;
+  double a0 = ap[0], a1 = ap[astep], b0 = bp[0], b1 = bp[bstep];
+  for (int k = 8; k < K; k += 8) {
+    ap += 2 * astep;
+    bp += 2 * bstep;
+    double na0 = ap[0], na1 = ap[astep], nb0 = bp[0], nb1 = bp[bstep];
+    dmma884(c0, c1, flip_sign(a0, sgn), b0);
+    dmma884(c0, c1, flip_sign(a1, sgn), b1);
+    a0 = na0;
+    a1 = na1;
+    b0 = nb0;
+    b1 = nb1;
   }
+  dmma884(c0, c1, flip_sign(a0, sgn), b0);
+  dmma884(c0, c1, flip_sign(a1, sgn), b1);
+}
+
+// 32x32 Cholesky of the diagonal block at `base` by one warp (lane = row).
+__device__ __noinline__ void chol32_warp(double* s, double* rdiag, double* dvec, double* colbuf, int base,
+                                            int lane, int kblock, int n_valid, int* info) {
+  const unsigned FULL = 0xffffffffu;
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = s[(base + lane) + (base + c) * DG_LD];
+  double ajj = __shfl_sync(FULL, a[0], 0);
+  double rs = rsqrt(ajj);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const double l = a[j] * rs;  // L[lane][j]
+    a[j] = l;
+    if (lane == j) {
+      if (!(ajj > 0.0) && (kblock * TB + base + j < n_valid)) atomicCAS(info, 0, kblock * TB + base + j + 1);
+      rdiag[base + j] = rs;
+      dvec[base + j] = l;
+    }
+    double ajj_n = 1.0, rs_n = 1.0;
+    if (j + 1 < 32) {
+      // lane j+1 owns the next pivot and can update it with its own l: start the broadcast + rsqrt now
+      const double piv = fma(-l, l, a[j + 1]);
+      ajj_n = __shfl_sync(FULL, piv, j + 1);
+      rs_n = rsqrt(ajj_n);
+    }
+    double* cb = colbuf + (j & 1) * 32;
+    cb[lane] = l;
+    __syncwarp();
+#pragma unroll
+    for (int c2 = ((j + 1) & ~1); c2 < 32; c2 += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(cb + c2);
+      if (c2 > j) a[c2] = fma(-l, v.x, a[c2]);
+      a[c2 + 1] = fma(-l, v.y, a[c2 + 1]);
+    }
+    ajj = ajj_n;
+    rs = rs_n;
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) s[(base + lane) + (base + c) * DG_LD] = (c <= lane) ? a[c] : 0.0;
 }
 
 __global__ void __launch_bounds__(DG_THREADS, 1)
@@ -49,9 +105,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
   double* w = sm + TB * DG_LD;      // [64][68] scratch
   double* rdiag = w + 64 * DG_WLD;  // 1 / L_jj
   double* dvec = rdiag + TB;        // L_jj, later reduction scratch
+  double* colbuf = dvec + TB;       // [2][32] pivot-column broadcast buffer
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const unsigned FULL = 0xffffffffu;
+  constexpr int NW = DG_THREADS / 32;
 
   DG_TS(0);
 #pragma unroll 8
@@ -63,47 +120,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
   DG_TS(1);
 
   // ---------------- Cholesky, 4 block columns of width 32 ----------------
+  if (warp == 0) chol32_warp(s, rdiag, dvec, colbuf, 0, lane, kblock, n_valid, info);
+  __syncthreads();
+  DG_TS(2);
 #pragma unroll 1
-  for (int kb = 0; kb < 4; ++kb) {
+  for (int kb = 0; kb < 3; ++kb) {
     const int base = kb * 32;
-    if (warp == 0) {
-      double a[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) a[c] = s[(base + lane) + (base + c) * DG_LD];
-      // software-pipelined: the next pivot (broadcast + rsqrt) is started right after the first
-      // update of column j so its latency hides under the remaining rank-1 update instructions.
-      double ajj = __shfl_sync(FULL, a[0], 0);
-      double rs = rsqrt(ajj);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        double l = a[j] * rs;
-        a[j] = l;
-        if (lane == j) {
-          if (!(ajj > 0.0) && (kblock * TB + base + j < n_valid)) atomicCAS(info, 0, kblock * TB + base + j + 1);
-          rdiag[base + j] = rs;
-          dvec[base + j] = l;
-        }
-        double ajj_n = 1.0, rs_n = 1.0;
-        if (j + 1 < 32) {
-          double lc1 = __shfl_sync(FULL, l, j + 1);
-          a[j + 1] = fma(-l, lc1, a[j + 1]);
-          ajj_n = __shfl_sync(FULL, a[j + 1], j + 1);
-          rs_n = rsqrt(ajj_n);
-        }
-#pragma unroll
-        for (int c = j + 2; c < 32; ++c) {
-          double lc = __shfl_sync(FULL, l, c);
-          a[c] = fma(-l, lc, a[c]);
-        }
-        ajj = ajj_n;
-        rs = rs_n;
-      }
-#pragma unroll
-      for (int c = 0; c < 32; ++c) s[(base + lane) + (base + c) * DG_LD] = (c <= lane) ? a[c] : 0.0;
-    }
-    __syncthreads();
-    DG_TS(2 + 3 * kb);
-    // panel: rows below the diagonal block, forward substitution per row
+    // panel: rows below the diagonal block, forward substitution per row (lane = row)
     if (warp < 3 - kb) {
       const int row = base + 32 * (warp + 1) + lane;
       double a[32];
@@ -111,33 +134,54 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
       for (int c = 0; c < 32; ++c) a[c] = s[row + (base + c) * DG_LD];
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        double x = a[c] * rdiag[base + c];
+        const double x = a[c] * rdiag[base + c];
         a[c] = x;
+        const double* lcol = s + base + (base + c) * DG_LD;  // column c of L_kk, contiguous
 #pragma unroll
-        for (int c2 = c + 1; c2 < 32; ++c2) a[c2] = fma(-x, s[(base + c2) + (base + c) * DG_LD], a[c2]);
+        for (int c2 = ((c + 1) & ~1); c2 < 32; c2 += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(lcol + c2);
+          if (c2 > c) a[c2] = fma(-x, v.x, a[c2]);
+          a[c2 + 1] = fma(-x, v.y, a[c2 + 1]);
+        }
       }
 #pragma unroll
       for (int c = 0; c < 32; ++c) s[row + (base + c) * DG_LD] = a[c];
     }
     __syncthreads();
     DG_TS(3 + 3 * kb);
-    // trailing update on the remaining lower 32x32 blocks (16 DMMA tiles each)
-    const int m = 3 - kb;
-    const int ntile = m * (m + 1) / 2 * 16;
-    for (int q = warp; q < ntile; q += DG_THREADS / 32) {
-      int blk = q >> 4, tile = q & 15;
-      int bi = blk < 1 ? 0 : (blk < 3 ? 1 : 2);
-      int bj = blk - bi * (bi + 1) / 2;
-      int row0 = base + 32 * (bi + 1) + 8 * (tile >> 2);
-      int col0 = base + 32 * (bj + 1) + 8 * (tile & 3);
+    // trailing update, phase A: the next diagonal block (16 tiles, one per warp)
+    {
+      const int nb0 = base + 32;
+      const int row0 = nb0 + 8 * (warp >> 2), col0 = nb0 + 8 * (warp & 3);
       double* cp = s + (row0 + g) + (col0 + 2 * t) * DG_LD;
       double c0 = cp[0], c1 = cp[DG_LD];
-      tile_mma<true>(c0, c1, s + row0 + base * DG_LD, DG_LD, s + col0 + base * DG_LD, DG_LD, 32, true, g, t);
+      tile_mma<true>(c0, c1, s + row0 + base * DG_LD, DG_LD, s + col0 + base * DG_LD, DG_LD, 32, 0x80000000u, g, t);
       cp[0] = c0;
       cp[DG_LD] = c1;
     }
     __syncthreads();
     DG_TS(4 + 3 * kb);
+    // phase B: warp 0 factors the next diagonal block while warps 1..15 update the blocks below it
+    if (warp == 0) {
+      chol32_warp(s, rdiag, dvec, colbuf, base + 32, lane, kblock, n_valid, info);
+    } else {
+      const int m = 2 - kb;                     // block rows below the next diagonal block
+      const int nblk = m * (m + 3) / 2;         // blocks (bi, bj), bi in 1..m, bj in 0..bi  (relative to kb+1)
+      for (int q = warp - 1; q < nblk * 16; q += NW - 1) {
+        const int blk = q >> 4, tile = q & 15;
+        int bi = (blk < 2) ? 1 : 2;             // m <= 2: blocks (1,0),(1,1),(2,0),(2,1),(2,2)
+        int bj = blk - (bi == 1 ? 0 : 2);
+        const int row0 = base + 32 * (bi + 1) + 8 * (tile >> 2);
+        const int col0 = base + 32 * (bj + 1) + 8 * (tile & 3);
+        double* cp = s + (row0 + g) + (col0 + 2 * t) * DG_LD;
+        double c0 = cp[0], c1 = cp[DG_LD];
+        tile_mma<true>(c0, c1, s + row0 + base * DG_LD, DG_LD, s + col0 + base * DG_LD, DG_LD, 32, 0x80000000u, g, t);
+        cp[0] = c0;
+        cp[DG_LD] = c1;
+      }
+    }
+    __syncthreads();
+    DG_TS(5 + 3 * kb);
   }
 
   // ---------------- write L, log-determinant part ----------------
@@ -159,79 +203,59 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
   }
   DG_TS(14);
 
-  // ---------------- inverse: 32x32 diagonal blocks (warp b, lane = column) ----------------
-  if (warp < 4) {
-    const int base = warp * 32;
-    double x[32];
+  // ---------------- inverse: 8x8 diagonal blocks, one thread per column ----------------
+  {
+    double x[8];
+    const int b8 = (tid >> 3) * 8, c = tid & 7;  // threads 0..127: block tid/8, column tid%8
+    if (tid < TB) {
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int r = 0; r < 8; ++r) {
+        double acc = 0.0;
 #pragma unroll
-      for (int mm = 0; mm < r; ++mm) {
-        double lv = s[(base + r) + (base + mm) * DG_LD];
-        if ((mm & 3) == 0) s0 = fma(lv, x[mm], s0);
-        else if ((mm & 3) == 1) s1 = fma(lv, x[mm], s1);
-        else if ((mm & 3) == 2) s2 = fma(lv, x[mm], s2);
-        else s3 = fma(lv, x[mm], s3);
+        for (int mm = 0; mm < r; ++mm) acc = fma(s[(b8 + r) + (b8 + mm) * DG_LD], x[mm], acc);
+        const double rd = rdiag[b8 + r];
+        x[r] = (r == c) ? rd : ((r < c) ? 0.0 : -acc * rd);
       }
-      s0 = (s0 + s1) + (s2 + s3);
-      s1 = 0.0;
-      double rd = rdiag[base + r];
-      double v = -(s0 + s1) * rd;
-      x[r] = (r == lane) ? rd : ((r < lane) ? 0.0 : v);
     }
-    __syncwarp();
+    __syncthreads();
+    if (tid < TB) {
 #pragma unroll
-    for (int r = 0; r < 32; ++r) s[(base + r) + (base + lane) * DG_LD] = x[r];
+      for (int r = 0; r < 8; ++r) s[(b8 + r) + (b8 + c) * DG_LD] = x[r];
+    }
   }
   __syncthreads();
   DG_TS(15);
-  // ---------------- level 1: 32-blocks, pairs (0,1) and (2,3) ----------------
-  for (int q = warp; q < 32; q += DG_THREADS / 32) {  // W = L21 * X11
-    int p = q >> 4, tile = q & 15;
-    int o = p * 64;
-    int r0 = 8 * (tile >> 2), c0i = 8 * (tile & 3);
-    double c0 = 0.0, c1 = 0.0;
-    tile_mma<false>(c0, c1, s + (o + 32 + r0) + o * DG_LD, DG_LD, s + o + (o + c0i) * DG_LD, DG_LD, 32, false, g, t);
-    double* wp = w + (p * 32 + r0 + g) + (c0i + 2 * t) * DG_WLD;
-    wp[0] = c0;
-    wp[DG_WLD] = c1;
+  // ---------------- recursive doubling: block sizes 8, 16, 32, 64 ----------------
+#pragma unroll 1
+  for (int sz = 8; sz <= 64; sz *= 2) {
+    const int tps = sz >> 3;               // 8x8 tiles per block edge
+    const int tpp = tps * tps;             // tiles per pair
+    const int ntile = (TB / (2 * sz)) * tpp;
+    for (int q = warp; q < ntile; q += NW) {  // W = L21 * X11  (k >= column of the tile: X11 is lower triangular)
+      const int p = q / tpp, tile = q % tpp;
+      const int o = p * 2 * sz;
+      const int r0 = 8 * (tile / tps), c0i = 8 * (tile % tps);
+      double c0 = 0.0, c1 = 0.0;
+      tile_mma<false>(c0, c1, s + (o + sz + r0) + (o + c0i) * DG_LD, DG_LD, s + (o + c0i) + (o + c0i) * DG_LD, DG_LD,
+                      sz - c0i, 0u, g, t);
+      double* wp = w + (p * sz + r0 + g) + (c0i + 2 * t) * DG_WLD;
+      wp[0] = c0;
+      wp[DG_WLD] = c1;
+    }
+    __syncthreads();
+    for (int q = warp; q < ntile; q += NW) {  // X21 = -X22 * W  (k <= row of the tile: X22 is lower triangular)
+      const int p = q / tpp, tile = q % tpp;
+      const int o = p * 2 * sz;
+      const int r0 = 8 * (tile / tps), c0i = 8 * (tile % tps);
+      double c0 = 0.0, c1 = 0.0;
+      tile_mma<false>(c0, c1, s + (o + sz + r0) + (o + sz) * DG_LD, DG_LD, w + p * sz + c0i * DG_WLD, DG_WLD, r0 + 8,
+                      0x80000000u, g, t);
+      double* xp = s + (o + sz + r0 + g) + (o + c0i + 2 * t) * DG_LD;
+      xp[0] = c0;
+      xp[DG_LD] = c1;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int q = warp; q < 32; q += DG_THREADS / 32) {  // X21 = -X22 * W
-    int p = q >> 4, tile = q & 15;
-    int o = p * 64;
-    int r0 = 8 * (tile >> 2), c0i = 8 * (tile & 3);
-    double c0 = 0.0, c1 = 0.0;
-    tile_mma<false>(c0, c1, s + (o + 32 + r0) + (o + 32) * DG_LD, DG_LD, w + p * 32 + c0i * DG_WLD, DG_WLD, 32, true, g,
-                    t);
-    double* xp = s + (o + 32 + r0 + g) + (o + c0i + 2 * t) * DG_LD;
-    xp[0] = c0;
-    xp[DG_LD] = c1;
-  }
-  __syncthreads();
-  DG_TS(16);
-  // ---------------- level 2: 64-blocks ----------------
-  for (int q = warp; q < 64; q += DG_THREADS / 32) {  // W = L21 * X11, k >= 32*colblock
-    int r0 = 8 * (q >> 3), c0i = 8 * (q & 7);
-    int kbeg = (c0i >= 32) ? 32 : 0;
-    double c0 = 0.0, c1 = 0.0;
-    tile_mma<false>(c0, c1, s + (64 + r0) + kbeg * DG_LD, DG_LD, s + kbeg + c0i * DG_LD, DG_LD, 64 - kbeg, false, g, t);
-    double* wp = w + (r0 + g) + (c0i + 2 * t) * DG_WLD;
-    wp[0] = c0;
-    wp[DG_WLD] = c1;
-  }
-  __syncthreads();
-  for (int q = warp; q < 64; q += DG_THREADS / 32) {  // X21 = -X22 * W, k < 32*(rowblock+1)
-    int r0 = 8 * (q >> 3), c0i = 8 * (q & 7);
-    int kend = (r0 >= 32) ? 64 : 32;
-    double c0 = 0.0, c1 = 0.0;
-    tile_mma<false>(c0, c1, s + (64 + r0) + 64 * DG_LD, DG_LD, w + c0i * DG_WLD, DG_WLD, kend, true, g, t);
-    double* xp = s + (64 + r0 + g) + (c0i + 2 * t) * DG_LD;
-    xp[0] = c0;
-    xp[DG_LD] = c1;
-  }
-  __syncthreads();
   DG_TS(17);
   for (int idx = tid; idx < TB * TB; idx += DG_THREADS) {
     int r = idx & 127, c = idx >> 7;

@@ -11,6 +11,9 @@ m = G.GPModel(Y, X); p0 = default_initparst(3, True)
 for _ in range(3): m.likegrad(p0, 1.0, None, None, True)
 ts = (C.c_longlong * 32)()
 G.lib().gpedm_debug_diag_timing(ts)
-t = np.array(ts[:19]); print('cycles since start:', (t - t[0]).tolist()); print('deltas:', np.diff(t).tolist())
-names = ['load','chol0','panel0','trail0','chol1','panel1','trail1','chol2','panel2','trail2','chol3','panel3','trail3','storeL+logdet','inv32','lvl1','lvl2','storeD']
-print({n: int(d) for n, d in zip(names, np.diff(t))})
+t = np.array(ts[:19], dtype=np.int64)
+idx = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 14, 15, 17, 18]
+names = ['load', 'chol0', 'panel0', 'diagupd0', 'chol1+trail0', 'panel1', 'diagupd1', 'chol2+trail1', 'panel2', 'diagupd2',
+         'chol3', 'storeL+logdet', 'inv8', 'doubling', 'storeD']
+tt = t[idx]
+print({n: int(d) for n, d in zip(names, np.diff(tt))}, 'total', int(tt[-1] - tt[0]))
