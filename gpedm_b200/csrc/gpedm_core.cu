@@ -67,6 +67,8 @@ struct gpedm_fit_s {
   int* dinfo = nullptr;
   int* hinfo = nullptr;  // pinned
   int num_sms = 148;
+  cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // gradient-only / full / through-z variants
+  int64_t graph_launches[3] = {0, 0, 0};
   cudaStream_t stream = nullptr;
   cudaStream_t aux = nullptr;  // high-priority stream for the look-ahead chain (diag, panel, next column)
   std::vector<cudaEvent_t> evPanel, evTrail;
@@ -91,6 +93,8 @@ static const bool g_no_lookahead = getenv("GPEDM_NO_LOOKAHEAD") != nullptr && at
 static const int g_group = getenv("GPEDM_POTRF_GROUP") ? std::max(1, atoi(getenv("GPEDM_POTRF_GROUP"))) : 2;
 static const int g_group_min = getenv("GPEDM_POTRF_GROUP_MIN") ? atoi(getenv("GPEDM_POTRF_GROUP_MIN")) : 24;
 static const bool g_no_split = getenv("GPEDM_NO_SPLIT") != nullptr && atoi(getenv("GPEDM_NO_SPLIT")) != 0;
+static const int g_graph_max_nb = getenv("GPEDM_GRAPH_MAX_NB") ? atoi(getenv("GPEDM_GRAPH_MAX_NB")) : 48;
+static const bool g_no_graph = getenv("GPEDM_NO_GRAPH") != nullptr && atoi(getenv("GPEDM_NO_GRAPH")) != 0;
 static const bool g_diag_ref = getenv("GPEDM_DIAG_REF") != nullptr && atoi(getenv("GPEDM_DIAG_REF")) != 0;
 static int ensure_kernel_attrs(int device) {
   if (device < 64 && g_attr_set[device]) return 0;
@@ -160,6 +164,8 @@ static void free_handle(gpedm_fit_s* h) {
   if (h->hparams) cudaFreeHost(h->hparams);
   if (h->hscal) cudaFreeHost(h->hscal);
   if (h->hinfo) cudaFreeHost(h->hinfo);
+  for (auto& g : h->graph_exec)
+    if (g) cudaGraphExecDestroy(g);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : h->evPanel) cudaEventDestroy(e);
@@ -318,23 +324,30 @@ static TileOp make_op(int type, int ntiles, int nb) {
   return op;
 }
 
+// Phase-timing events must stay usable from outside when the launch sequence is captured into a
+// CUDA graph: record them as "external" event nodes during capture.
+static thread_local bool g_capturing = false;  // set only inside enqueue_eval while capturing
+static cudaError_t record_phase_event(cudaEvent_t ev, cudaStream_t st) {
+  return g_capturing ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
+}
+
 // ------------------------------------------------------------------------------- pipeline
 // Enqueue the device work of one evaluation on h->stream.  h->hparams must be filled.
 // stages: through z/a (need_inverse_products=false stops after z for the sequential helper).
-static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) {
+static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   cudaStream_t st = h->stream;
   const int nb = h->nb, Np = h->Np, N = (int)h->N, d = h->d;
   const size_t ld = Np;
   CU(cudaMemcpyAsync(h->dparams, h->hparams, sizeof(EvalParams), cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(h->dinfo, 0, 4, st));
-  CU(cudaEventRecord(h->ev[0], st));
+  CU(record_phase_event(h->ev[0], st));
   // --- assemble Sigma (lower tiles) into bufA
   {
     int smem = 2 * d * TB * 8 + 2 * TB * 4;
     assemble_sigma_kernel<<<h->ntiles, 256, smem, st>>>(h->bufA, ld, N, h->dX, h->dpop, h->drhotab, h->dparams);
     h->launches++;
   }
-  CU(cudaEventRecord(h->ev[1], st));
+  CU(record_phase_event(h->ev[1], st));
   // --- Cholesky, right-looking over 128-wide block columns, with look-ahead and grouped updates.
   // Steps are processed in groups [g0, g1) of G block columns (G = GPEDM_POTRF_GROUP while the
   // trailing matrix is large, 1 near the end); [g1, g2) is the next group.
@@ -411,7 +424,7 @@ static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) 
     CU(cudaEventRecord(h->evJoin, ax));
     CU(cudaStreamWaitEvent(st, h->evJoin, 0));
   }
-  CU(cudaEventRecord(h->ev[2], st));
+  CU(record_phase_event(h->ev[2], st));
   // --- triangular inverse X = L^-1 by recursive doubling (diagonal blocks already in bufB)
   for (int s = 1; s < nb; s *= 2) {
     const int pf = nb / (2 * s);
@@ -434,13 +447,13 @@ static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) 
     rc = launch_tiles(h, st, x, 1);
     if (rc) return rc;
   }
-  CU(cudaEventRecord(h->ev[3], st));
+  CU(record_phase_event(h->ev[3], st));
   // --- z = X Y
   trmv_n_part_kernel<<<h->ntiles, 256, 0, st>>>(h->bufB, ld, h->dY, h->dpart, ld);
   reduce_parts_kernel<<<ceil_div(Np, 256), 256, 0, st>>>(h->dpart, ld, nb, 0, h->dz, Np);
   h->launches += 2;
   if (through_z_only) {
-    CU(cudaEventRecord(h->ev[4], st));
+    CU(record_phase_event(h->ev[4], st));
     CU(cudaMemcpyAsync(h->hinfo, h->dinfo, 4, cudaMemcpyDeviceToHost, st));
     return 0;
   }
@@ -448,7 +461,7 @@ static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) 
   trmv_t_part_kernel<<<h->ntiles, 256, 0, st>>>(h->bufB, ld, h->dz, h->dpart, ld);
   reduce_parts_kernel<<<ceil_div(Np, 256), 256, 0, st>>>(h->dpart, ld, nb, 1, h->da, Np);
   h->launches += 2;
-  CU(cudaEventRecord(h->ev[4], st));
+  CU(record_phase_event(h->ev[4], st));
   // --- S = Sigma^-1 = X^T X (lower tiles) into bufC
   {
     TileOp lu = make_op(OP_LAUUM, h->ntiles, nb);
@@ -458,7 +471,7 @@ static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) 
     int rc = launch_tiles(h, st, lu, 2);
     if (rc) return rc;
   }
-  CU(cudaEventRecord(h->ev[5], st));
+  CU(record_phase_event(h->ev[5], st));
   // --- gradient trace terms + scalar reductions
   {
     int DC = d <= 8 ? 8 : (d <= 16 ? 16 : 32);
@@ -481,9 +494,42 @@ static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) 
                                            d + 3, full ? 1 : 0, h->dscal);
     h->launches++;
   }
-  CU(cudaEventRecord(h->ev[6], st));
+  CU(record_phase_event(h->ev[6], st));
   CU(cudaMemcpyAsync(h->hscal, h->dscal, NSCAL * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h->hinfo, h->dinfo, 4, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+
+// One evaluation = a fixed launch sequence on two streams (parameters live in device memory), so
+// it is captured once per handle and variant into a CUDA graph and replayed: one graph launch
+// instead of hundreds of kernel launches / event waits per evaluation.
+static int enqueue_eval(gpedm_fit_s* h, bool full, bool through_z_only = false) {
+  // Above ~48 block columns the bulk kernels dominate and the stream-priority look-ahead (which the
+  // graph replay does not honour as well as live streams do, measured) matters more than launch cost.
+  if (g_no_graph || h->nb > g_graph_max_nb) return enqueue_eval_raw(h, full, through_z_only);
+  const int v = through_z_only ? 2 : (full ? 1 : 0);
+  if (!h->graph_exec[v]) {
+    const int64_t l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    g_capturing = true;
+    int rc = enqueue_eval_raw(h, full, through_z_only);
+    g_capturing = false;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->graph_exec[v], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(e));
+    h->graph_launches[v] = h->launches - l0;
+    h->launches = l0;
+  }
+  CU(cudaGraphLaunch(h->graph_exec[v], h->stream));
+  h->launches += h->graph_launches[v];
   return 0;
 }
 
