@@ -56,6 +56,91 @@ __device__ __forceinline__ void tile_mma(double& c0, double& c1, const double* A
   dmma884(c0, c1, flip_sign(a1, sgn), b1);
 }
 
+
+// RG output tiles at once that share one operand: SHARE_B (tiles stacked along rows: distinct A
+// row blocks 8 rows apart, common B) or shared A (tiles side by side: common A, distinct B column
+// blocks 8 columns apart).  The RG independent DMMA chains hide each other's latency.
+// All operands are plain (non-transposed) here: element (k,n) of B = Bm[k][n].
+template <int RG, bool SHARE_B>
+__device__ __forceinline__ void tile_mma_multi(double (&c)[RG][2], const double* Abase, int lda, const double* Bbase,
+                                               int ldb, int K, unsigned sgn, int g, int t) {
+  const double* ap = Abase + g + t * lda;
+  const double* bp = Bbase + t + g * ldb;
+  for (int k = 0; k < K; k += 4) {
+    if (SHARE_B) {
+      const double b = bp[0];
+#pragma unroll
+      for (int r = 0; r < RG; ++r) dmma884(c[r][0], c[r][1], flip_sign(ap[8 * r], sgn), b);
+    } else {
+      const double a = flip_sign(ap[0], sgn);
+#pragma unroll
+      for (int r = 0; r < RG; ++r) dmma884(c[r][0], c[r][1], a, bp[8 * r * ldb]);
+    }
+    ap += 4 * lda;
+    bp += 4;
+  }
+}
+
+// One level of the recursive doubling (block size sz, RG = tiles per warp).
+template <int RG>
+__device__ __forceinline__ void doubling_level(double* s, double* w, int sz, int warp, int g, int t) {
+  constexpr int NW = DG_THREADS / 32;
+  const int tps = sz >> 3;              // 8x8 tiles per block edge
+  const int gpp = tps * tps / RG;       // tile groups per pair
+  const int ngroups = (TB / (2 * sz)) * gpp;
+  const int gpl = tps / RG;             // groups per column (W) / per row (X)
+  // W = L21 * X11: a group = RG vertically stacked tiles of one tile column (same k range, same B)
+  for (int q = warp; q < ngroups; q += NW) {
+    const int p = q / gpp, gi = q % gpp;
+    const int o = p * 2 * sz;
+    const int c0i = 8 * (gi / gpl), r0 = 8 * RG * (gi % gpl);
+    double c[RG][2];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) c[r][0] = c[r][1] = 0.0;
+    tile_mma_multi<RG, true>(c, s + (o + sz + r0) + (o + c0i) * DG_LD, DG_LD, s + (o + c0i) + (o + c0i) * DG_LD, DG_LD,
+                             sz - c0i, 0u, g, t);
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+      double* wp = w + (p * sz + r0 + 8 * r + g) + (c0i + 2 * t) * DG_WLD;
+      wp[0] = c[r][0];
+      wp[DG_WLD] = c[r][1];
+    }
+  }
+  __syncthreads();
+  // X21 = -X22 * W: a group = RG tiles side by side in one tile row (same k range, same A)
+  for (int q = warp; q < ngroups; q += NW) {
+    const int p = q / gpp, gi = q % gpp;
+    const int o = p * 2 * sz;
+    const int r0 = 8 * (gi / gpl), c0i = 8 * RG * (gi % gpl);
+    double c[RG][2];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) c[r][0] = c[r][1] = 0.0;
+    tile_mma_multi<RG, false>(c, s + (o + sz + r0) + (o + sz) * DG_LD, DG_LD, w + p * sz + c0i * DG_WLD, DG_WLD, r0 + 8,
+                              0x80000000u, g, t);
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+      double* xp = s + (o + sz + r0 + g) + (o + c0i + 8 * r + 2 * t) * DG_LD;
+      xp[0] = c[r][0];
+      xp[DG_LD] = c[r][1];
+    }
+  }
+  __syncthreads();
+}
+
+// Reciprocal square root for the pivot chain: the library rsqrt() is a ~35-instruction dependent
+// sequence (special-case handling + refinement) and dominates the per-column latency of the
+// warp-level factorisation.  Pivots here are ordinary positive numbers (ve <= pivot <= sigma2+ve), so
+// start from the hardware approximation (rsqrt.approx.f64, ~2^-22) and apply one cubically convergent
+// Halley step: y' = y (1 + e/2 + 3e^2/8), e = 1 - x y^2  ->  relative error ~1e-19 before rounding.
+// Non-positive / NaN pivots still produce NaN / inf and are flagged by the caller.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);
+  const double q = e * fma(0.375, e, 0.5);
+  return fma(y, q, y);
+}
+
 // 32x32 Cholesky of the diagonal block at `base` by one warp (lane = row).
 __device__ __noinline__ void chol32_warp(double* s, double* rdiag, double* dvec, double* colbuf, int base,
                                             int lane, int kblock, int n_valid, int* info) {
@@ -64,7 +149,7 @@ __device__ __noinline__ void chol32_warp(double* s, double* rdiag, double* dvec,
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = s[(base + lane) + (base + c) * DG_LD];
   double ajj = __shfl_sync(FULL, a[0], 0);
-  double rs = rsqrt(ajj);
+  double rs = fast_rsqrt(ajj);
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const double l = a[j] * rs;  // L[lane][j]
@@ -79,7 +164,7 @@ __device__ __noinline__ void chol32_warp(double* s, double* rdiag, double* dvec,
       // lane j+1 owns the next pivot and can update it with its own l: start the broadcast + rsqrt now
       const double piv = fma(-l, l, a[j + 1]);
       ajj_n = __shfl_sync(FULL, piv, j + 1);
-      rs_n = rsqrt(ajj_n);
+      rs_n = fast_rsqrt(ajj_n);
     }
     double* cb = colbuf + (j & 1) * 32;
     cb[lane] = l;
@@ -226,36 +311,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
   __syncthreads();
   DG_TS(15);
   // ---------------- recursive doubling: block sizes 8, 16, 32, 64 ----------------
-#pragma unroll 1
-  for (int sz = 8; sz <= 64; sz *= 2) {
-    const int tps = sz >> 3;               // 8x8 tiles per block edge
-    const int tpp = tps * tps;             // tiles per pair
-    const int ntile = (TB / (2 * sz)) * tpp;
-    for (int q = warp; q < ntile; q += NW) {  // W = L21 * X11  (k >= column of the tile: X11 is lower triangular)
-      const int p = q / tpp, tile = q % tpp;
-      const int o = p * 2 * sz;
-      const int r0 = 8 * (tile / tps), c0i = 8 * (tile % tps);
-      double c0 = 0.0, c1 = 0.0;
-      tile_mma<false>(c0, c1, s + (o + sz + r0) + (o + c0i) * DG_LD, DG_LD, s + (o + c0i) + (o + c0i) * DG_LD, DG_LD,
-                      sz - c0i, 0u, g, t);
-      double* wp = w + (p * sz + r0 + g) + (c0i + 2 * t) * DG_WLD;
-      wp[0] = c0;
-      wp[DG_WLD] = c1;
-    }
-    __syncthreads();
-    for (int q = warp; q < ntile; q += NW) {  // X21 = -X22 * W  (k <= row of the tile: X22 is lower triangular)
-      const int p = q / tpp, tile = q % tpp;
-      const int o = p * 2 * sz;
-      const int r0 = 8 * (tile / tps), c0i = 8 * (tile % tps);
-      double c0 = 0.0, c1 = 0.0;
-      tile_mma<false>(c0, c1, s + (o + sz + r0) + (o + sz) * DG_LD, DG_LD, w + p * sz + c0i * DG_WLD, DG_WLD, r0 + 8,
-                      0x80000000u, g, t);
-      double* xp = s + (o + sz + r0 + g) + (o + c0i + 2 * t) * DG_LD;
-      xp[0] = c0;
-      xp[DG_LD] = c1;
-    }
-    __syncthreads();
-  }
+  doubling_level<1>(s, w, 8, warp, g, t);    //  8 tiles
+  doubling_level<1>(s, w, 16, warp, g, t);   // 16 tiles
+  doubling_level<2>(s, w, 32, warp, g, t);   // 32 tiles, 2 per warp
+  doubling_level<4>(s, w, 64, warp, g, t);   // 64 tiles, 4 per warp
   DG_TS(17);
   for (int idx = tid; idx < TB * TB; idx += DG_THREADS) {
     int r = idx & 127, c = idx >> 7;
