@@ -518,6 +518,110 @@ def predict_seq(obj, newdata, restart_initpars=False):
     return model
 
 
+def predict_iter(obj, newdata, xlags=None):
+    """Iterated multi-step forecasts (reference R/predict_iter.R:57-163, non-fisheries models): predict one
+    time step, feed the prediction in as the first lag of the next step, shift the other lags."""
+    inp = obj["inputs"]
+    if inp.get("time_names") is None:
+        raise ValueError("Model must include `data` and `time` to use this function.")
+    if inp.get("E") is not None:
+        raise ValueError("Lags must be pre-generated to use this function. See option A1 in help(fitGP).")
+    tn = inp["time_names"]
+    if tn not in newdata:
+        raise ValueError("Time column '%s' not found in newdata." % tn)
+    if xlags is None:
+        xlags = list(inp["x_names"])
+    nd = {k: np.array(v, dtype=object if np.asarray(v).dtype == object else np.float64) for k, v in newdata.items()}
+    has_pop = inp.get("pop_names") is not None
+    pn = inp["pop_names"] if has_pop else "pop"
+    if not has_pop:
+        nd[pn] = np.ones(len(nd[tn]), dtype=np.int64).astype(object)
+    elif pn not in nd:
+        raise ValueError("Pop column '%s' not found in newdata." % pn)
+    newtimes = unique_stable(nd[tn].tolist())
+    up = unique_stable(nd[pn])
+    preds = []
+    for i, t in enumerate(newtimes):
+        mask = nd[tn] == t
+        cur = _rows(nd, mask)
+        if not has_pop:
+            cur = {k: v for k, v in cur.items() if k != pn}
+        pr = predict(obj, newdata=cur)["outsampresults"]
+        preds.append(pr)
+        if np.any(np.isinf(pr["predmean"])):
+            break
+        if i + 1 < len(newtimes):
+            nxt = nd[tn] == newtimes[i + 1]
+            for u in up:
+                pj = pr["predmean"][np.asarray(pr["pop"], dtype=object) == u] if has_pop else pr["predmean"]
+                sel_n, sel_c = nxt & (nd[pn] == u), mask & (nd[pn] == u)
+                old = [nd[c][sel_c].copy() for c in xlags]
+                nd[xlags[0]][sel_n] = pj
+                for q in range(1, len(xlags)):
+                    nd[xlags[q]][sel_n] = old[q - 1]
+    res = preds[0]
+    for p_ in preds[1:]:
+        res = _rbind(res, p_)
+    out = {"outsampresults": res}
+    if "obs" in res and not np.all(np.isnan(np.asarray(res["obs"], dtype=float))):
+        out["outsampfitstats"] = dict(R2=getR2(res["obs"], res["predmean"]),
+                                      rmse=math.sqrt(_mean((np.asarray(res["obs"], float) - res["predmean"]) ** 2)))
+        if len(unique_stable(res["pop"])) > 1:
+            out["outsampfitstatspop"] = getR2pop(res["obs"], res["predmean"], res["pop"])
+    return out
+
+
+def getconditionals(fit, xrange="default", extrap=0.01, nvals=25):
+    """Conditional responses (reference R/PlotsConditionals.R:166-266, without the plot): for every
+    population and predictor, `nvals` points along that predictor with the other scaled predictors at
+    0.  All np x d x nvals slice points go to the GPU in ONE predict_new call against the resident
+    factorisation (the reference issues np*d getcov calls and np*d*nvals quadratic forms).
+    Returns one dict per population: poppred, xval, predmean, predsd (each nvals x d)."""
+    inp, sc = fit["inputs"], fit["scaling"]
+    X, Pop = inp["X"], np.asarray(inp["Pop"], dtype=object)
+    d = X.shape[1]
+    scaling = sc["scaling"]
+    if xrange not in ("default", "local", "global"):
+        raise ValueError("xrange must be one of default, local, global")
+    xr = ("local" if scaling == "local" else "global") if xrange == "default" else xrange
+    up = unique_stable(Pop)
+    pts, pops, grids = [], [], {}
+    for u in up:
+        indi = Pop == u
+        for i in range(d):
+            if xr == "local":
+                ext = (X[indi, i].max() - X[indi, i].min()) * extrap
+                xgi = np.linspace(X[indi, i].min() - ext, X[indi, i].max() + ext, nvals)
+            else:  # quirk kept: upper end from max over the whole X matrix (:205)
+                ext = (X[:, i].max() - X[:, i].min()) * extrap
+                xgi = np.linspace(X[:, i].min() - ext, X.max() + ext, nvals)
+            xp = np.zeros((nvals, d))
+            xp[:, i] = xgi
+            pts.append(xp)
+            pops.extend([u] * nvals)
+            grids[(u, i)] = xgi
+    mean, var, _ = fit["model"].predict_new(np.vstack(pts), np.array(pops, dtype=object))
+    out, k = [], 0
+    for u in up:
+        xval, pm, ps = np.zeros((nvals, d)), np.zeros((nvals, d)), np.zeros((nvals, d))
+        for i in range(d):
+            pm[:, i] = mean[k:k + nvals]
+            with np.errstate(invalid="ignore"):
+                ps[:, i] = np.sqrt(var[k:k + nvals])
+            xval[:, i] = grids[(u, i)]
+            k += nvals
+        if scaling == "global":
+            pm = pm * sc["ysds"] + sc["ymeans"]
+            ps = np.sqrt(ps ** 2 * sc["ysds"] ** 2)
+            xval = xval * sc["xsds"][None, :] + sc["xmeans"][None, :]
+        if scaling == "local":
+            pm = pm * sc["ysds"][u] + sc["ymeans"][u]
+            ps = np.sqrt(ps ** 2 * sc["ysds"][u] ** 2)
+            xval = xval * sc["xsds"][u][None, :] + sc["xmeans"][u][None, :]
+        out.append(dict(poppred=np.array([u] * nvals, dtype=object), xval=xval, predmean=pm, predsd=ps))
+    return out
+
+
 def summary(obj):
     """Text summary in the layout of summary.GP (R/PlotsConditionals.R:10-52)."""
     d = obj["inputs"]["X"].shape[1]

@@ -732,6 +732,100 @@ def predict_seq(obj, data, newdata, restart_initpars=False):
     return model
 
 
+def predict_iter(obj, newdata, xlags=None):
+    """R/predict_iter.R:57-163 (non-fisheries): iterated multi-step forecasts; the prediction at one
+    time step becomes the first lag of the next, the other lags shift."""
+    inp = obj["inputs"]
+    if inp.get("time_names") is None:
+        raise ValueError("Model must include `data` and `time` to use this function.")
+    if inp.get("E") is not None:
+        raise ValueError("Lags must be pre-generated to use this function. See option A1 in help(fitGP).")
+    tn = inp["time_names"]
+    if tn not in newdata:
+        raise ValueError("Time column '%s' not found in newdata." % tn)
+    if xlags is None:
+        xlags = list(inp["x_names"])
+    nd = {k: np.array(v, dtype=object if np.asarray(v).dtype == object else np.float64) for k, v in newdata.items()}
+    pn = inp.get("pop_names")
+    if pn is None:
+        pn = "pop"
+        nd[pn] = np.array([1] * len(nd[tn]), dtype=object)
+    elif pn not in nd:
+        raise ValueError("Pop column '%s' not found in newdata." % pn)
+    newtimes = unique_stable(nd[tn].tolist())
+    up = unique_stable(nd[pn])
+    preds = []
+    for i, t in enumerate(newtimes):
+        mask = nd[tn] == t
+        cur = _rows(nd, mask)
+        if inp.get("pop_names") is None:
+            cur = {k: v for k, v in cur.items() if k != pn}
+        pr = predict(obj, newdata=cur)["outsampresults"]
+        preds.append(pr)
+        if np.any(np.isinf(pr["predmean"])):
+            break
+        if i + 1 < len(newtimes):
+            nxt = nd[tn] == newtimes[i + 1]
+            for u in up:
+                pj = pr["predmean"][np.asarray(pr["pop"], dtype=object) == u] if inp.get("pop_names") is not None else pr["predmean"]
+                sel_n = nxt & (nd[pn] == u)
+                sel_c = mask & (nd[pn] == u)
+                old = [nd[c][sel_c].copy() for c in xlags]
+                nd[xlags[0]][sel_n] = pj
+                for q in range(1, len(xlags)):
+                    nd[xlags[q]][sel_n] = old[q - 1]
+    res = preds[0]
+    for p_ in preds[1:]:
+        res = _rbind(res, p_)
+    out = {"outsampresults": res}
+    if "obs" in res and not np.all(np.isnan(np.asarray(res["obs"], dtype=float))):
+        out["outsampfitstats"] = dict(R2=getR2(res["obs"], res["predmean"]),
+                                      rmse=math.sqrt(_mean((np.asarray(res["obs"], float) - res["predmean"]) ** 2)))
+    return out
+
+
+def getconditionals(fit, xrange="default", extrap=0.01, nvals=25):
+    """R/PlotsConditionals.R:166-266: conditional responses - for every population and predictor, nvals
+    points along that predictor with all other (scaled) predictors held at 0.  Returns one dict per
+    population: poppred, xval, predmean, predsd (each nvals x d), unscaled like the reference.
+    Quirk kept: with xrange global the upper end uses max(X[]) over the whole matrix (:205)."""
+    pars = fit["pars"]
+    inp, sc = fit["inputs"], fit["scaling"]
+    X, Y, Pop = inp["X"], inp["Y"], np.asarray(inp["Pop"], dtype=object)
+    d = X.shape[1]
+    phi, ve, sigma2, rho = pars[:d], pars[d], pars[d + 1], pars[d + 2]
+    iKVs = fit["covm"]["iKVs"]
+    scaling = sc["scaling"]
+    xr = ("local" if scaling == "local" else "global") if xrange == "default" else xrange
+    out = []
+    for u in unique_stable(Pop):
+        indi = Pop == u
+        xval, pm, ps = np.zeros((nvals, d)), np.zeros((nvals, d)), np.zeros((nvals, d))
+        poppred = np.array([u] * nvals, dtype=object)
+        for i in range(d):
+            if xr == "local":
+                ext = (X[indi, i].max() - X[indi, i].min()) * extrap
+                xgi = np.linspace(X[indi, i].min() - ext, X[indi, i].max() + ext, nvals)
+            else:
+                ext = (X[:, i].max() - X[:, i].min()) * extrap
+                xgi = np.linspace(X[:, i].min() - ext, X.max() + ext, nvals)
+            xp = np.zeros((nvals, d))
+            xp[:, i] = xgi
+            m, v, _ = predict_newdata_core(phi, sigma2, rho, ve, X, Y, Pop, iKVs, xp, poppred, inp.get("rhomatrix"),
+                                           inp.get("rhomatrix_names"))
+            pm[:, i], ps[:, i], xval[:, i] = m, np.sqrt(v), xgi
+        if scaling == "global":
+            pm = pm * sc["ysds"] + sc["ymeans"]
+            ps = np.sqrt(ps ** 2 * sc["ysds"] ** 2)
+            xval = xval * sc["xsds"][None, :] + sc["xmeans"][None, :]
+        if scaling == "local":
+            pm = pm * sc["ysds"][u] + sc["ymeans"][u]
+            ps = np.sqrt(ps ** 2 * sc["ysds"][u] ** 2)
+            xval = xval * sc["xsds"][u][None, :] + sc["xmeans"][u][None, :]
+        out.append(dict(poppred=poppred, xval=xval, predmean=pm, predsd=ps))
+    return out
+
+
 # ------------------------------------------------------------------ extended precision
 def chol_lower_ld(S):
     """Cholesky (lower) in x87 80-bit long double; O(N) python steps of vectorised numpy."""

@@ -384,3 +384,35 @@ def test_batch_two_gpus_nccl_gather(gpu_lib):
     two = G.fit_batch(probs, ngpus=2)
     for a, b in zip(one, two):
         assert a["iter"] == b["iter"] and a["nllpost"] == b["nllpost"] and np.array_equal(a["pars"], b["pars"])
+
+
+def test_predict_iter_and_getconditionals(gpu_lib, thetalog2pop):
+    """'next' row of SURVEY section 8f: predict_iter (R/predict_iter.R:57-163) and getconditionals
+    (R/PlotsConditionals.R:166-266) on the resident factorisation, against the oracle and the README's
+    iterated-forecast rows (README.md:444-456)."""
+    tl = thetalog2pop
+    d1 = G.makelags(data=tl, y="Abundance", pop="Population", time="Time", E=3, tau=1, append=True)
+    fore = G.makelags(data=tl, y="Abundance", pop="Population", time="Time", E=3, tau=1, forecast=True)
+    cols = ["Abundance_1", "Abundance_2", "Abundance_3"]
+    kw = dict(y="Abundance", x=cols, pop="Population", time="Time", scaling="local")
+    g = G.fitGP(data=d1, **kw)
+    o = O.fitGP(data=d1, **kw)
+    nd = {"Time": np.array([51., 51., 52., 52., 53., 53., 54., 54.]), "Population": np.array(["PopA", "PopB"] * 4, dtype=object)}
+    for c in cols:
+        nd[c] = np.concatenate([fore[c], np.full(6, np.nan)])
+    rg = G.predict_iter(g, nd)["outsampresults"]
+    ro = O.predict_iter(o, nd)["outsampresults"]
+    np.testing.assert_allclose(rg["predmean"], ro["predmean"], atol=1e-8)
+    np.testing.assert_allclose(rg["predsd"], ro["predsd"], rtol=1e-6)
+    assert ["%.7g" % v for v in rg["predmean"][:6]] == ["0.04932054", "1.416254", "0.15775", "0.265825", "0.5336754", "0.8318641"]
+    cg = G.getconditionals(g)
+    co = O.getconditionals(o)
+    assert len(cg) == 2
+    for a, b in zip(cg, co):
+        np.testing.assert_allclose(a["xval"], b["xval"], rtol=1e-13)
+        np.testing.assert_allclose(a["predmean"], b["predmean"], atol=1e-8)
+        np.testing.assert_allclose(a["predsd"], b["predsd"], rtol=1e-5, atol=1e-9)
+    cg2 = G.getconditionals(g, xrange="global", nvals=7)
+    co2 = O.getconditionals(o, xrange="global", nvals=7)
+    np.testing.assert_allclose(cg2[1]["predmean"], co2[1]["predmean"], atol=1e-8)
+    g.close()

@@ -125,3 +125,31 @@ def test_extended_precision_oracle_consistent(k1):
     like64 = -(k1["nllpost"] if "nllpost" in k1 else -k1["insampfitstats"]["ln_post"]) - k1["insampfitstats"]["ln_prior"]
     assert abs(float(like) - like64) / abs(like64) < 1e-12
     np.testing.assert_allclose(np.diag(k1["covm"]["iKVs"]), np.asarray(dinv, dtype=float), rtol=1e-9)
+
+
+def test_K4_predict_iter_readme_444_456(thetalog2pop):
+    """Rows 3-6 of the README forecast table are iterated forecasts (predict_iter)."""
+    tl = thetalog2pop
+    lags = O.makelags_subrt(tl["Abundance"], tl["Population"], 3, 1)
+    fore = O.makelags_subrt(tl["Abundance"], tl["Population"], 3, 1, forecast=True)
+    d = dict(tl)
+    cols = ["Abundance_%d" % (i + 1) for i in range(3)]
+    for i, c in enumerate(cols):
+        d[c] = lags[:, i]
+    m = O.fitGP(data=d, y="Abundance", x=cols, pop="Population", time="Time", scaling="local")
+    # README.md:425-437: first forecast rows from makelags(forecast=T), later time points empty
+    times = np.concatenate([[51., 51.], np.repeat(np.arange(52., 54.), 1).repeat(2)])
+    pops = np.array(["PopA", "PopB"] * 3, dtype=object)
+    nd = {"Time": np.array([51., 51., 52., 52., 53., 53.]), "Population": pops}
+    for i, c in enumerate(cols):
+        nd[c] = np.concatenate([fore[:, i], np.full(4, np.nan)])
+    r = O.predict_iter(m, nd)["outsampresults"]
+    want_mean = [0.04932054, 1.41625389, 0.15774996, 0.26582495, 0.53367538, 0.83186406]
+    want_fsd = [0.01647408, 0.01679414, 0.01367564, 0.01688767, 0.01829694, 0.01782242]
+    want_sd = [0.06829043, 0.04612410, 0.06766986, 0.04615824, 0.06875293, 0.04650837]
+    for got, ref in zip(r["predmean"], want_mean):
+        assert digits(got, ref, 7), (got, ref)
+    for got, ref in zip(r["predfsd"], want_fsd):
+        assert digits(got, ref, 7), (got, ref)
+    for got, ref in zip(r["predsd"], want_sd):
+        assert digits(got, ref, 7), (got, ref)
