@@ -32,26 +32,30 @@ constexpr int TB = 128;  // tile edge
 // TM = 128 is the bulk shape; TM = 32 splits one 128 x 128 tile over four CTAs for the
 // latency-critical chain of the Cholesky (panel + next-column update), where there are fewer
 // tiles than SMs.
-template <int WM_, int WN_, int BK_, int NSTAGE_, int TM_ = 128>
+template <int WM_, int WN_, int BK_, int NSTAGE_, int TM_ = 128, int TN_ = 128, int MINCTA_ = 1>
 struct GemmCfgT {
-  static constexpr int WM = WM_, WN = WN_, BK = BK_, NSTAGE = NSTAGE_, TM = TM_;
+  static constexpr int WM = WM_, WN = WN_, BK = BK_, NSTAGE = NSTAGE_, TM = TM_, TN = TN_, MINCTA = MINCTA_;
   static constexpr int THREADS = WM * WN * 32;
   static constexpr int MT = TM / WM / 8;  // 8-row DMMA tiles per warp along m
-  static constexpr int NT = TB / WN / 8;  // 8-col DMMA tiles per warp along n
+  static constexpr int NT = TN / WN / 8;  // 8-col DMMA tiles per warp along n
   static constexpr int LD_MN_A = TM + 4;  // smem row stride (doubles) of an MN-major A slab [BK][TM+4]
-  static constexpr int LD_MN_B = TB + 4;  // ... of an MN-major B slab [BK][132]
+  static constexpr int LD_MN_B = TN + 4;  // ... of an MN-major B slab [BK][TN+4]
   static constexpr int LD_K = BK + 4;     // smem row stride of a K-major slab [rows][BK+4]
   static constexpr int SLAB_A = (BK * LD_MN_A > TM * LD_K) ? BK * LD_MN_A : TM * LD_K;
-  static constexpr int SLAB_B = (BK * LD_MN_B > TB * LD_K) ? BK * LD_MN_B : TB * LD_K;
+  static constexpr int SLAB_B = (BK * LD_MN_B > TN * LD_K) ? BK * LD_MN_B : TN * LD_K;
   static constexpr int SMEM_BYTES = NSTAGE * (SLAB_A + SLAB_B) * (int)sizeof(double);
-  static_assert(TM % (WM * 8) == 0 && TB % (WN * 8) == 0, "warp grid must tile the output");
-  static_assert((TM + 4) % 16 == 4 && (BK + 4) % 16 == 4, "strides must be 4 mod 16 for conflict-free LDS.64");
+  static_assert(TM % (WM * 8) == 0 && TN % (WN * 8) == 0, "warp grid must tile the output");
+  static_assert((TM + 4) % 16 == 4 && (TN + 4) % 16 == 4 && (BK + 4) % 16 == 4,
+                "strides must be 4 mod 16 for conflict-free LDS.64");
 };
 #ifndef GPEDM_GEMM_CFG
 #define GPEDM_GEMM_CFG GemmCfgT<2, 4, 16, 4>
 #endif
 using GemmCfg = GPEDM_GEMM_CFG;
 using GemmCfgSplit = GemmCfgT<1, 8, 16, 4, 32>;  // 32 x 128 tiles, 8 warps of 32 x 16
+// 128 x 64 half tiles, 4 warps of 64 x 32, two CTAs resident per SM: the prologue (accumulate-from
+// load, pipeline fill) and epilogue (store) of one CTA overlap the k loop of the other.
+using GemmCfgHalf = GemmCfgT<2, 2, 16, 4, 128, 64, 2>;
 constexpr int GEMM_THREADS = GemmCfg::THREADS;
 constexpr int GEMM_SMEM_BYTES = GemmCfg::SMEM_BYTES;
 
@@ -134,7 +138,7 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, size_t l
   for (int s = 0; s < NS - 1; ++s) {
     if (s < nk) {
       load_slab<Cfg, A_KMAJOR, Cfg::TM>(sA + s * SLAB_A, A, lda, kbeg + s * BK, tid);
-      load_slab<Cfg, B_KMAJOR, TB>(sB + s * SLAB_B, B, ldb, kbeg + s * BK, tid);
+      load_slab<Cfg, B_KMAJOR, Cfg::TN>(sB + s * SLAB_B, B, ldb, kbeg + s * BK, tid);
     }
     cp_async_commit();
   }
@@ -163,7 +167,7 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, size_t l
       if (nxt < nk) {
         int sb = nxt % NS;
         load_slab<Cfg, A_KMAJOR, Cfg::TM>(sA + sb * SLAB_A, A, lda, kbeg + nxt * BK, tid);
-        load_slab<Cfg, B_KMAJOR, TB>(sB + sb * SLAB_B, B, ldb, kbeg + nxt * BK, tid);
+        load_slab<Cfg, B_KMAJOR, Cfg::TN>(sB + sb * SLAB_B, B, ldb, kbeg + nxt * BK, tid);
       }
       cp_async_commit();
     }
@@ -260,7 +264,7 @@ __device__ __forceinline__ void gemm_tile_mb(const double* __restrict__ A, size_
     const int s = j % NS, r = j / NS;
     if (r > 0) mbar_wait(&empty_bar[s], (unsigned)((r - 1) & 1));
     load_slab<Cfg, A_KMAJOR, Cfg::TM>(sA + s * SLAB_A, A, lda, kbeg + j * BK, tid);
-    load_slab<Cfg, B_KMAJOR, TB>(sB + s * SLAB_B, B, ldb, kbeg + j * BK, tid);
+    load_slab<Cfg, B_KMAJOR, Cfg::TN>(sB + s * SLAB_B, B, ldb, kbeg + j * BK, tid);
     mbar_cp_async_arrive(&full_bar[s]);
   };
 #pragma unroll

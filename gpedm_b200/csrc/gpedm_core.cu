@@ -92,6 +92,7 @@ static int g_num_sms[64] = {};
 static const bool g_no_lookahead = getenv("GPEDM_NO_LOOKAHEAD") != nullptr && atoi(getenv("GPEDM_NO_LOOKAHEAD")) != 0;
 static const int g_group = getenv("GPEDM_POTRF_GROUP") ? std::max(1, atoi(getenv("GPEDM_POTRF_GROUP"))) : 2;
 static const int g_group_min = getenv("GPEDM_POTRF_GROUP_MIN") ? atoi(getenv("GPEDM_POTRF_GROUP_MIN")) : 24;
+static const bool g_no_half_tiles = getenv("GPEDM_NO_HALF_TILES") != nullptr && atoi(getenv("GPEDM_NO_HALF_TILES")) != 0;
 static const bool g_no_split = getenv("GPEDM_NO_SPLIT") != nullptr && atoi(getenv("GPEDM_NO_SPLIT")) != 0;
 static const int g_graph_max_nb = getenv("GPEDM_GRAPH_MAX_NB") ? atoi(getenv("GPEDM_GRAPH_MAX_NB")) : 48;
 static const int g_batch_workers = getenv("GPEDM_BATCH_WORKERS_PER_GPU") ? atoi(getenv("GPEDM_BATCH_WORKERS_PER_GPU")) : 0;
@@ -104,6 +105,12 @@ static int ensure_kernel_attrs(int device) {
   CU(cudaFuncSetAttribute(tile_once_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CU(cudaFuncSetAttribute(tile_once_kernel<false, false, GemmCfgSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           GemmCfgSplit::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<false, false, GemmCfgHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          GemmCfgHalf::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<false, true, GemmCfgHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          GemmCfgHalf::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<true, true, GemmCfgHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          GemmCfgHalf::SMEM_BYTES));
   {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -311,7 +318,19 @@ static int launch_tiles(gpedm_fit_s* h, cudaStream_t st, const TileOp& op, int l
   if (split && layout == 0)  // latency-critical launch with fewer tiles than SMs: 4 row strips per tile
     tile_once_kernel<false, false, GemmCfgSplit>
         <<<op.ntiles * (TB / GemmCfgSplit::TM), GemmCfgSplit::THREADS, GemmCfgSplit::SMEM_BYTES, st>>>(op);
-  else if (layout == 0)
+  else if (!g_no_half_tiles && op.type != OP_PANEL && op.ntiles * 2 <= h->num_sms) {
+    // launches with fewer tiles than half the SMs (low levels of the triangular inverse, small N):
+    // 128 x 64 half tiles double the number of busy SMs.  (Measured slower than full tiles once the
+    // grid fills the chip, so only used below that point.  The panel stays on row strips / full
+    // tiles: it is updated in place and a column half would read columns another CTA overwrites.)
+    const int grid = op.ntiles * 2;
+    if (layout == 0)
+      tile_once_kernel<false, false, GemmCfgHalf><<<grid, GemmCfgHalf::THREADS, GemmCfgHalf::SMEM_BYTES, st>>>(op);
+    else if (layout == 1)
+      tile_once_kernel<false, true, GemmCfgHalf><<<grid, GemmCfgHalf::THREADS, GemmCfgHalf::SMEM_BYTES, st>>>(op);
+    else
+      tile_once_kernel<true, true, GemmCfgHalf><<<grid, GemmCfgHalf::THREADS, GemmCfgHalf::SMEM_BYTES, st>>>(op);
+  } else if (layout == 0)
     tile_once_kernel<false, false><<<op.ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op);
   else if (layout == 1)
     tile_once_kernel<false, true><<<op.ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op);

@@ -160,21 +160,24 @@ __device__ __forceinline__ bool decode_tile(const TileOp& op, int t, TileWork& w
 }
 
 // One tile per CTA (grid = ntiles, hardware block scheduler hands out tiles in launch order).
-// With Cfg::TM < 128 each 128 x 128 tile is split into 128/TM row strips handled by consecutive
-// CTAs (grid = ntiles * 128/TM).  Row strips keep the in-place panel update safe: a CTA reads
-// only the rows of A it overwrites.
+// With Cfg::TM < 128 / Cfg::TN < 128 each 128 x 128 tile is split into row strips / column halves
+// handled by consecutive CTAs.  Row strips keep the in-place panel update safe (a CTA reads only
+// the rows of A it overwrites); column halves are used for the out-of-place operations only.
 template <bool A_KMAJOR, bool B_KMAJOR, class Cfg = GemmCfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1) tile_once_kernel(const TileOp op) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINCTA) tile_once_kernel(const TileOp op) {
   extern __shared__ double smem[];
-  constexpr int SPLIT = TB / Cfg::TM;
-  static_assert(SPLIT == 1 || !A_KMAJOR, "row-strip split is implemented for MN-major A only");
+  constexpr int SPLIT_M = TB / Cfg::TM, SPLIT_N = TB / Cfg::TN;
+  static_assert(SPLIT_M == 1 || !A_KMAJOR, "row-strip split is implemented for MN-major A only");
   TileWork w;
-  if (!decode_tile<A_KMAJOR, B_KMAJOR, Cfg::BK>(op, blockIdx.x / SPLIT, w)) return;
+  if (!decode_tile<A_KMAJOR, B_KMAJOR, Cfg::BK>(op, blockIdx.x / (SPLIT_M * SPLIT_N), w)) return;
   size_t lda, ldb, ldc;
   op_strides(op, lda, ldb, ldc);
-  const int roff = (blockIdx.x % SPLIT) * Cfg::TM;
-  gemm_tile_mb<A_KMAJOR, B_KMAJOR, Cfg>(w.A + roff, lda, w.B, ldb, 0, w.nslab * Cfg::BK, (w.flags & 1) != 0,
-                                     (w.flags & 2) ? w.C + roff : nullptr, ldc, w.C + roff, ldc, smem);
+  const int sub = blockIdx.x % (SPLIT_M * SPLIT_N);
+  const int roff = (sub % SPLIT_M) * Cfg::TM, coff = (sub / SPLIT_M) * Cfg::TN;
+  const double* Bp = w.B + (B_KMAJOR ? (size_t)coff * ldb : (size_t)coff);
+  double* Cp = w.C + roff + (size_t)coff * ldc;
+  gemm_tile_mb<A_KMAJOR, B_KMAJOR, Cfg>(w.A + roff, lda, Bp, ldb, 0, w.nslab * Cfg::BK, (w.flags & 1) != 0,
+                                        (w.flags & 2) ? Cp : nullptr, ldc, Cp, ldc, smem);
 }
 
 }  // namespace gpedm
