@@ -69,8 +69,12 @@ struct gpedm_fit_s {
   int num_sms = 148;
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // gradient-only / full / through-z variants
   int64_t graph_launches[3] = {0, 0, 0};
+  int trtri_done[16] = {};  // per level: full pairs of the triangular inverse already launched this evaluation
   cudaStream_t stream = nullptr;
   cudaStream_t aux = nullptr;  // high-priority stream for the look-ahead chain (diag, panel, next column)
+  cudaStream_t fill = nullptr; // low-priority stream: early triangular-inverse levels filling the Cholesky tail
+  cudaEvent_t evFill = nullptr;
+  std::vector<cudaEvent_t> evCol;  // "block columns < c are final" checkpoints for the fill stream
   std::vector<cudaEvent_t> evPanel, evTrail;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaEvent_t ev[GPEDM_NPHASE + 1] = {};
@@ -93,6 +97,8 @@ static const bool g_no_lookahead = getenv("GPEDM_NO_LOOKAHEAD") != nullptr && at
 static const int g_group = getenv("GPEDM_POTRF_GROUP") ? std::max(1, atoi(getenv("GPEDM_POTRF_GROUP"))) : 2;
 static const int g_group_min = getenv("GPEDM_POTRF_GROUP_MIN") ? atoi(getenv("GPEDM_POTRF_GROUP_MIN")) : 24;
 static const bool g_no_half_tiles = getenv("GPEDM_NO_HALF_TILES") != nullptr && atoi(getenv("GPEDM_NO_HALF_TILES")) != 0;
+static const int g_fill_tail = getenv("GPEDM_FILL_TAIL") ? atoi(getenv("GPEDM_FILL_TAIL")) : 32;
+static const bool g_no_fill = getenv("GPEDM_NO_FILL") != nullptr && atoi(getenv("GPEDM_NO_FILL")) != 0;
 static const bool g_no_split = getenv("GPEDM_NO_SPLIT") != nullptr && atoi(getenv("GPEDM_NO_SPLIT")) != 0;
 static const int g_graph_max_nb = getenv("GPEDM_GRAPH_MAX_NB") ? atoi(getenv("GPEDM_GRAPH_MAX_NB")) : 48;
 static const int g_batch_workers = getenv("GPEDM_BATCH_WORKERS_PER_GPU") ? atoi(getenv("GPEDM_BATCH_WORKERS_PER_GPU")) : 0;
@@ -179,6 +185,9 @@ static void free_handle(gpedm_fit_s* h) {
     if (e) cudaEventDestroy(e);
   for (auto& e : h->evPanel) cudaEventDestroy(e);
   for (auto& e : h->evTrail) cudaEventDestroy(e);
+  for (auto& e : h->evCol) cudaEventDestroy(e);
+  if (h->evFill) cudaEventDestroy(h->evFill);
+  if (h->fill) cudaStreamDestroy(h->fill);
   if (h->evFork) cudaEventDestroy(h->evFork);
   if (h->evJoin) cudaEventDestroy(h->evJoin);
   if (h->aux) cudaStreamDestroy(h->aux);
@@ -257,7 +266,12 @@ extern "C" int gpedm_create(int device, int64_t N, int32_t d, int32_t np, const 
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     e = cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->fill, cudaStreamNonBlocking, lo);
   }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evFill, cudaEventDisableTiming);
+  h->evCol.resize(h->nb / 8 + 1, nullptr);
+  for (size_t i = 0; i < h->evCol.size() && e == cudaSuccess; ++i)
+    e = cudaEventCreateWithFlags(&h->evCol[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming);
   h->evPanel.resize(h->nb, nullptr);
@@ -349,6 +363,48 @@ static TileOp make_op(int type, int ntiles, int nb) {
   return op;
 }
 
+
+// Triangular inverse X = L^-1 by recursive doubling, restricted to what is computable once the
+// first `ncols` block columns of L are final.  Level s (block size in tiles) combines the inverses of
+// two adjacent s-blocks: X21 = -X22 (L21 X11); W = L21 X11 goes to bufC.  h->trtri_done[level] counts
+// the full pairs already launched, so repeated calls with growing `ncols` launch each pair once, in
+// dependency order (ascending s within a call, calls in stream order).  `final` also launches the
+// ragged last pair of each level.
+static int enqueue_trtri_levels(gpedm_fit_s* h, cudaStream_t st, int ncols, bool final) {
+  const int nb = h->nb;
+  const size_t ld = h->Np;
+  int lv = 0;
+  for (int s = 1; s < nb; s *= 2, ++lv) {
+    const int pf = nb / (2 * s);                    // full pairs of this level
+    const int ready = std::min(pf, ncols / (2 * s));
+    const int p0 = h->trtri_done[lv];
+    const int nfull = std::max(0, ready - p0);
+    const int rem = nb - 2 * s * pf;
+    const int ragged = (final && rem > s) ? (rem - s) * s : 0;
+    const int ntl = nfull * s * s + ragged;
+    if (ntl <= 0) continue;
+    TileOp w = make_op(OP_TRTRI_W, ntl, nb);
+    w.s = s;
+    w.p0 = p0;
+    w.nfull = nfull;
+    w.P0 = h->bufA;
+    w.P1 = h->bufB;
+    w.P2 = h->bufC;
+    w.ld0 = w.ld1 = w.ld2 = ld;
+    int rc = launch_tiles(h, st, w, 1);
+    if (rc) return rc;
+    TileOp x = w;
+    x.type = OP_TRTRI_X;
+    x.P0 = h->bufB;
+    x.P1 = h->bufC;
+    x.P2 = h->bufB;
+    rc = launch_tiles(h, st, x, 1);
+    if (rc) return rc;
+    h->trtri_done[lv] = p0 + nfull;
+  }
+  return 0;
+}
+
 // Phase-timing events must stay usable from outside when the launch sequence is captured into a
 // CUDA graph: record them as "external" event nodes during capture.
 static thread_local bool g_capturing = false;  // set only inside enqueue_eval while capturing
@@ -398,6 +454,13 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
       return launch_tiles(h, s_, t, 0, s_ == ax && !g_no_split && ntl * 4 <= 2 * h->num_sms);
     };
     auto group_size = [&](int start) { return (nb - start - 1 >= g_group_min) ? g_group : 1; };
+    // Early triangular inverse: level s, pair p (tile rows/cols [2ps, 2ps+2s)) only needs block
+    // columns < 2s(p+1) of L and the diagonal-block inverses, so it can run as soon as the Cholesky
+    // has passed that column - on a low-priority stream, filling the SMs the chain-bound tail of the
+    // factorisation leaves idle.  Checkpoints every 8 block columns.
+    cudaStream_t fl = (g_no_lookahead || g_no_fill) ? nullptr : h->fill;
+    if (fl) CU(cudaStreamWaitEvent(fl, h->evFork, 0));
+    for (int lv = 0; lv < 16; ++lv) h->trtri_done[lv] = 0;
     int prev_bulk = -1;  // index of the event recorded after the previous group's bulk update
     int g0 = 0, G = group_size(0);
     while (g0 < nb) {
@@ -426,6 +489,12 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
           if (rc) return rc;
         }
       }
+      if (fl && g1 % 8 == 0 && g1 < nb && nb - g1 <= g_fill_tail) {  // only once the factorisation is chain-bound
+        CU(cudaEventRecord(h->evCol[g1 / 8], ax));
+        CU(cudaStreamWaitEvent(fl, h->evCol[g1 / 8], 0));
+        int rc = enqueue_trtri_levels(h, fl, g1, false);
+        if (rc) return rc;
+      }
       if (g1 >= nb) break;
       const int Gn = group_size(g1);
       const int g2 = std::min(nb, g1 + Gn);
@@ -448,28 +517,16 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     }
     CU(cudaEventRecord(h->evJoin, ax));
     CU(cudaStreamWaitEvent(st, h->evJoin, 0));
+    if (fl) {
+      CU(cudaEventRecord(h->evFill, fl));
+      CU(cudaStreamWaitEvent(st, h->evFill, 0));
+    }
   }
   CU(record_phase_event(h->ev[2], st));
-  // --- triangular inverse X = L^-1 by recursive doubling (diagonal blocks already in bufB)
-  for (int s = 1; s < nb; s *= 2) {
-    const int pf = nb / (2 * s);
-    const int rem = nb - 2 * s * pf;
-    const int ntl = pf * s * s + (rem > s ? (rem - s) * s : 0);
-    TileOp w = make_op(OP_TRTRI_W, ntl, nb);
-    w.s = s;
-    w.P0 = h->bufA;
-    w.P1 = h->bufB;
-    w.P2 = h->bufC;
-    w.ld0 = w.ld1 = w.ld2 = ld;
-    int rc = launch_tiles(h, st, w, 1);
-    if (rc) return rc;
-    TileOp x = make_op(OP_TRTRI_X, ntl, nb);
-    x.s = s;
-    x.P0 = h->bufB;
-    x.P1 = h->bufC;
-    x.P2 = h->bufB;
-    x.ld0 = x.ld1 = x.ld2 = ld;
-    rc = launch_tiles(h, st, x, 1);
+  // --- triangular inverse X = L^-1 by recursive doubling (diagonal blocks already in bufB): whatever the
+  // fill stream has not done yet, level by level
+  {
+    int rc = enqueue_trtri_levels(h, st, nb, true);
     if (rc) return rc;
   }
   CU(record_phase_event(h->ev[3], st));

@@ -25,6 +25,8 @@ struct TileOp {
   int k;         // block column (panel) / first block column of the update (trail)
   int kcount;    // trail: number of consecutive block columns applied (rank = 128 * kcount)
   int s;         // trtri block size in tiles
+  int p0;        // trtri: first pair covered by this launch
+  int nfull;     // trtri: number of full (s x s tile) pairs covered; a ragged last pair may follow
   int jlo, jhi;  // trail column range
   int mt;        // tri_apply: number of column tiles of V
   const double* P0;  // operand matrices (meaning depends on type)
@@ -103,16 +105,15 @@ __device__ __forceinline__ bool decode_tile(const TileOp& op, int t, TileWork& w
       // pairs p cover tile rows/cols [2ps, 2ps+2s); all but possibly the last are full (s x s
       // tiles), the last may have only s2 < s rows (ragged nb).  No empty tiles are enumerated.
       const int s = op.s, per = s * s;
-      const int pf = op.nb / (2 * s);
       int p, rem, s2;
-      if (t < pf * per) {
-        p = t / per;
+      if (t < op.nfull * per) {
+        p = op.p0 + t / per;
         rem = t % per;
         s2 = s;
-      } else {
-        p = pf;
-        rem = t - pf * per;
-        s2 = op.nb - 2 * s * pf - s;
+      } else {  // ragged last pair of the level: only s2 < s block rows exist below the split
+        p = op.nb / (2 * s);
+        rem = t - op.nfull * per;
+        s2 = op.nb - 2 * s * p - s;
       }
       const int o = p * 2 * s;
       if (op.type == OP_TRTRI_W) {
