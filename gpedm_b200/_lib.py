@@ -66,7 +66,7 @@ class FitDesc(C.Structure):
 EXPORTS = [
     "gpedm_abi_version", "gpedm_last_error", "gpedm_device_count", "gpedm_default_rprop_options",
     "gpedm_create", "gpedm_set_data", "gpedm_destroy", "gpedm_n", "gpedm_likegrad", "gpedm_fit_rprop", "gpedm_get_vector",
-    "gpedm_get_matrix", "gpedm_getcov", "gpedm_predict_new", "gpedm_predict_loo", "gpedm_predict_lto",
+    "gpedm_get_matrix", "gpedm_getcov", "gpedm_covinv", "gpedm_predict_new", "gpedm_predict_loo", "gpedm_predict_lto",
     "gpedm_predict_sequential", "gpedm_fit_batch", "gpedm_last_phase_ms", "gpedm_launch_count",
     "gpedm_fp64_peak", "gpedm_bench_evals",
 ]
@@ -119,6 +119,7 @@ def lib():
     L.gpedm_get_matrix.argtypes = [C.c_void_p, C.c_int, dp]
     L.gpedm_getcov.argtypes = [C.c_int, C.c_int32, dp, C.c_double, C.c_double, C.c_int64, dp, ip, C.c_int64, dp, ip,
                                C.c_int32, dp, dp]
+    L.gpedm_covinv.argtypes = [C.c_int, C.c_int64, dp, dp, dp]
     L.gpedm_predict_new.argtypes = [C.c_void_p, C.c_int64, dp, ip, dp, dp, dp]
     L.gpedm_predict_loo.argtypes = [C.c_void_p, C.c_int32, dp, ip, dp, dp, dp]
     L.gpedm_predict_lto.argtypes = [C.c_void_p, C.c_int32, dp, ip, dp, dp, dp]

@@ -233,6 +233,19 @@ def getcov(phi, sigma2, rho, X, X2, pop, pop2, rhomat=None, rhomat_names=None, d
     return dict(popsame=popsame, Cd=Cd)
 
 
+def getcovinv(Sigma, device=0):
+    """R/GPfunctions.R:818-830: Cholesky factor and inverse of a covariance matrix.  Returns
+    dict(L=<upper factor, like Matrix::chol>, iKVs=<inverse>)."""
+    S = f64(Sigma)
+    if S.ndim != 2 or S.shape[0] != S.shape[1]:
+        raise ValueError("Sigma must be a square matrix")
+    n = S.shape[0]
+    L = np.empty((n, n), order="F")
+    inv = np.empty((n, n), order="F")
+    check(lib().gpedm_covinv(device, n, dptr(S), dptr(L), dptr(inv)))
+    return dict(L=np.ascontiguousarray(L.T), iKVs=inv)
+
+
 def getlikegrad(parst, Y, X, pop, modeprior, fixedpars, rhofixed, rhomatrix, D=None, returngradonly=True,
                 rhomatrix_names=None, device=0):
     """R/GPfunctions.R:586-750 as a one-shot call (the per-coordinate distance list `D` of the
@@ -275,5 +288,5 @@ def fp64_peak(which=0, device=0):
     return float(v.value)
 
 
-__all__ = ["GPModel", "GPEDMError", "getcov", "getlikegrad", "fmingrad_Rprop", "logit", "pop_codes",
+__all__ = ["GPModel", "GPEDMError", "getcov", "getcovinv", "getlikegrad", "fmingrad_Rprop", "logit", "pop_codes",
            "unique_stable", "fp64_peak"]

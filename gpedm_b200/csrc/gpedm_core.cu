@@ -69,6 +69,7 @@ struct gpedm_fit_s {
   int num_sms = 148;
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // gradient-only / full / through-z variants
   int64_t graph_launches[3] = {0, 0, 0};
+  const double* dsigma_in = nullptr;  // gpedm_covinv: factor this N x N matrix instead of assembling Sigma
   int trtri_done[16] = {};  // per level: full pairs of the triangular inverse already launched this evaluation
   cudaStream_t stream = nullptr;
   cudaStream_t aux = nullptr;  // high-priority stream for the look-ahead chain (diag, panel, next column)
@@ -422,8 +423,11 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   CU(cudaMemcpyAsync(h->dparams, h->hparams, sizeof(EvalParams), cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(h->dinfo, 0, 4, st));
   CU(record_phase_event(h->ev[0], st));
-  // --- assemble Sigma (lower tiles) into bufA
-  {
+  // --- assemble Sigma (lower tiles) into bufA (or take the caller's matrix: gpedm_covinv)
+  if (h->dsigma_in) {
+    load_sigma_kernel<<<h->ntiles, 256, 0, st>>>(h->bufA, ld, N, h->dsigma_in);
+    h->launches++;
+  } else {
     int smem = 2 * d * TB * 8 + 2 * TB * 4;
     assemble_sigma_kernel<<<h->ntiles, 256, smem, st>>>(h->bufA, ld, N, h->dX, h->dpop, h->drhotab, h->dparams);
     h->launches++;
@@ -969,6 +973,47 @@ extern "C" int gpedm_getcov(int device, int32_t d, const double* phi, double sig
   cudaFree(drt);
   if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "gpedm_getcov failed: %s", cudaGetErrorString(e));
   return 0;
+}
+
+
+// getcovinv (reference R/GPfunctions.R:818-830): Cholesky factor and full inverse of a caller-supplied
+// symmetric positive definite matrix, through the same factorisation pipeline as the likelihood.
+extern "C" int gpedm_covinv(int device, int64_t n, const double* Sigma, double* L_out, double* iKVs_out) {
+  if (!Sigma || (!L_out && !iKVs_out) || n < 1) return set_err(GPEDM_ERR_ARG, "bad arguments");
+  std::vector<double> X((size_t)n, 0.0), Y((size_t)n, 0.0);
+  std::vector<int32_t> pop((size_t)n, 0);
+  gpedm_handle h = nullptr;
+  int rc = gpedm_create(device, n, 1, 1, X.data(), Y.data(), pop.data(), nullptr, &h);
+  if (rc) return rc;
+  double* dS = nullptr;
+  cudaError_t e = cudaMalloc((void**)&dS, (size_t)n * n * 8);
+  if (e == cudaSuccess) e = cudaMemcpy(dS, Sigma, (size_t)n * n * 8, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(dS);
+    gpedm_destroy(h);
+    return set_err(GPEDM_ERR_CUDA, "gpedm_covinv: %s", cudaGetErrorString(e));
+  }
+  h->dsigma_in = dS;
+  memset(h->hparams, 0, sizeof(EvalParams));
+  h->hparams->d = 1;
+  h->hparams->np = 1;
+  h->hparams->sigma2 = 1.0;
+  h->hparams->rho = 0.5;
+  rc = enqueue_eval(h, true);
+  if (!rc) {
+    e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = set_err(GPEDM_ERR_CUDA, "gpedm_covinv: %s", cudaGetErrorString(e));
+  }
+  if (!rc && *h->hinfo > 0)
+    rc = set_err(*h->hinfo, "matrix not positive definite: non-positive pivot at row %d", *h->hinfo);
+  if (!rc) {
+    h->have_full = true;
+    if (L_out) rc = gpedm_get_matrix(h, GPEDM_MAT_L, L_out);
+    if (!rc && iKVs_out) rc = gpedm_get_matrix(h, GPEDM_MAT_IKVS, iKVs_out);
+  }
+  cudaFree(dS);
+  gpedm_destroy(h);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------- prediction

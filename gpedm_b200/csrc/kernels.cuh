@@ -149,6 +149,26 @@ __global__ void __launch_bounds__(256) cov_rect_kernel(double* __restrict__ out,
   }
 }
 
+// getcovinv on a caller-supplied matrix (reference R/GPfunctions.R:818-830): load the symmetrised lower
+// tiles of Sigma (N x N column-major, "(Sigma + t(Sigma))/2" as the reference does before calling it,
+// :641, :1076) into the padded work matrix, identity in the padding.
+__global__ void __launch_bounds__(256) load_sigma_kernel(double* __restrict__ A, size_t ld, int N,
+                                                          const double* __restrict__ S) {
+  int ti, tj;
+  tri_decode(blockIdx.x, ti, tj);
+  const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int gi = ti * TB + r;
+  for (int c = half * 64; c < half * 64 + 64; ++c) {
+    const int gj = tj * TB + c;
+    double v;
+    if (gi < N && gj < N)
+      v = 0.5 * (S[(size_t)gi + (size_t)gj * N] + S[(size_t)gj + (size_t)gi * N]);
+    else
+      v = (gi == gj) ? 1.0 : 0.0;
+    A[(size_t)gi + (size_t)gj * ld] = v;
+  }
+}
+
 // popsame (reference :796) for export.
 __global__ void popsame_kernel(double* out, int N, const int* pop) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -134,6 +134,12 @@ int gpedm_getcov(int device, int32_t d, const double* phi, double sigma2, double
                  const int32_t* pop, int64_t M, const double* X2, const int32_t* pop2, int32_t np,
                  const double* rhomat, double* Cd_out);
 
+/* ---- getcovinv (reference R/GPfunctions.R:818-830), stateless --------------------------- */
+/* Sigma: n x n column-major (symmetrised internally as the reference does at :641 / :1076).
+ * L_out: lower Cholesky factor (= transpose of R's upper `L`), iKVs_out: full inverse; either may
+ * be NULL.  Returns >0 (failing pivot) when Sigma is not positive definite. */
+int gpedm_covinv(int device, int64_t n, const double* Sigma, double* L_out, double* iKVs_out);
+
 /* ---- predict.GP numerical cores -------------------------------------------------------- */
 /* newdata (reference R/GPfunctions.R:1012-1036 + getGPgrad :1863-1865).  Xnew: M x d
  * column-major (already scaled), popnew codes.  mean, var: length M (var is the latent

@@ -416,3 +416,21 @@ def test_predict_iter_and_getconditionals(gpu_lib, thetalog2pop):
     co2 = O.getconditionals(o, xrange="global", nvals=7)
     np.testing.assert_allclose(cg2[1]["predmean"], co2[1]["predmean"], atol=1e-8)
     g.close()
+
+
+def test_getcovinv(gpu_lib):
+    """getcovinv (R/GPfunctions.R:818-830) on caller-supplied matrices, incl. a slightly asymmetric one
+    (the reference symmetrises before factoring) and a non-PD one."""
+    rng = np.random.default_rng(6)
+    for n in (5, 130, 300):
+        B = rng.standard_normal((n, n))
+        S = B @ B.T / n + 0.5 * np.eye(n)
+        S[0, n - 1] += 1e-13
+        out = G.getcovinv(S)
+        Ssym = (S + S.T) / 2
+        Lr, ir = O.getcovinv(Ssym)
+        np.testing.assert_allclose(out["L"], Lr, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(out["iKVs"], ir, rtol=1e-9, atol=1e-10)
+    with pytest.raises(G.GPEDMError) as e:
+        G.getcovinv(np.array([[1.0, 2.0], [2.0, 1.0]]))
+    assert e.value.status == 2
