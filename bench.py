@@ -11,8 +11,9 @@ reference R/GPfunctions.R:586-725) at fitGP's default start.
 N > 1 is launched by the driver with torchrun (one process per GPU); every rank evaluates its own
 independent grid member (weak scaling: the path shards across fits with no data-path collective),
 rank 0 prints one JSON line with the whole-job evaluation rate (max-over-ranks device time).
-`--grid` additionally times the full batched fitGP grid (E=1..10 x tau=1..4, 40 fits, LOO
-predictions) sharded over the ranks, with one all-gather of the result records.
+Unless `--no-grid` is given it also times the full batched fitGP grid (E=1..10 x tau=1..4, 40 fits,
+closed-form LOO predictions) sharded over the ranks, with one all-gather of the result records
+(the second half of the BASELINE.json metric; strong scaling), reported under "grid".
 `--impl reference` times the CPU restatement of the reference (oracle/, LAPACK dpotrf + dpotri
 with all host threads) on the same workload.
 """
@@ -147,6 +148,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the lauum launch from the committed ncu --set full
+    capture (profiles/r01_lauum_tile_kernel_ncu.txt); None when the summary is absent."""
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "r01_lauum_tile_kernel_ncu.txt")):
+            if line.startswith("dram__bytes_read.sum =") or line.startswith("dram__bytes_write.sum ="):
+                val, unit = line.split("=")[1].split()[:2]
+                tot += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return tot or None
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 # ------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -231,7 +246,7 @@ def run_ours(args):
         lauum_tf = n3 / 3 / (phases["lauum"] * 1e-3) * 1e-12
         roof = {"bound": "tensor", "kernel": "tile_once_kernel<K,K> (lauum: Sigma^-1 = L^-T L^-1, one launch, N^3/3 flop)",
                 "achieved": lauum_tf, "peak": peak_dmma, "unit": "TFLOP/s", "frac": lauum_tf / peak_dmma,
-                "traffic": None,
+                "traffic": ncu_traffic_bytes(),
                 "peak_source": "live FP64 DMMA m8n8k4 issue-rate probe (gpedm_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "eval": {"flops_per_eval": n3, "achieved": n3 / (step_ms * 1e-3) * 1e-12, "frac": n3 / (step_ms * 1e-3) * 1e-12 / peak_dmma},
                 "phases_ms": phases,
@@ -243,7 +258,7 @@ def run_ours(args):
                                 "hbm_peak_GBs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
                 "dfma_peak": peak_dfma}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             use_all_host_threads()
             t, out, _ = time_reference_eval(Y, X, p0)
             cpu = {"value": 1.0 / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
@@ -302,7 +317,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grid", action="store_true", help="also time the 40-fit E x tau grid")
+    ap.add_argument("--grid", dest="grid", action="store_true", default=True,
+                    help="also time the 40-fit E x tau grid sharded over the ranks (default)")
+    ap.add_argument("--no-grid", dest="grid", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

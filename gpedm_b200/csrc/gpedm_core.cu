@@ -70,7 +70,7 @@ struct gpedm_fit_s {
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // gradient-only / full / through-z variants
   int64_t graph_launches[3] = {0, 0, 0};
   const double* dsigma_in = nullptr;  // gpedm_covinv: factor this N x N matrix instead of assembling Sigma
-  int trtri_done[16] = {};  // per level: full pairs of the triangular inverse already launched this evaluation
+  int trtri_w_done[16] = {}, trtri_x_done[16] = {};  // per level: full pairs already launched this evaluation
   cudaStream_t stream = nullptr;
   cudaStream_t aux = nullptr;  // high-priority stream for the look-ahead chain (diag, panel, next column)
   cudaStream_t fill = nullptr; // low-priority stream: early triangular-inverse levels filling the Cholesky tail
@@ -366,42 +366,62 @@ static TileOp make_op(int type, int ntiles, int nb) {
 
 
 // Triangular inverse X = L^-1 by recursive doubling, restricted to what is computable once the
-// first `ncols` block columns of L are final.  Level s (block size in tiles) combines the inverses of
-// two adjacent s-blocks: X21 = -X22 (L21 X11); W = L21 X11 goes to bufC.  h->trtri_done[level] counts
-// the full pairs already launched, so repeated calls with growing `ncols` launch each pair once, in
-// dependency order (ascending s within a call, calls in stream order).  `final` also launches the
-// ragged last pair of each level.
+// first `ncols` block columns of L are final.  Level s (block size in tiles), pair p (tile rows/cols
+// [2ps, 2ps+2s)): X21 = -X22 (L21 X11) in two launches,
+//   W = L21 X11   needs X11 (level s/2, pair 2p) and block columns < 2ps+s of L,
+//   X21 = -X22 W  needs X22 (level s/2, pair 2p+1), i.e. block columns < 2ps+2s.
+// h->trtri_w_done / trtri_x_done count the full pairs already launched per level, so repeated calls
+// with growing `ncols` launch every product exactly once and in dependency order (ascending s within a
+// call, calls in stream order).  In particular the W product of the TOP level - a quarter of all
+// the flops of the inverse - becomes available when the Cholesky is only half way.
+// `final` also launches the ragged last pair of each level.
 static int enqueue_trtri_levels(gpedm_fit_s* h, cudaStream_t st, int ncols, bool final) {
   const int nb = h->nb;
   const size_t ld = h->Np;
   int lv = 0;
   for (int s = 1; s < nb; s *= 2, ++lv) {
-    const int pf = nb / (2 * s);                    // full pairs of this level
-    const int ready = std::min(pf, ncols / (2 * s));
-    const int p0 = h->trtri_done[lv];
-    const int nfull = std::max(0, ready - p0);
+    const int pf = nb / (2 * s);  // full pairs of this level
     const int rem = nb - 2 * s * pf;
-    const int ragged = (final && rem > s) ? (rem - s) * s : 0;
-    const int ntl = nfull * s * s + ragged;
-    if (ntl <= 0) continue;
-    TileOp w = make_op(OP_TRTRI_W, ntl, nb);
-    w.s = s;
-    w.p0 = p0;
-    w.nfull = nfull;
-    w.P0 = h->bufA;
-    w.P1 = h->bufB;
-    w.P2 = h->bufC;
-    w.ld0 = w.ld1 = w.ld2 = ld;
-    int rc = launch_tiles(h, st, w, 1);
-    if (rc) return rc;
-    TileOp x = w;
-    x.type = OP_TRTRI_X;
-    x.P0 = h->bufB;
-    x.P1 = h->bufC;
-    x.P2 = h->bufB;
-    rc = launch_tiles(h, st, x, 1);
-    if (rc) return rc;
-    h->trtri_done[lv] = p0 + nfull;
+    const bool ragged = final && rem > s;
+    // ---- W phase
+    int wready = h->trtri_w_done[lv];
+    while (wready < pf && 2 * wready * s + s <= ncols && (lv == 0 || h->trtri_x_done[lv - 1] >= 2 * wready + 1)) ++wready;
+    {
+      const int p0 = h->trtri_w_done[lv], nfull = wready - p0;
+      const int ntl = nfull * s * s + (ragged ? (rem - s) * s : 0);
+      if (ntl > 0) {
+        TileOp w = make_op(OP_TRTRI_W, ntl, nb);
+        w.s = s;
+        w.p0 = p0;
+        w.nfull = nfull;
+        w.P0 = h->bufA;
+        w.P1 = h->bufB;
+        w.P2 = h->bufC;
+        w.ld0 = w.ld1 = w.ld2 = ld;
+        int rc = launch_tiles(h, st, w, 1);
+        if (rc) return rc;
+        h->trtri_w_done[lv] = wready;
+      }
+    }
+    // ---- X phase
+    {
+      const int xready = std::min(h->trtri_w_done[lv], std::min(pf, ncols / (2 * s)));
+      const int p0 = h->trtri_x_done[lv], nfull = std::max(0, xready - p0);
+      const int ntl = nfull * s * s + (ragged ? (rem - s) * s : 0);
+      if (ntl > 0) {
+        TileOp x = make_op(OP_TRTRI_X, ntl, nb);
+        x.s = s;
+        x.p0 = p0;
+        x.nfull = nfull;
+        x.P0 = h->bufB;
+        x.P1 = h->bufC;
+        x.P2 = h->bufB;
+        x.ld0 = x.ld1 = x.ld2 = ld;
+        int rc = launch_tiles(h, st, x, 1);
+        if (rc) return rc;
+        h->trtri_x_done[lv] = p0 + nfull;
+      }
+    }
   }
   return 0;
 }
@@ -464,7 +484,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     // factorisation leaves idle.  Checkpoints every 8 block columns.
     cudaStream_t fl = (g_no_lookahead || g_no_fill) ? nullptr : h->fill;
     if (fl) CU(cudaStreamWaitEvent(fl, h->evFork, 0));
-    for (int lv = 0; lv < 16; ++lv) h->trtri_done[lv] = 0;
+    for (int lv = 0; lv < 16; ++lv) h->trtri_w_done[lv] = h->trtri_x_done[lv] = 0;
     int prev_bulk = -1;  // index of the event recorded after the previous group's bulk update
     int g0 = 0, G = group_size(0);
     while (g0 < nb) {
