@@ -288,11 +288,27 @@ def run_grid(G, gd, world, rank, local, barrier):
     from gpedm_b200.fitgp import getR2
     y = synth.ricker(SERIES_LEN, SEED)
     probs, meta = batch.grid_problems(y, list(range(1, 11)), [1, 2, 3, 4])
-    costs = [float(len(p["Y"])) ** 3 for p in probs]
-    mine = gd.shard_indices(len(probs), world, rank, costs)
+    costs = [float(len(p["Y"])) ** 3 * (1 + 0.01 * p["X"].shape[1]) for p in probs]
+    order = sorted(range(len(probs)), key=lambda i: -costs[i])
+    # dynamic work queue across the ranks: an atomic counter in the process-group store hands out
+    # the next fit (iteration counts differ 4x between grid cells, so a static split is unbalanced);
+    # this is control-plane only - no data-path collective
+    store = None
+    if world > 1:
+        import torch.distributed as dist
+        store = dist.distributed_c10d._get_default_store()
     barrier()
     t0 = time.perf_counter()
-    res = G.fit_batch([probs[i] for i in mine], ngpus=1, devices=[local], want_loo=True)
+    mine, res, q = [], [], 0
+    while True:
+        q = (store.add("gpedm_grid_next", 1) - 1) if store is not None else q
+        if q >= len(probs):
+            break
+        i = order[q]
+        res.extend(G.fit_batch([probs[i]], ngpus=1, devices=[local], want_loo=True))
+        mine.append(i)
+        if store is None:
+            q += 1
     torch.cuda.synchronize()
     local_s = time.perf_counter() - t0
     allres = gd.gather_records(list(zip(mine, res)), len(probs), device=torch.device("cuda", local))
@@ -305,7 +321,8 @@ def run_grid(G, gd, world, rank, local, barrier):
     if rank != 0:
         return None
     best = max(r2, key=r2.get) if r2 else None
-    return {"fits": len(probs), "wall_s": wall, "rank0_local_s": local_s,
+    return {"fits": len(probs), "wall_s": wall, "rank0_local_s": local_s, "rank0_fits": len(mine),
+            "scheduling": "dynamic queue (store counter), one all-gather of result records",
             "total_evals": int(sum(r["nevals"] for r in allres)),
             "iters": [int(r["iter"]) for r in allres], "status_ok": all(r["status"] == 0 for r in allres),
             "rank0_best": None if best is None else {"E": meta[best]["E"], "tau": meta[best]["tau"], "R2_loo": r2[best]}}
