@@ -434,3 +434,30 @@ def test_getcovinv(gpu_lib):
     with pytest.raises(G.GPEDMError) as e:
         G.getcovinv(np.array([[1.0, 2.0], [2.0, 1.0]]))
     assert e.value.status == 2
+
+
+def test_predict_new_chunking_and_set_data(gpu_lib):
+    """More new points than one prediction chunk (4096), and re-uploading the training set in place."""
+    Y, X, pop, parst = make_case(21, 260, 3, 2)
+    m = G.GPModel(Y, X, pop)
+    full = m.likegrad(parst, 1, None, None, False)
+    rng = np.random.default_rng(3)
+    Xn = rng.standard_normal((4500, 3))
+    pn = rng.integers(0, 2, 4500)
+    mean, var, grad = m.predict_new(Xn, pn, returnGPgrad=True)
+    ref = oracle_eval(parst, Y, X, pop)
+    p = ref["pars"]
+    mo, vo, go = O.predict_newdata_core(p[:3], p[4], p[5], p[3], X, Y, pop, ref["covm"]["iKVs"], Xn, pn, returnGPgrad=True)
+    np.testing.assert_allclose(mean, mo, atol=TOL_MEAN)
+    np.testing.assert_allclose(grad, go, atol=1e-8)
+    np.testing.assert_allclose(np.sqrt(var), np.sqrt(vo), rtol=1e-6)
+    # same handle, new data of the same shape
+    Y2, X2, pop2, _ = make_case(22, 260, 3, 2)
+    codes2 = np.array([m.levels.index(q) for q in pop2], dtype=np.int32)
+    m.set_data(Y2, X2, codes2)
+    with pytest.raises(G.GPEDMError):
+        m.vector(_lib.VEC_ALPHA)  # the resident factorisation belonged to the old data
+    out = m.likegrad(parst, 1, None, None, True)
+    ref2 = oracle_eval(parst, Y2, X2, pop2)
+    assert rel(out["nllpost"], ref2["nllpost"]) <= TOL_NLL and grad_err(out["grad"], ref2["grad"]) <= TOL_GRAD
+    m.close()
