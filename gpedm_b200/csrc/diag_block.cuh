@@ -182,28 +182,14 @@ __device__ __noinline__ void chol32_warp(double* s, double* rdiag, double* dvec,
   for (int c = 0; c < 32; ++c) s[(base + lane) + (base + c) * DG_LD] = (c <= lane) ? a[c] : 0.0;
 }
 
-__global__ void __launch_bounds__(DG_THREADS, 1)
-    diag_block_kernel(double* __restrict__ Akk, size_t lda, double* __restrict__ Dkk, size_t ldd, int kblock,
-                      int n_valid, double* __restrict__ logdet_part, int* __restrict__ info) {
-  extern __shared__ double sm[];
-  double* s = sm;                   // [128][132]
-  double* w = sm + TB * DG_LD;      // [64][68] scratch
-  double* rdiag = w + 64 * DG_WLD;  // 1 / L_jj
-  double* dvec = rdiag + TB;        // L_jj, later reduction scratch
-  double* colbuf = dvec + TB;       // [2][32] pivot-column broadcast buffer
+// Cholesky of the 128x128 tile held in shared memory `s` (stride DG_LD), in place (lower part = L;
+// the part above the diagonal is left undefined except inside the 32x32 diagonal blocks, which are
+// zeroed).  rdiag <- 1/L_jj, dvec <- L_jj.  All DG_THREADS threads of the CTA must call it.
+__device__ __forceinline__ void diag_cholesky_smem(double* s, double* rdiag, double* dvec, double* colbuf, int kblock,
+                                                   int n_valid, int* info) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   constexpr int NW = DG_THREADS / 32;
-
-  DG_TS(0);
-#pragma unroll 8
-  for (int idx = tid; idx < TB * TB; idx += DG_THREADS) {
-    int r = idx & 127, c = idx >> 7;
-    s[r + c * DG_LD] = Akk[(size_t)r + (size_t)c * lda];
-  }
-  __syncthreads();
-  DG_TS(1);
-
   // ---------------- Cholesky, 4 block columns of width 32 ----------------
   if (warp == 0) chol32_warp(s, rdiag, dvec, colbuf, 0, lane, kblock, n_valid, info);
   __syncthreads();
@@ -269,25 +255,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
     DG_TS(5 + 3 * kb);
   }
 
-  // ---------------- write L, log-determinant part ----------------
-  for (int idx = tid; idx < TB * TB; idx += DG_THREADS) {
-    int r = idx & 127, c = idx >> 7;
-    Akk[(size_t)r + (size_t)c * lda] = (r >= c) ? s[r + c * DG_LD] : 0.0;
-  }
-  {
-    double v = 0.0;
-    if (tid < TB && kblock * TB + tid < n_valid) v = log(dvec[tid]);
-    __syncthreads();
-    if (tid < TB) dvec[tid] = v;
-    __syncthreads();
-    for (int off = 64; off > 0; off >>= 1) {
-      if (tid < off) dvec[tid] += dvec[tid + off];
-      __syncthreads();
-    }
-    if (tid == 0) logdet_part[kblock] = dvec[0];
-  }
-  DG_TS(14);
+}
 
+// In-place inverse of the lower-triangular factor held in `s` (needs rdiag from diag_cholesky_smem):
+// on return the lower part of `s` is L^-1.  `w` is a 64 x DG_WLD scratch.
+__device__ __forceinline__ void diag_invert_smem(double* s, double* w, const double* rdiag) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
   // ---------------- inverse: 8x8 diagonal blocks, one thread per column ----------------
   {
     double x[8];
@@ -315,6 +289,48 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
   doubling_level<1>(s, w, 16, warp, g, t);   // 16 tiles
   doubling_level<2>(s, w, 32, warp, g, t);   // 32 tiles, 2 per warp
   doubling_level<4>(s, w, 64, warp, g, t);   // 64 tiles, 4 per warp
+}
+
+__global__ void __launch_bounds__(DG_THREADS, 1)
+    diag_block_kernel(double* __restrict__ Akk, size_t lda, double* __restrict__ Dkk, size_t ldd, int kblock,
+                      int n_valid, double* __restrict__ logdet_part, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  double* s = sm;                   // [128][132]
+  double* w = sm + TB * DG_LD;      // [64][68] scratch
+  double* rdiag = w + 64 * DG_WLD;  // 1 / L_jj
+  double* dvec = rdiag + TB;        // L_jj, later reduction scratch
+  double* colbuf = dvec + TB;       // [2][32] pivot-column broadcast buffer
+  const int tid = threadIdx.x;
+
+  DG_TS(0);
+#pragma unroll 8
+  for (int idx = tid; idx < TB * TB; idx += DG_THREADS) {
+    int r = idx & 127, c = idx >> 7;
+    s[r + c * DG_LD] = Akk[(size_t)r + (size_t)c * lda];
+  }
+  __syncthreads();
+  DG_TS(1);
+  diag_cholesky_smem(s, rdiag, dvec, colbuf, kblock, n_valid, info);
+  // ---------------- write L, log-determinant part ----------------
+  for (int idx = tid; idx < TB * TB; idx += DG_THREADS) {
+    int r = idx & 127, c = idx >> 7;
+    Akk[(size_t)r + (size_t)c * lda] = (r >= c) ? s[r + c * DG_LD] : 0.0;
+  }
+  {
+    double v = 0.0;
+    if (tid < TB && kblock * TB + tid < n_valid) v = log(dvec[tid]);
+    __syncthreads();
+    if (tid < TB) dvec[tid] = v;
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {
+      if (tid < off) dvec[tid] += dvec[tid + off];
+      __syncthreads();
+    }
+    if (tid == 0) logdet_part[kblock] = dvec[0];
+  }
+  DG_TS(14);
+
+  diag_invert_smem(s, w, rdiag);
   DG_TS(17);
   for (int idx = tid; idx < TB * TB; idx += DG_THREADS) {
     int r = idx & 127, c = idx >> 7;

@@ -21,6 +21,7 @@
 #include "../../include/gpedm.h"
 #include "kernels.cuh"
 #include "diag_block.cuh"
+#include "small_fit.cuh"
 
 using namespace gpedm;
 
@@ -99,6 +100,7 @@ static const int g_group = getenv("GPEDM_POTRF_GROUP") ? std::max(1, atoi(getenv
 static const int g_group_min = getenv("GPEDM_POTRF_GROUP_MIN") ? atoi(getenv("GPEDM_POTRF_GROUP_MIN")) : 24;
 static const bool g_no_half_tiles = getenv("GPEDM_NO_HALF_TILES") != nullptr && atoi(getenv("GPEDM_NO_HALF_TILES")) != 0;
 static const int g_fill_tail = getenv("GPEDM_FILL_TAIL") ? atoi(getenv("GPEDM_FILL_TAIL")) : 32;
+static const bool g_no_small_batch = getenv("GPEDM_NO_SMALL_BATCH") != nullptr && atoi(getenv("GPEDM_NO_SMALL_BATCH")) != 0;
 static const bool g_no_fill = getenv("GPEDM_NO_FILL") != nullptr && atoi(getenv("GPEDM_NO_FILL")) != 0;
 static const bool g_no_split = getenv("GPEDM_NO_SPLIT") != nullptr && atoi(getenv("GPEDM_NO_SPLIT")) != 0;
 static const int g_graph_max_nb = getenv("GPEDM_GRAPH_MAX_NB") ? atoi(getenv("GPEDM_GRAPH_MAX_NB")) : 48;
@@ -133,6 +135,9 @@ static int ensure_kernel_attrs(int device) {
   }
   CU(cudaFuncSetAttribute(diag_potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
   CU(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(small_eval_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<8>()));
+  CU(cudaFuncSetAttribute(small_eval_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<16>()));
+  CU(cudaFuncSetAttribute(small_eval_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<32>()));
   int trace_smem = (4 * MAXD * TB + 2 * TB + 8 * (MAXD + 3)) * 8 + 2 * TB * 4;
   CU(cudaFuncSetAttribute(grad_trace_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
   CU(cudaFuncSetAttribute(grad_trace_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
@@ -1451,6 +1456,260 @@ static bool load_nccl(NcclApi& n) {
   return n.CommInitAll && n.CommDestroy && n.AllGather && n.GroupStart && n.GroupEnd;
 }
 
+
+// ------------------------------------------------------------------------------- batched small fits
+// All fits of a batch with N <= 128 advance in lockstep: one small_eval_kernel launch per Rprop
+// iteration evaluates every still-active fit (one CTA each); the scalar Rprop logic of
+// fmingrad_Rprop (reference R/GPfunctions.R:522-584) runs on the host per fit exactly as in
+// gpedm_fit_rprop.  A last launch with full = 1 at each fit's final parameters yields a and
+// diag(Sigma^-1), from which the in-sample and leave-one-out vectors follow in O(N).
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+};
+struct PinnedBuf {
+  void* p = nullptr;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMallocHost(&p, std::max<size_t>(bytes, 16)); }
+};
+
+static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_fit_desc* descs,
+                           const gpedm_rprop_options* opts_in, gpedm_result* results) {
+  const int nf = (int)idx.size();
+  if (nf == 0) return 0;
+  CU(cudaSetDevice(device));
+  int rc = ensure_kernel_attrs(device);
+  if (rc) return rc;
+  gpedm_rprop_options o;
+  if (opts_in)
+    o = *opts_in;
+  else
+    gpedm_default_rprop_options(&o);
+  const double eta_minus = o.eta_minus - 1, eta_plus = o.eta_plus - 1;
+  // ---- pack inputs
+  std::vector<size_t> offX(nf), offN(nf), offR(nf);
+  size_t totX = 0, totN = 0, totR = 0;
+  int dmax = 1;
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    if (ds.N < 1 || ds.N > TB || ds.d < 1 || ds.d > GPEDM_MAX_D || ds.np < 1 || !ds.X || !ds.Y || !ds.pop || !ds.initparst)
+      return set_err(GPEDM_ERR_ARG, "bad descriptor for fit %d", idx[q]);
+    for (int64_t i = 0; i < ds.N; ++i)
+      if (ds.pop[i] < 0 || ds.pop[i] >= ds.np) return set_err(GPEDM_ERR_ARG, "fit %d: pop code outside 0..np-1", idx[q]);
+    offX[q] = totX;
+    offN[q] = totN;
+    offR[q] = totR;
+    totX += (size_t)ds.N * ds.d;
+    totN += (size_t)ds.N;
+    totR += ds.rhomat ? (size_t)ds.np * ds.np : 0;
+    dmax = std::max(dmax, (int)ds.d);
+  }
+  std::vector<double> hX(totX), hY(totN), hR(std::max<size_t>(totR, 1));
+  std::vector<int> hP(totN);
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    memcpy(&hX[offX[q]], ds.X, (size_t)ds.N * ds.d * 8);
+    memcpy(&hY[offN[q]], ds.Y, (size_t)ds.N * 8);
+    memcpy(&hP[offN[q]], ds.pop, (size_t)ds.N * 4);
+    if (ds.rhomat) memcpy(&hR[offR[q]], ds.rhomat, (size_t)ds.np * ds.np * 8);
+  }
+  DevBuf dX, dY, dP, dR, dFits, dParams, dScal, dA, dDiag, dInfo, dActive;
+  PinnedBuf pParams, pScal, pInfo;
+  cudaError_t e = dX.alloc(totX * 8);
+  if (e == cudaSuccess) e = dY.alloc(totN * 8);
+  if (e == cudaSuccess) e = dP.alloc(totN * 4);
+  if (e == cudaSuccess) e = dR.alloc(totR * 8);
+  if (e == cudaSuccess) e = dFits.alloc(sizeof(SmallFit) * nf);
+  if (e == cudaSuccess) e = dParams.alloc(sizeof(EvalParams) * nf);
+  if (e == cudaSuccess) e = dScal.alloc((size_t)NSCAL * 8 * nf);
+  if (e == cudaSuccess) e = dA.alloc(totN * 8);
+  if (e == cudaSuccess) e = dDiag.alloc(totN * 8);
+  if (e == cudaSuccess) e = dInfo.alloc((size_t)nf * 4);
+  if (e == cudaSuccess) e = dActive.alloc((size_t)nf * 4);
+  if (e == cudaSuccess) e = pParams.alloc(sizeof(EvalParams) * nf);
+  if (e == cudaSuccess) e = pScal.alloc((size_t)NSCAL * 8 * nf);
+  if (e == cudaSuccess) e = pInfo.alloc((size_t)nf * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(dX.p, hX.data(), totX * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dY.p, hY.data(), totN * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dP.p, hP.data(), totN * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && totR) e = cudaMemcpy(dR.p, hR.data(), totR * 8, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "small-fit batch setup failed: %s", cudaGetErrorString(e));
+  EvalParams* hparams = (EvalParams*)pParams.p;
+  double* hscal = (double*)pScal.p;
+  int* hinfo = (int*)pInfo.p;
+  std::vector<SmallFit> hfits(nf);
+  // light host-side stand-ins for a handle: only the fields the scalar head / tail of an evaluation reads
+  std::vector<gpedm_fit_s> meta(nf);
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    SmallFit& F = hfits[q];
+    F.X = (const double*)dX.p + offX[q];
+    F.Y = (const double*)dY.p + offN[q];
+    F.pop = (const int*)dP.p + offN[q];
+    F.rhotab = ds.rhomat ? (const double*)dR.p + offR[q] : nullptr;
+    F.scal = (double*)dScal.p + (size_t)q * NSCAL;
+    F.a_out = (double*)dA.p + offN[q];
+    F.diag_out = (double*)dDiag.p + offN[q];
+    F.info = (int*)dInfo.p + q;
+    F.N = (int)ds.N;
+    F.d = ds.d;
+    F.np = ds.np;
+    F.pad = 0;
+    gpedm_fit_s& m = meta[q];
+    m.N = ds.N;
+    m.d = ds.d;
+    m.np = ds.np;
+    m.p = ds.d + 3;
+    m.has_rhomat = ds.rhomat != nullptr;
+    m.single_pop = true;
+    for (int64_t i = 1; i < ds.N; ++i)
+      if (ds.pop[i] != ds.pop[0]) m.single_pop = false;
+    m.hparams = hparams + q;
+    m.hscal = hscal + (size_t)q * NSCAL;
+  }
+  CU(cudaMemcpy(dFits.p, hfits.data(), sizeof(SmallFit) * nf, cudaMemcpyHostToDevice));
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  const int DC = dmax <= 8 ? 8 : (dmax <= 16 ? 16 : 32);
+  std::vector<int> active;
+  auto launch = [&](int full) -> int {
+    const int na = (int)active.size();
+    if (na == 0) return 0;
+    cudaError_t e2 = cudaMemcpyAsync(dParams.p, hparams, sizeof(EvalParams) * nf, cudaMemcpyHostToDevice, st);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(dActive.p, active.data(), (size_t)na * 4, cudaMemcpyHostToDevice, st);
+    if (e2 != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "small-fit upload failed: %s", cudaGetErrorString(e2));
+    if (DC == 8)
+      small_eval_kernel<8><<<na, DG_THREADS, small_eval_smem_bytes<8>(), st>>>((const SmallFit*)dFits.p, (const EvalParams*)dParams.p, (const int*)dActive.p, full);
+    else if (DC == 16)
+      small_eval_kernel<16><<<na, DG_THREADS, small_eval_smem_bytes<16>(), st>>>((const SmallFit*)dFits.p, (const EvalParams*)dParams.p, (const int*)dActive.p, full);
+    else
+      small_eval_kernel<32><<<na, DG_THREADS, small_eval_smem_bytes<32>(), st>>>((const SmallFit*)dFits.p, (const EvalParams*)dParams.p, (const int*)dActive.p, full);
+    e2 = cudaMemcpyAsync(hscal, dScal.p, (size_t)NSCAL * 8 * nf, cudaMemcpyDeviceToHost, st);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(hinfo, dInfo.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+    if (e2 == cudaSuccess) e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "small-fit evaluation failed: %s", cudaGetErrorString(e2));
+    return 0;
+  };
+  struct State {
+    double pa[GPEDM_MAX_P], del[GPEDM_MAX_P], grad[GPEDM_MAX_P], panew[GPEDM_MAX_P];
+    double nll = 0, s = 0, df = 10;
+    int iter = 0, nevals = 0, status = 0;
+    bool done = false;
+  };
+  std::vector<State> stt(nf);
+  std::vector<HostPars> hp(nf);
+  // ---- initial evaluation (:545)
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    for (int i = 0; i < ds.d + 3; ++i) {
+      stt[q].pa[i] = stt[q].panew[i] = ds.initparst[i];
+      stt[q].del[i] = o.delta0;
+    }
+    host_transform(&meta[q], stt[q].panew, ds.modeprior, ds.fixedpars, ds.rhofixed, hp[q]);
+    fill_params(&meta[q], hp[q]);
+    active.push_back(q);
+  }
+  rc = launch(0);
+  bool first = true;
+  while (rc == 0) {
+    std::vector<int> next_active;
+    for (int q : active) {
+      State& S = stt[q];
+      const gpedm_fit_desc& ds = descs[idx[q]];
+      gpedm_result r;
+      finish_result(&meta[q], hp[q], false, &r);
+      S.nevals++;
+      if (hinfo[q] > 0) {
+        S.status = hinfo[q];
+        S.done = true;
+        continue;
+      }
+      const int p = ds.d + 3;
+      if (first) {
+        S.nll = r.nllpost;
+        for (int i = 0; i < p; ++i) S.grad[i] = r.grad[i];
+        S.s = r.gradnorm;
+      } else {
+        S.s = r.gradnorm;
+        S.df = fabs(r.nllpost / S.nll - 1);  // :565
+        for (int i = 0; i < p; ++i) {
+          const double gc = S.grad[i] * r.grad[i];
+          const double tdel = S.del[i] * (1 + eta_plus * (gc > 0) + eta_minus * (gc < 0));  // :569
+          S.del[i] = tdel < o.deltamin ? o.deltamin : (tdel > o.deltamax ? o.deltamax : tdel);
+          S.pa[i] = S.panew[i];
+          S.grad[i] = r.grad[i];
+        }
+        S.nll = r.nllpost;
+        S.iter++;
+      }
+      if (S.s > o.tol_grad && S.iter < o.maxiter && S.df > o.tol_df) {  // :556
+        for (int i = 0; i < p; ++i) S.panew[i] = S.pa[i] - sgn(S.grad[i]) * S.del[i];  // :559
+        host_transform(&meta[q], S.panew, ds.modeprior, ds.fixedpars, ds.rhofixed, hp[q]);
+        fill_params(&meta[q], hp[q]);
+        next_active.push_back(q);
+      } else {
+        S.done = true;
+      }
+    }
+    first = false;
+    active.swap(next_active);
+    if (active.empty()) break;
+    rc = launch(0);
+  }
+  // ---- final full evaluation at each fit's last parameters (:580)
+  std::vector<double> ha(totN), hd(totN);
+  if (rc == 0) {
+    active.clear();
+    for (int q = 0; q < nf; ++q) {
+      if (stt[q].status != 0) continue;
+      const gpedm_fit_desc& ds = descs[idx[q]];
+      host_transform(&meta[q], stt[q].pa, ds.modeprior, ds.fixedpars, ds.rhofixed, hp[q]);
+      fill_params(&meta[q], hp[q]);
+      active.push_back(q);
+    }
+    rc = launch(1);
+    if (rc == 0) {
+      e = cudaMemcpy(ha.data(), dA.p, totN * 8, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(hd.data(), dDiag.p, totN * 8, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = set_err(GPEDM_ERR_CUDA, "small-fit download failed: %s", cudaGetErrorString(e));
+    }
+  }
+  cudaStreamDestroy(st);
+  if (rc) return rc;
+  int first_bad = 0;
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    gpedm_result& R = results[idx[q]];
+    State& S = stt[q];
+    if (S.status == 0 && hinfo[q] > 0) S.status = hinfo[q];
+    if (S.status != 0) {
+      memset(&R, 0, sizeof(R));
+      R.status = S.status;
+      R.iter = S.iter;
+      R.nevals = S.nevals;
+      R.p = ds.d + 3;
+      if (!first_bad) first_bad = S.status;
+      continue;
+    }
+    finish_result(&meta[q], hp[q], true, &R);
+    R.iter = S.iter;
+    R.nevals = S.nevals + 1;
+    R.status = 0;
+    const double ve = hp[q].ve;
+    for (int64_t i = 0; i < ds.N; ++i) {
+      const double a = ha[offN[q] + i], sii = hd[offN[q] + i], y = ds.Y[i];
+      if (ds.want_loo && ds.loo_mean) ds.loo_mean[i] = y - a / sii;
+      if (ds.want_loo && ds.loo_var) ds.loo_var[i] = 1.0 / sii - ve;
+      if (ds.insamp_mean) ds.insamp_mean[i] = y - ve * a;
+      if (ds.insamp_var) ds.insamp_var[i] = ve - ve * ve * sii;
+    }
+  }
+  if (first_bad) return set_err(first_bad, "at least one small fit failed: covariance matrix not positive definite (pivot %d)", first_bad);
+  return 0;
+}
+
 // Fixed-width record exchanged by the final all-gather.
 struct BatchRecord {
   int32_t fit_index;
@@ -1526,8 +1785,32 @@ extern "C" int gpedm_fit_batch(int32_t nfits, const gpedm_fit_desc* descs, int32
       per_worker[wi].push_back(rec);
     }
   };
+  bool all_small = !g_no_small_batch;
+  for (int i = 0; i < nfits && all_small; ++i) all_small = descs[i].N <= TB;
   std::vector<std::thread> th;
-  for (int wi = 0; wi < ngpus * W; ++wi) th.emplace_back(worker, wi);
+  if (all_small) {
+    // every fit fits one tile: lockstep batched evaluation, one thread (and one launch per Rprop
+    // iteration) per GPU over a strided share of the fits
+    auto small_worker = [&](int g) {
+      std::vector<int> mine;
+      for (int q = g; q < nfits; q += ngpus) mine.push_back(order[q]);
+      std::vector<gpedm_result> tmp(nfits);
+      int rc = fit_batch_small(devs[g], mine, descs, opts, tmp.data());
+      if (rc != 0) werrs[g * W] = gpedm_last_error();
+      for (int i : mine) {
+        BatchRecord rec;
+        memset(&rec, 0, sizeof(rec));
+        rec.fit_index = i;
+        rec.valid = 1;
+        rec.res = tmp[i];
+        if (rc < 0 && rec.res.status == 0) rec.res.status = rc;
+        per_worker[g * W].push_back(rec);
+      }
+    };
+    for (int g = 0; g < ngpus; ++g) th.emplace_back(small_worker, g);
+  } else {
+    for (int wi = 0; wi < ngpus * W; ++wi) th.emplace_back(worker, wi);
+  }
   for (auto& t : th) t.join();
   for (int wi = 0; wi < ngpus * W; ++wi) {
     const int g = wi / W;

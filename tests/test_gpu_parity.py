@@ -461,3 +461,43 @@ def test_predict_new_chunking_and_set_data(gpu_lib):
     ref2 = oracle_eval(parst, Y2, X2, pop2)
     assert rel(out["nllpost"], ref2["nllpost"]) <= TOL_NLL and grad_err(out["grad"], ref2["grad"]) <= TOL_GRAD
     m.close()
+
+
+def test_small_fit_batch_matches_tiled_path_and_oracle(gpu_lib, thetalog2pop):
+    """Batches whose fits all have N <= 128 take the one-CTA-per-fit lockstep path (SURVEY 8f rank 3);
+    it must agree with the tiled per-handle path and with the oracle (K1 is such a fit)."""
+    tl = thetalog2pop
+    probs = []
+    # K1 itself (N=94, 2 pops, local scaling) built by the fitGP front end of the oracle
+    o = O.fitGP(data=tl, y="Abundance", pop="Population", E=3, tau=1, scaling="local")
+    probs.append(dict(Y=o["inputs"]["Y"], X=o["inputs"]["X"], pop=o["inputs"]["Pop"],
+                      initparst=batch.default_initparst(3, single_pop=False)))
+    # an E x tau grid on a short single-population series
+    y = synth.ricker(120, 8)
+    g, _ = batch.grid_problems(y, [1, 2, 3, 4], [1, 2])
+    probs += g
+    # pairwise fits with a fixed rho and a fixed ve (getrhomatrix-style clients)
+    Y, X, pop = synth.hierarchical_thetalog(npop=3, n=44, E=2, seed0=70)
+    for a, b in [(0, 1), (0, 2), (1, 2)]:
+        m = (pop == a) | (pop == b)
+        probs.append(dict(Y=Y[m], X=X[m], pop=pop[m], initparst=batch.default_initparst(2, single_pop=False)))
+    probs.append(dict(Y=Y, X=X, pop=pop, initparst=batch.default_initparst(2, False), rhofixed=0.3,
+                      fixedpars=[np.nan, np.nan, 0.01, np.nan]))
+    assert max(len(p["Y"]) for p in probs) <= 128
+    res = G.fit_batch(probs, ngpus=1, want_loo=True)
+    for pr, r in zip(probs, res):
+        m = G.GPModel(pr["Y"], pr["X"], pr.get("pop"))
+        one = m.fit_rprop(pr.get("initparst", batch.default_initparst(np.atleast_2d(pr["X"].T).T.shape[1])), 1.0,
+                          pr.get("fixedpars"), pr.get("rhofixed"))
+        assert one["iter"] == r["iter"] and r["status"] == 0
+        assert np.max(np.abs(one["pars"] - r["pars"]) / np.maximum(1, np.abs(one["pars"]))) <= 1e-9
+        assert rel(r["nllpost"], one["nllpost"]) <= 1e-11
+        assert rel(r["lnL_LOO"], one["lnL_LOO"]) <= 1e-9 and rel(r["df"], one["df"]) <= 1e-9
+        np.testing.assert_allclose(r["loo_mean"], m.vector(_lib.VEC_LOO_MEAN), atol=1e-9)
+        np.testing.assert_allclose(r["loo_var"], m.vector(_lib.VEC_LOO_VAR), rtol=1e-6)
+        np.testing.assert_allclose(r["insamp_mean"], m.vector(_lib.VEC_MEAN), atol=1e-9)
+        m.close()
+    # K1 against the oracle (README.md:79-101)
+    assert res[0]["iter"] == o["iter"] == 38
+    assert np.max(np.abs(res[0]["pars"] - o["pars"]) / np.maximum(1, np.abs(o["pars"]))) <= TOL_MODE
+    assert rel(res[0]["nllpost"], o["nllpost"]) <= TOL_NLL
