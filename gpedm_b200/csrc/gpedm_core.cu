@@ -96,7 +96,7 @@ static bool g_attr_set[64] = {};
 static int g_num_sms[64] = {};
 // GPEDM_DIAG_REF=1 selects the simple (slow) reference diagonal-block kernel, for A/B debugging.
 static const bool g_no_lookahead = getenv("GPEDM_NO_LOOKAHEAD") != nullptr && atoi(getenv("GPEDM_NO_LOOKAHEAD")) != 0;
-static const int g_group = getenv("GPEDM_POTRF_GROUP") ? std::max(1, atoi(getenv("GPEDM_POTRF_GROUP"))) : 2;
+static const int g_group = getenv("GPEDM_POTRF_GROUP") ? std::max(1, atoi(getenv("GPEDM_POTRF_GROUP"))) : 0;
 static const int g_group_min = getenv("GPEDM_POTRF_GROUP_MIN") ? atoi(getenv("GPEDM_POTRF_GROUP_MIN")) : 24;
 static const bool g_no_half_tiles = getenv("GPEDM_NO_HALF_TILES") != nullptr && atoi(getenv("GPEDM_NO_HALF_TILES")) != 0;
 static const int g_fill_tail = getenv("GPEDM_FILL_TAIL") ? atoi(getenv("GPEDM_FILL_TAIL")) : 32;
@@ -482,7 +482,9 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
       t.ld2 = ld;
       return launch_tiles(h, s_, t, 0, s_ == ax && !g_no_split && ntl * 4 <= 2 * h->num_sms);
     };
-    auto group_size = [&](int start) { return (nb - start - 1 >= g_group_min) ? g_group : 1; };
+    // group size: GPEDM_POTRF_GROUP if set, else 4 for large matrices (bulk-dominated), 2 otherwise
+    const int gsz = g_group > 0 ? g_group : (nb >= 96 ? 4 : 2);
+    auto group_size = [&](int start) { return (nb - start - 1 >= g_group_min) ? gsz : 1; };
     // Early triangular inverse: level s, pair p (tile rows/cols [2ps, 2ps+2s)) only needs block
     // columns < 2s(p+1) of L and the diagonal-block inverses, so it can run as soon as the Cholesky
     // has passed that column - on a low-priority stream, filling the SMs the chain-bound tail of the
