@@ -22,7 +22,7 @@ namespace gpedm {
 constexpr int DG_THREADS = 512;
 #ifdef GPEDM_DIAG_TIMING
 __device__ long long g_diag_ts[32];
-#define DG_TS(i) do { if (threadIdx.x == 0) g_diag_ts[i] = clock64(); } while (0)
+#define DG_TS(i) do { if (threadIdx.x == 0) g_diag_ts[i] = clock64(); __syncwarp(); } while (0)
 #else
 #define DG_TS(i) do { } while (0)
 #endif

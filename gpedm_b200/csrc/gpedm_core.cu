@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -107,7 +108,9 @@ static const int g_graph_max_nb = getenv("GPEDM_GRAPH_MAX_NB") ? atoi(getenv("GP
 static const int g_batch_workers = getenv("GPEDM_BATCH_WORKERS_PER_GPU") ? atoi(getenv("GPEDM_BATCH_WORKERS_PER_GPU")) : 0;
 static const bool g_no_graph = getenv("GPEDM_NO_GRAPH") != nullptr && atoi(getenv("GPEDM_NO_GRAPH")) != 0;
 static const bool g_diag_ref = getenv("GPEDM_DIAG_REF") != nullptr && atoi(getenv("GPEDM_DIAG_REF")) != 0;
+static std::mutex g_attr_mutex;
 static int ensure_kernel_attrs(int device) {
+  std::lock_guard<std::mutex> lock(g_attr_mutex);  // batch workers create handles concurrently
   if (device < 64 && g_attr_set[device]) return 0;
   CU(cudaFuncSetAttribute(tile_once_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CU(cudaFuncSetAttribute(tile_once_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -201,7 +204,7 @@ static void free_handle(gpedm_fit_s* h) {
   delete h;
 }
 
-extern "C" int gpedm_create(int device, int64_t N, int32_t d, int32_t np, const double* X, const double* Y,
+static int gpedm_create_impl(int device, int64_t N, int32_t d, int32_t np, const double* X, const double* Y,
                             const int32_t* pop, const double* rhomat, gpedm_handle* out) {
   if (!out) return set_err(GPEDM_ERR_ARG, "out handle is NULL");
   *out = nullptr;
@@ -300,7 +303,7 @@ extern "C" int gpedm_create(int device, int64_t N, int32_t d, int32_t np, const 
   return 0;
 }
 
-extern "C" int gpedm_set_data(gpedm_handle h, const double* X, const double* Y, const int32_t* pop) {
+static int gpedm_set_data_impl(gpedm_handle h, const double* X, const double* Y, const int32_t* pop) {
   if (!h || !X || !Y || !pop) return set_err(GPEDM_ERR_ARG, "NULL argument");
   for (int64_t i = 0; i < h->N; ++i)
     if (pop[i] < 0 || pop[i] >= h->np) return set_err(GPEDM_ERR_ARG, "pop[%lld]=%d outside 0..np-1", (long long)i, pop[i]);
@@ -878,7 +881,7 @@ extern "C" int gpedm_fit_rprop(gpedm_handle h, const double* initparst, double m
 }
 
 // ------------------------------------------------------------------------------- exports
-extern "C" int gpedm_get_vector(gpedm_handle h, int which, double* outv) {
+static int gpedm_get_vector_impl(gpedm_handle h, int which, double* outv) {
   if (!h || !outv) return set_err(GPEDM_ERR_ARG, "NULL argument");
   if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident (call gpedm_likegrad(full=1) or gpedm_fit_rprop first)");
   CU(cudaSetDevice(h->device));
@@ -912,7 +915,7 @@ static int launch_cov_rect(gpedm_fit_s* h, double* out, size_t ldo, int rows_all
   return 0;
 }
 
-extern "C" int gpedm_get_matrix(gpedm_handle h, int which, double* outm) {
+static int gpedm_get_matrix_impl(gpedm_handle h, int which, double* outm) {
   if (!h || !outm) return set_err(GPEDM_ERR_ARG, "NULL argument");
   if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
   CU(cudaSetDevice(h->device));
@@ -946,7 +949,7 @@ extern "C" int gpedm_get_matrix(gpedm_handle h, int which, double* outm) {
   return 0;
 }
 
-extern "C" int gpedm_getcov(int device, int32_t d, const double* phi, double sigma2, double rho, int64_t N,
+static int gpedm_getcov_impl(int device, int32_t d, const double* phi, double sigma2, double rho, int64_t N,
                             const double* X, const int32_t* pop, int64_t M, const double* X2, const int32_t* pop2,
                             int32_t np, const double* rhomat, double* Cd_out) {
   if (!phi || !X || !pop || !X2 || !pop2 || !Cd_out) return set_err(GPEDM_ERR_ARG, "NULL argument");
@@ -1005,7 +1008,7 @@ extern "C" int gpedm_getcov(int device, int32_t d, const double* phi, double sig
 
 // getcovinv (reference R/GPfunctions.R:818-830): Cholesky factor and full inverse of a caller-supplied
 // symmetric positive definite matrix, through the same factorisation pipeline as the likelihood.
-extern "C" int gpedm_covinv(int device, int64_t n, const double* Sigma, double* L_out, double* iKVs_out) {
+static int gpedm_covinv_impl(int device, int64_t n, const double* Sigma, double* L_out, double* iKVs_out) {
   if (!Sigma || (!L_out && !iKVs_out) || n < 1) return set_err(GPEDM_ERR_ARG, "bad arguments");
   std::vector<double> X((size_t)n, 0.0), Y((size_t)n, 0.0);
   std::vector<int32_t> pop((size_t)n, 0);
@@ -1043,8 +1046,20 @@ extern "C" int gpedm_covinv(int device, int64_t n, const double* Sigma, double* 
   return rc;
 }
 
+// ------------------------------------------------------------------------------- RAII buffers
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+};
+struct PinnedBuf {
+  void* p = nullptr;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMallocHost(&p, std::max<size_t>(bytes, 16)); }
+};
+
 // ------------------------------------------------------------------------------- prediction
-extern "C" int gpedm_predict_new(gpedm_handle h, int64_t M, const double* Xnew, const int32_t* popnew, double* mean,
+static int gpedm_predict_new_impl(gpedm_handle h, int64_t M, const double* Xnew, const int32_t* popnew, double* mean,
                                  double* var, double* gpgrad) {
   if (!h || !Xnew || !popnew || !mean || !var) return set_err(GPEDM_ERR_ARG, "NULL argument");
   if (M < 1) return set_err(GPEDM_ERR_ARG, "M must be >= 1");
@@ -1117,148 +1132,86 @@ extern "C" int gpedm_predict_new(gpedm_handle h, int64_t M, const double* Xnew, 
   return 0;
 }
 
-// Small dense SPD solve on the host for the block leave-out formulas (blocks are the size of the
-// excluded set: 2*exclradius+1 rows, or the rows sharing a time value).
-static bool host_chol(std::vector<double>& A, int n) {
-  for (int j = 0; j < n; ++j) {
-    double s = A[j + (size_t)j * n];
-    for (int k = 0; k < j; ++k) s -= A[j + (size_t)k * n] * A[j + (size_t)k * n];
-    if (!(s > 0)) return false;
-    double dj = sqrt(s);
-    A[j + (size_t)j * n] = dj;
-    for (int i = j + 1; i < n; ++i) {
-      double t = A[i + (size_t)j * n];
-      for (int k = 0; k < j; ++k) t -= A[i + (size_t)k * n] * A[j + (size_t)k * n];
-      A[i + (size_t)j * n] = t / dj;
-    }
-  }
-  return true;
-}
-static void host_chol_solve(const std::vector<double>& L, int n, double* b) {
-  for (int i = 0; i < n; ++i) {
-    double t = b[i];
-    for (int k = 0; k < i; ++k) t -= L[i + (size_t)k * n] * b[k];
-    b[i] = t / L[i + (size_t)i * n];
-  }
-  for (int i = n - 1; i >= 0; --i) {
-    double t = b[i];
-    for (int k = i + 1; k < n; ++k) t -= L[k + (size_t)i * n] * b[k];
-    b[i] = t / L[i + (size_t)i * n];
-  }
-}
-
 // Shared implementation of loo / lto given the groups (excluded sets) and focal rows.
 //   members/goff : concatenated excluded-row indices per group;  focal[f], fgroup[f].
+// The block solves run on the device (leaveout_blocks_kernel); the host only maps focal rows to
+// their position inside their group.
 static int leaveout_core(gpedm_fit_s* h, const std::vector<int>& members, const std::vector<int>& goff,
                          const std::vector<int>& focal, const std::vector<int>& fgroup, double* mean, double* var,
                          double* gpgrad) {
   CU(cudaSetDevice(h->device));
   const int64_t N = h->N;
   const int ng = (int)goff.size() - 1, nf = (int)focal.size();
-  std::vector<double> a(N), ds(N);
-  CU(cudaMemcpy(a.data(), h->da, N * 8, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(ds.data(), h->ddiagS, N * 8, cudaMemcpyDeviceToHost));
+  const size_t nm = members.size();
   std::vector<long long> boff(ng + 1, 0);
   for (int g = 0; g < ng; ++g) {
     long long nbk = goff[g + 1] - goff[g];
-    boff[g + 1] = boff[g] + nbk * nbk;
+    boff[g + 1] = boff[g] + (nbk > 1 ? nbk * nbk : 0);
   }
-  std::vector<double> blocks((size_t)boff[ng]);
-  int *didx = nullptr, *dgoff = nullptr;
-  long long* dboff = nullptr;
-  double* dblocks = nullptr;
-  cudaError_t e = cudaMalloc((void**)&didx, std::max<size_t>(1, members.size()) * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dgoff, (size_t)(ng + 1) * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dboff, (size_t)(ng + 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dblocks, std::max<size_t>(1, blocks.size()) * 8);
-  if (e == cudaSuccess) e = cudaMemcpy(didx, members.data(), members.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(dgoff, goff.data(), (size_t)(ng + 1) * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(dboff, boff.data(), (size_t)(ng + 1) * 8, cudaMemcpyHostToDevice);
+  DevBuf didx, dgoff, dboff, dwork, du, ddinv, dbad, dfocal, dfg, dg;
+  cudaError_t e = didx.alloc(nm * 4);
+  if (e == cudaSuccess) e = dgoff.alloc((size_t)(ng + 1) * 4);
+  if (e == cudaSuccess) e = dboff.alloc((size_t)(ng + 1) * 8);
+  if (e == cudaSuccess) e = dwork.alloc((size_t)boff[ng] * 2 * 8);
+  if (e == cudaSuccess) e = du.alloc(nm * 8);
+  if (e == cudaSuccess) e = ddinv.alloc(nm * 8);
+  if (e == cudaSuccess) e = dbad.alloc(4);
+  if (e == cudaSuccess && nm) e = cudaMemcpyAsync(didx.p, members.data(), nm * 4, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dgoff.p, goff.data(), (size_t)(ng + 1) * 4, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dboff.p, boff.data(), (size_t)(ng + 1) * 8, cudaMemcpyHostToDevice, h->stream);
+  const int big = 0x7fffffff;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dbad.p, &big, 4, cudaMemcpyHostToDevice, h->stream);
+  std::vector<double> u(nm), dinv(nm);
+  int bad = big;
   if (e == cudaSuccess && ng > 0) {
-    gather_blocks_kernel<<<ng, 128, 0, h->stream>>>(h->bufC, (size_t)h->Np, didx, dgoff, dboff, ng, dblocks);
+    leaveout_blocks_kernel<<<ng, 128, 0, h->stream>>>(h->bufC, (size_t)h->Np, (const int*)didx.p, (const int*)dgoff.p,
+                                                      (const long long*)dboff.p, ng, h->da, (double*)dwork.p,
+                                                      (double*)du.p, (double*)ddinv.p, (int*)dbad.p);
     h->launches++;
-    e = cudaStreamSynchronize(h->stream);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && nm) e = cudaMemcpyAsync(u.data(), du.p, nm * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && nm) e = cudaMemcpyAsync(dinv.data(), ddinv.p, nm * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, dbad.p, 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   }
-  if (e == cudaSuccess) e = cudaMemcpy(blocks.data(), dblocks, blocks.size() * 8, cudaMemcpyDeviceToHost);
-  // per-group solves: u = S_BB^-1 a_B, and diag(S_BB^-1)
-  std::vector<double> u(members.size()), dinv(members.size());
-  int bad = 0;
-  if (e == cudaSuccess) {
-    std::vector<double> Lb, rhs;
-    for (int g = 0; g < ng; ++g) {
-      int b0 = goff[g], nbk = goff[g + 1] - b0;
-      if (nbk == 0) continue;
-      Lb.assign(blocks.begin() + boff[g], blocks.begin() + boff[g + 1]);
-      if (!host_chol(Lb, nbk)) {
-        bad = g + 1;
-        break;
-      }
-      rhs.resize(nbk);
-      for (int r = 0; r < nbk; ++r) rhs[r] = a[members[b0 + r]];
-      host_chol_solve(Lb, nbk, rhs.data());
-      for (int r = 0; r < nbk; ++r) u[b0 + r] = rhs[r];
-      // diag of inverse: column-wise forward solves  ||L^-1 e_r||^2
-      for (int r = 0; r < nbk; ++r) {
-        std::vector<double> w(nbk, 0.0);
-        w[r] = 1.0;
-        double acc = 0.0;
-        for (int i = r; i < nbk; ++i) {
-          double t = w[i];
-          for (int k = r; k < i; ++k) t -= Lb[i + (size_t)k * nbk] * w[k];
-          w[i] = t / Lb[i + (size_t)i * nbk];
-          acc += w[i] * w[i];
-        }
-        dinv[b0 + r] = acc;
-      }
-    }
-  }
-  if (e == cudaSuccess && !bad) {
-    for (int f = 0; f < nf; ++f) {
-      int g = fgroup[f], b0 = goff[g], nbk = goff[g + 1] - b0;
-      int pos = -1;
-      for (int r = 0; r < nbk; ++r)
-        if (members[b0 + r] == focal[f]) pos = r;
-      if (pos < 0) {
-        mean[f] = NAN;
-        var[f] = NAN;
-        continue;
-      }
-      mean[f] = h->hY[focal[f]] - u[b0 + pos];
-      var[f] = dinv[b0 + pos] - h->cur_ve;
-    }
-    if (gpgrad && nf > 0) {
-      int *dfocal = nullptr, *dfg = nullptr;
-      double *du = nullptr, *dg = nullptr;
-      e = cudaMalloc((void**)&dfocal, (size_t)nf * 4);
-      if (e == cudaSuccess) e = cudaMalloc((void**)&dfg, (size_t)nf * 4);
-      if (e == cudaSuccess) e = cudaMalloc((void**)&du, std::max<size_t>(1, u.size()) * 8);
-      if (e == cudaSuccess) e = cudaMalloc((void**)&dg, (size_t)nf * h->d * 8);
-      if (e == cudaSuccess) e = cudaMemcpy(dfocal, focal.data(), (size_t)nf * 4, cudaMemcpyHostToDevice);
-      if (e == cudaSuccess) e = cudaMemcpy(dfg, fgroup.data(), (size_t)nf * 4, cudaMemcpyHostToDevice);
-      if (e == cudaSuccess) e = cudaMemcpy(du, u.data(), u.size() * 8, cudaMemcpyHostToDevice);
-      if (e == cudaSuccess) {
-        loo_gpgrad_kernel<<<nf, 256, 0, h->stream>>>(h->bufC, (size_t)h->Np, (int)N, h->dX, h->dpop, h->drhotab, h->da,
-                                                     h->dparams, dfocal, dfg, didx, dgoff, du, nf, dg);
-        h->launches++;
-        e = cudaStreamSynchronize(h->stream);
-      }
-      if (e == cudaSuccess) e = cudaMemcpy(gpgrad, dg, (size_t)nf * h->d * 8, cudaMemcpyDeviceToHost);
-      cudaFree(dfocal);
-      cudaFree(dfg);
-      cudaFree(du);
-      cudaFree(dg);
-    }
-  }
-  cudaFree(didx);
-  cudaFree(dgoff);
-  cudaFree(dboff);
-  cudaFree(dblocks);
   if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "leave-out prediction failed: %s", cudaGetErrorString(e));
-  if (bad) return set_err(GPEDM_ERR_STATE, "leave-out block %d of Sigma^-1 is not positive definite", bad);
+  if (bad != big) return set_err(GPEDM_ERR_STATE, "leave-out block %d of Sigma^-1 is not positive definite", bad);
+  for (int f = 0; f < nf; ++f) {
+    const int g = fgroup[f], b0 = goff[g], nbk = goff[g + 1] - b0;
+    int pos = -1;
+    for (int r = 0; r < nbk; ++r)
+      if (members[b0 + r] == focal[f]) pos = r;
+    if (pos < 0) {
+      mean[f] = NAN;
+      var[f] = NAN;
+      continue;
+    }
+    mean[f] = h->hY[focal[f]] - u[b0 + pos];
+    var[f] = dinv[b0 + pos] - h->cur_ve;
+  }
+  if (gpgrad && nf > 0) {
+    e = dfocal.alloc((size_t)nf * 4);
+    if (e == cudaSuccess) e = dfg.alloc((size_t)nf * 4);
+    if (e == cudaSuccess) e = dg.alloc((size_t)nf * h->d * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dfocal.p, focal.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dfg.p, fgroup.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+      loo_gpgrad_kernel<<<nf, 256, 0, h->stream>>>(h->bufC, (size_t)h->Np, (int)N, h->dX, h->dpop, h->drhotab, h->da,
+                                                   h->dparams, (const int*)dfocal.p, (const int*)dfg.p,
+                                                   (const int*)didx.p, (const int*)dgoff.p, (const double*)du.p, nf,
+                                                   (double*)dg.p);
+      h->launches++;
+      e = cudaGetLastError();
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(gpgrad, dg.p, (size_t)nf * h->d * 8, cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    }
+    if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "leave-out gradient failed: %s", cudaGetErrorString(e));
+  }
   return 0;
 }
 
-extern "C" int gpedm_predict_loo(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary,
+static int gpedm_predict_loo_impl(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary,
                                  double* mean, double* var, double* gpgrad) {
   if (!h || !mean || !var) return set_err(GPEDM_ERR_ARG, "NULL argument");
   if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
@@ -1289,7 +1242,7 @@ extern "C" int gpedm_predict_loo(gpedm_handle h, int32_t exclradius, const doubl
   return leaveout_core(h, members, goff, focal, fgroup, mean, var, gpgrad);
 }
 
-extern "C" int gpedm_predict_lto(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary,
+static int gpedm_predict_lto_impl(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary,
                                  double* mean, double* var, double* gpgrad) {
   if (!h || !mean || !var || !time) return set_err(GPEDM_ERR_ARG, "NULL argument (time is required)");
   if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
@@ -1348,7 +1301,7 @@ extern "C" int gpedm_predict_lto(gpedm_handle h, int32_t exclradius, const doubl
   return 0;
 }
 
-extern "C" int gpedm_predict_sequential(gpedm_handle h, const double* time, double* ymean, double* ysd2) {
+static int gpedm_predict_sequential_impl(gpedm_handle h, const double* time, double* ymean, double* ysd2) {
   if (!h || !time || !ymean || !ysd2) return set_err(GPEDM_ERR_ARG, "NULL argument");
   if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
   CU(cudaSetDevice(h->device));
@@ -1465,17 +1418,6 @@ static bool load_nccl(NcclApi& n) {
 // fmingrad_Rprop (reference R/GPfunctions.R:522-584) runs on the host per fit exactly as in
 // gpedm_fit_rprop.  A last launch with full = 1 at each fit's final parameters yields a and
 // diag(Sigma^-1), from which the in-sample and leave-one-out vectors follow in O(N).
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() { cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
-};
-struct PinnedBuf {
-  void* p = nullptr;
-  ~PinnedBuf() { if (p) cudaFreeHost(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMallocHost(&p, std::max<size_t>(bytes, 16)); }
-};
-
 static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_fit_desc* descs,
                            const gpedm_rprop_options* opts_in, gpedm_result* results) {
   const int nf = (int)idx.size();
@@ -1739,7 +1681,7 @@ static int run_one_fit(int device, const gpedm_fit_desc& ds, const gpedm_rprop_o
   return rc;
 }
 
-extern "C" int gpedm_fit_batch(int32_t nfits, const gpedm_fit_desc* descs, int32_t ngpus, const int32_t* devices,
+static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int32_t ngpus, const int32_t* devices,
                                const gpedm_rprop_options* opts, gpedm_result* results) {
   if (nfits < 0 || (nfits > 0 && (!descs || !results))) return set_err(GPEDM_ERR_ARG, "bad arguments");
   if (nfits == 0) return 0;
@@ -1759,25 +1701,35 @@ extern "C" int gpedm_fit_batch(int32_t nfits, const gpedm_fit_desc* descs, int32
     return n * n * n + 40.0 * descs[i].d * n * n;
   };
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+  // Fits with N <= 128 (one tile) advance in lockstep through the batched one-CTA-per-fit kernel,
+  // one host thread per GPU over a strided share; everything larger goes through the tiled
+  // pipeline, pulled from a shared queue by W worker threads per GPU.  Both kinds run concurrently.
+  std::vector<int> small_order, big_order;
+  for (int q = 0; q < nfits; ++q) (descs[order[q]].N <= TB && !g_no_small_batch ? small_order : big_order).push_back(order[q]);
+  if (small_order.size() < 2) {  // a single small fit gains nothing from the batched kernel
+    big_order = order;
+    small_order.clear();
+  }
+  const int nbig = (int)big_order.size();
   std::atomic<int> next(0);
   std::vector<std::vector<BatchRecord>> per_gpu(ngpus);
   std::vector<std::string> errs(ngpus);
-  // W worker threads per GPU, each with its own handles / streams: two independent fits interleave
+  // W worker threads per GPU, each with its own handles / streams: independent fits interleave
   // on one device, so the latency-bound stretches of one evaluation (the serial Cholesky chain)
   // are filled by the bulk kernels of the other.
   int64_t nmax = 0;
-  for (int i = 0; i < nfits; ++i) nmax = std::max<int64_t>(nmax, descs[i].N);
+  for (int i : big_order) nmax = std::max<int64_t>(nmax, descs[i].N);
   // small problems leave most of the GPU idle -> interleave several fits; large ones already fill it
   const int W = g_batch_workers > 0 ? g_batch_workers : (nmax <= 4096 ? 3 : 1);
-  std::vector<std::vector<BatchRecord>> per_worker(ngpus * W);
-  std::vector<std::string> werrs(ngpus * W);
-  auto worker = [&](int wi) {
-    const int g = wi / W;
+  std::vector<std::vector<BatchRecord>> per_worker(ngpus * (W + 1));  // slot W of each GPU: the small-fit thread
+  std::vector<std::string> werrs(ngpus * (W + 1));
+  auto worker = [&](int g, int w) {
+    const int wi = g * (W + 1) + w;
     cudaSetDevice(devs[g]);
     for (;;) {
       int q = next.fetch_add(1);
-      if (q >= nfits) break;
-      int i = order[q];
+      if (q >= nbig) break;
+      int i = big_order[q];
       BatchRecord rec;
       memset(&rec, 0, sizeof(rec));
       rec.fit_index = i;
@@ -1787,37 +1739,48 @@ extern "C" int gpedm_fit_batch(int32_t nfits, const gpedm_fit_desc* descs, int32
       per_worker[wi].push_back(rec);
     }
   };
-  bool all_small = !g_no_small_batch;
-  for (int i = 0; i < nfits && all_small; ++i) all_small = descs[i].N <= TB;
-  std::vector<std::thread> th;
-  if (all_small) {
-    // every fit fits one tile: lockstep batched evaluation, one thread (and one launch per Rprop
-    // iteration) per GPU over a strided share of the fits
-    auto small_worker = [&](int g) {
-      std::vector<int> mine;
-      for (int q = g; q < nfits; q += ngpus) mine.push_back(order[q]);
-      std::vector<gpedm_result> tmp(nfits);
-      int rc = fit_batch_small(devs[g], mine, descs, opts, tmp.data());
-      if (rc != 0) werrs[g * W] = gpedm_last_error();
-      for (int i : mine) {
-        BatchRecord rec;
-        memset(&rec, 0, sizeof(rec));
-        rec.fit_index = i;
-        rec.valid = 1;
-        rec.res = tmp[i];
-        if (rc < 0 && rec.res.status == 0) rec.res.status = rc;
-        per_worker[g * W].push_back(rec);
-      }
-    };
-    for (int g = 0; g < ngpus; ++g) th.emplace_back(small_worker, g);
-  } else {
-    for (int wi = 0; wi < ngpus * W; ++wi) th.emplace_back(worker, wi);
+  auto small_worker = [&](int g) {
+    const int wi = g * (W + 1) + W;
+    std::vector<int> mine;
+    for (size_t q = g; q < small_order.size(); q += ngpus) mine.push_back(small_order[q]);
+    if (mine.empty()) return;
+    std::vector<gpedm_result> tmp(nfits);
+    int rc = fit_batch_small(devs[g], mine, descs, opts, tmp.data());
+    if (rc != 0) werrs[wi] = gpedm_last_error();
+    for (int i : mine) {
+      BatchRecord rec;
+      memset(&rec, 0, sizeof(rec));
+      rec.fit_index = i;
+      rec.valid = 1;
+      rec.res = tmp[i];
+      if (rc < 0 && rec.res.status == 0) rec.res.status = rc;
+      per_worker[wi].push_back(rec);
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    try {
+      if (!small_order.empty())
+        for (int g = 0; g < ngpus; ++g) th.emplace_back(small_worker, g);
+      if (nbig > 0)
+        for (int g = 0; g < ngpus; ++g)
+          for (int w = 0; w < W; ++w) th.emplace_back(worker, g, w);
+    } catch (...) {
+      next.store(nbig);  // could not start every thread: let the started ones drain and stop
+      for (auto& t : th) t.join();
+      return set_err(GPEDM_ERR_STATE, "could not start batch worker threads");
+    }
+    for (auto& t : th) t.join();
   }
-  for (auto& t : th) t.join();
-  for (int wi = 0; wi < ngpus * W; ++wi) {
-    const int g = wi / W;
+  for (int wi = 0; wi < ngpus * (W + 1); ++wi) {
+    const int g = wi / (W + 1);
     per_gpu[g].insert(per_gpu[g].end(), per_worker[wi].begin(), per_worker[wi].end());
     if (errs[g].empty() && !werrs[wi].empty()) errs[g] = werrs[wi];
+  }
+  {
+    size_t got = 0;
+    for (int g = 0; g < ngpus; ++g) got += per_gpu[g].size();
+    if (got != (size_t)nfits) return set_err(GPEDM_ERR_STATE, "batch produced %zu of %d records", got, nfits);
   }
 
   if (ngpus == 1) {
@@ -1960,6 +1923,63 @@ extern "C" int gpedm_bench_evals(gpedm_handle h, const double* parst, double mod
   collect_phase_times(h);
   if (*h->hinfo > 0) return set_err(*h->hinfo, "covariance matrix not positive definite at row %d", *h->hinfo);
   return 0;
+}
+
+
+// ------------------------------------------------------------------------------- guarded entry points
+// The implementations above use std::vector / std::thread; no C++ exception may cross the C boundary.
+#define GPEDM_GUARDED(call)                                                              \
+  try {                                                                                  \
+    return (call);                                                                       \
+  } catch (const std::bad_alloc&) {                                                      \
+    return set_err(GPEDM_ERR_STATE, "out of host memory");                               \
+  } catch (const std::exception& ex) {                                                   \
+    return set_err(GPEDM_ERR_STATE, "internal error: %s", ex.what());                    \
+  } catch (...) {                                                                        \
+    return set_err(GPEDM_ERR_STATE, "internal error");                                   \
+  }
+extern "C" int gpedm_create(int device, int64_t N, int32_t d, int32_t np, const double* X, const double* Y, const int32_t* pop, const double* rhomat, gpedm_handle* out) {
+  GPEDM_GUARDED(gpedm_create_impl(device, N, d, np, X, Y, pop, rhomat, out));
+}
+
+extern "C" int gpedm_set_data(gpedm_handle h, const double* X, const double* Y, const int32_t* pop) {
+  GPEDM_GUARDED(gpedm_set_data_impl(h, X, Y, pop));
+}
+
+extern "C" int gpedm_get_vector(gpedm_handle h, int which, double* outv) {
+  GPEDM_GUARDED(gpedm_get_vector_impl(h, which, outv));
+}
+
+extern "C" int gpedm_get_matrix(gpedm_handle h, int which, double* outm) {
+  GPEDM_GUARDED(gpedm_get_matrix_impl(h, which, outm));
+}
+
+extern "C" int gpedm_getcov(int device, int32_t d, const double* phi, double sigma2, double rho, int64_t N, const double* X, const int32_t* pop, int64_t M, const double* X2, const int32_t* pop2, int32_t np, const double* rhomat, double* Cd_out) {
+  GPEDM_GUARDED(gpedm_getcov_impl(device, d, phi, sigma2, rho, N, X, pop, M, X2, pop2, np, rhomat, Cd_out));
+}
+
+extern "C" int gpedm_covinv(int device, int64_t n, const double* Sigma, double* L_out, double* iKVs_out) {
+  GPEDM_GUARDED(gpedm_covinv_impl(device, n, Sigma, L_out, iKVs_out));
+}
+
+extern "C" int gpedm_predict_new(gpedm_handle h, int64_t M, const double* Xnew, const int32_t* popnew, double* mean, double* var, double* gpgrad) {
+  GPEDM_GUARDED(gpedm_predict_new_impl(h, M, Xnew, popnew, mean, var, gpgrad));
+}
+
+extern "C" int gpedm_predict_loo(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary, double* mean, double* var, double* gpgrad) {
+  GPEDM_GUARDED(gpedm_predict_loo_impl(h, exclradius, time, primary, mean, var, gpgrad));
+}
+
+extern "C" int gpedm_predict_lto(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary, double* mean, double* var, double* gpgrad) {
+  GPEDM_GUARDED(gpedm_predict_lto_impl(h, exclradius, time, primary, mean, var, gpgrad));
+}
+
+extern "C" int gpedm_predict_sequential(gpedm_handle h, const double* time, double* ymean, double* ysd2) {
+  GPEDM_GUARDED(gpedm_predict_sequential_impl(h, time, ymean, ysd2));
+}
+
+extern "C" int gpedm_fit_batch(int32_t nfits, const gpedm_fit_desc* descs, int32_t ngpus, const int32_t* devices, const gpedm_rprop_options* opts, gpedm_result* results) {
+  GPEDM_GUARDED(gpedm_fit_batch_impl(nfits, descs, ngpus, devices, opts, results));
 }
 
 #ifdef GPEDM_DIAG_TIMING

@@ -546,21 +546,89 @@ __global__ void __launch_bounds__(256) predict_reduce_kernel(const double* __res
   }
 }
 
-// Gather the (symmetric) sub-blocks S[B_g, B_g] of Sigma^-1 for the block leave-out formulas.
-// idx: concatenated member indices; goff[g]: start of group g in idx; boff[g]: start of its
-// |B|x|B| block in out (column-major).
-__global__ void gather_blocks_kernel(const double* __restrict__ S, size_t ld, const int* __restrict__ idx,
-                                     const int* __restrict__ goff, const long long* __restrict__ boff, int ngroups,
-                                     double* __restrict__ out) {
-  int g = blockIdx.x;
+// Block leave-out solves (replaces the per-point refactorisations of reference
+// R/GPfunctions.R:1056-1104 and :1140-1194).  One CTA per excluded set B_g: gather the symmetric
+// block S_BB = Sigma^-1[B_g, B_g], factor it (right-looking Cholesky in the CTA's workspace) and return
+//   u = S_BB^-1 a_B        (leave-out mean of row i in B:  Y_i - u_i)
+//   dinv = diag(S_BB^-1)   (leave-out variance:            dinv_i - ve)
+// idx: concatenated member rows; goff[g]: start of group g in idx; boff[g]: start of its |B|x|B|
+// block in `work` (two column-major copies per group: the factor, then the columns of its inverse).
+// `bad` (initialised to INT_MAX) receives the smallest 1-based group whose block is not positive definite.
+__global__ void __launch_bounds__(128)
+    leaveout_blocks_kernel(const double* __restrict__ S, size_t ld, const int* __restrict__ idx,
+                           const int* __restrict__ goff, const long long* __restrict__ boff, int ngroups,
+                           const double* __restrict__ a, double* __restrict__ work, double* __restrict__ u,
+                           double* __restrict__ dinv, int* __restrict__ bad) {
+  const int g = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   if (g >= ngroups) return;
-  int b0 = goff[g], nbk = goff[g + 1] - b0;
-  double* o = out + boff[g];
-  for (int e = threadIdx.x; e < nbk * nbk; e += blockDim.x) {
-    int r = e % nbk, c = e / nbk;
-    int ir = idx[b0 + r], ic = idx[b0 + c];
-    int hi = max(ir, ic), lo = min(ir, ic);
-    o[e] = S[(size_t)hi + (size_t)lo * ld];
+  const int b0 = goff[g], k = goff[g + 1] - b0;
+  if (k == 0) return;
+  if (k == 1) {  // plain leave-one-out: scalar closed form
+    if (tid == 0) {
+      const int m = idx[b0];
+      const double sii = S[(size_t)m + (size_t)m * ld];
+      if (!(sii > 0.0)) atomicMin(bad, g + 1);
+      u[b0] = a[m] / sii;
+      dinv[b0] = 1.0 / sii;
+    }
+    return;
+  }
+  double* L = work + 2 * boff[g];
+  double* Wi = L + (size_t)k * k;
+  for (int e = tid; e < k * k; e += T) {
+    const int r = e % k, c = e / k;
+    const int ir = idx[b0 + r], ic = idx[b0 + c];
+    const int hi = max(ir, ic), lo = min(ir, ic);
+    L[e] = S[(size_t)hi + (size_t)lo * ld];
+  }
+  for (int r = tid; r < k; r += T) u[b0 + r] = a[idx[b0 + r]];
+  __syncthreads();
+  // ---- Cholesky (lower), column by column
+  for (int j = 0; j < k; ++j) {
+    const double piv = L[j + (size_t)j * k];
+    __syncthreads();
+    if (!(piv > 0.0)) {  // uniform across the CTA
+      if (tid == 0) atomicMin(bad, g + 1);
+      return;
+    }
+    const double dj = sqrt(piv);
+    if (tid == 0) L[j + (size_t)j * k] = dj;
+    for (int i = j + 1 + tid; i < k; i += T) L[i + (size_t)j * k] /= dj;
+    __syncthreads();
+    const int m = k - j - 1;
+    for (int e = tid; e < m * m; e += T) {
+      const int i = j + 1 + e % m, c = j + 1 + e / m;
+      if (i >= c) L[i + (size_t)c * k] -= L[i + (size_t)j * k] * L[c + (size_t)j * k];
+    }
+    __syncthreads();
+  }
+  // ---- u = L^-T L^-1 a_B
+  for (int j = 0; j < k; ++j) {
+    if (tid == 0) u[b0 + j] /= L[j + (size_t)j * k];
+    __syncthreads();
+    const double uj = u[b0 + j];
+    for (int i = j + 1 + tid; i < k; i += T) u[b0 + i] -= L[i + (size_t)j * k] * uj;
+    __syncthreads();
+  }
+  for (int j = k - 1; j >= 0; --j) {
+    if (tid == 0) u[b0 + j] /= L[j + (size_t)j * k];
+    __syncthreads();
+    const double uj = u[b0 + j];
+    for (int i = tid; i < j; i += T) u[b0 + i] -= L[j + (size_t)i * k] * uj;
+    __syncthreads();
+  }
+  // ---- diag(S_BB^-1)_r = || L^-1 e_r ||^2 : one forward solve per column, a thread each
+  for (int r = tid; r < k; r += T) {
+    double* w = Wi + (size_t)r * k;
+    double acc = 0.0;
+    for (int i = r; i < k; ++i) {
+      double t = (i == r) ? 1.0 : 0.0;
+      for (int q = r; q < i; ++q) t -= L[i + (size_t)q * k] * w[q];
+      t /= L[i + (size_t)i * k];
+      w[i] = t;
+      acc += t * t;
+    }
+    dinv[b0 + r] = acc;
   }
 }
 

@@ -501,3 +501,57 @@ def test_small_fit_batch_matches_tiled_path_and_oracle(gpu_lib, thetalog2pop):
     assert res[0]["iter"] == o["iter"] == 38
     assert np.max(np.abs(res[0]["pars"] - o["pars"]) / np.maximum(1, np.abs(o["pars"]))) <= TOL_MODE
     assert rel(res[0]["nllpost"], o["nllpost"]) <= TOL_NLL
+
+
+def test_mixed_batch_small_and_tiled(gpu_lib):
+    """A batch mixing one-tile fits (lockstep small-fit kernel) and larger ones (tiled pipeline, worker
+    threads) must return, per fit, what an individual fit returns."""
+    probs = []
+    y = synth.ricker(110, 21)
+    g, _ = batch.grid_problems(y, [1, 2, 3], [1])
+    probs += g
+    for n, E, seed in [(300, 3, 22), (520, 4, 23)]:
+        Yb, Xb = synth.embed(synth.ricker(n, seed), E, 1)
+        probs.append(dict(Y=Yb, X=Xb, initparst=batch.default_initparst(E, True)))
+    sizes = [len(p["Y"]) for p in probs]
+    assert min(sizes) <= 128 < max(sizes)
+    res = G.fit_batch(probs, ngpus=1, want_loo=True)
+    for pr, r in zip(probs, res):
+        m = G.GPModel(pr["Y"], pr["X"], pr.get("pop"))
+        one = m.fit_rprop(pr.get("initparst", batch.default_initparst(np.atleast_2d(pr["X"].T).T.shape[1])), 1.0,
+                          None, None)
+        assert r["status"] == 0 and one["iter"] == r["iter"]
+        assert np.max(np.abs(one["pars"] - r["pars"]) / np.maximum(1, np.abs(one["pars"]))) <= 1e-9
+        assert rel(r["nllpost"], one["nllpost"]) <= 1e-11
+        np.testing.assert_allclose(r["loo_mean"], m.vector(_lib.VEC_LOO_MEAN), atol=1e-9)
+        m.close()
+
+
+def test_leaveout_blocks_on_device_vs_bruteforce(gpu_lib):
+    """lto / loo with wide exclusion windows (blocks of Sigma^-1 up to ~60 rows, solved by
+    leaveout_blocks_kernel) against the oracle's brute-force refactorisation loops
+    (reference R/GPfunctions.R:1056-1104, :1140-1194)."""
+    Y, X, pop = synth.hierarchical_thetalog(npop=4, n=40, E=2, seed0=90)
+    N = len(Y)
+    time = np.concatenate([np.arange(np.sum(pop == k)) for k in range(4)]).astype(float)
+    parst = np.array([np.log(0.4), np.log(0.05), -3.0, 0.3, 0.2])
+    m = G.GPModel(Y, X, pop)
+    full = m.likegrad(parst, 1.0, None, None, returngradonly=False)
+    D = [O.distance(X[:, i]) for i in range(2)]
+    ref = O.getlikegrad(parst, Y, X, pop, 1.0, np.full(4, np.nan), None, None, D, False)
+    assert rel(full["nllpost"], ref["nllpost"]) <= TOL_NLL
+    primary = np.ones(N, dtype=bool)
+    sigma2, ve = ref["pars"][3], ref["pars"][2]
+    Cd, Sigma = ref["covm"]["Cd"], ref["covm"]["Sigma"]
+    for method, r in [("lto", 0), ("lto", 7), ("loo", 3), ("loo", 12)]:
+        if method == "lto":
+            gm, gv, _ = m.predict_lto(time, r, None)
+            om, ov, _ = O.predict_lto_core(sigma2, Cd, Sigma, Y, time, primary, r)
+        else:
+            gm, gv, _ = m.predict_loo(r, time, None)
+            om, ov, _ = O.predict_loo_core(sigma2, Cd, Sigma, Y, pop, time, primary, r)
+        ok = ~np.isnan(om)
+        assert np.array_equal(np.isnan(gm), np.isnan(om))
+        assert np.max(np.abs(gm[ok] - om[ok])) <= 1e-9
+        assert np.max(np.abs(np.sqrt(gv[ok] + ve) - np.sqrt(ov[ok] + ve))) <= 1e-7
+    m.close()

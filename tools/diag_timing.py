@@ -2,7 +2,7 @@ import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from gpedm_b200 import _lib
-_lib.LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'build', 'libgpedm_timing.so')
+_lib.LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'build', os.environ.get('GPEDM_TIMING_LIB', 'libgpedm_timing.so'))
 import gpedm_b200 as G
 from gpedm_b200 import synth
 from gpedm_b200.batch import default_initparst
