@@ -62,12 +62,23 @@ class FitDesc(C.Structure):
                 ("insamp_mean", C.POINTER(C.c_double)), ("insamp_var", C.POINTER(C.c_double))]
 
 
+class FitStats(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("n", "obs_mean", "ss_total", "ss_insample", "ss_loo", "R2_insample",
+                                          "R2_loo", "rmse_insample", "rmse_loo")]
+
+    def to_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+SCALE_CODES = {"none": 0, "global": 1, "local": 2}
+
 # every symbol include/gpedm.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "gpedm_abi_version", "gpedm_last_error", "gpedm_device_count", "gpedm_default_rprop_options",
     "gpedm_create", "gpedm_set_data", "gpedm_destroy", "gpedm_n", "gpedm_likegrad", "gpedm_fit_rprop", "gpedm_get_vector",
     "gpedm_get_matrix", "gpedm_getcov", "gpedm_covinv", "gpedm_predict_new", "gpedm_predict_loo", "gpedm_predict_lto",
-    "gpedm_predict_sequential", "gpedm_fit_batch", "gpedm_last_phase_ms", "gpedm_launch_count",
+    "gpedm_predict_sequential", "gpedm_fit_batch", "gpedm_create_lagged", "gpedm_lagged_info",
+    "gpedm_get_fit_stats", "gpedm_fit_grid", "gpedm_last_phase_ms", "gpedm_launch_count",
     "gpedm_fp64_peak", "gpedm_bench_evals",
 ]
 
@@ -126,6 +137,13 @@ def lib():
     L.gpedm_predict_sequential.argtypes = [C.c_void_p, dp, dp, dp]
     L.gpedm_fit_batch.argtypes = [C.c_int32, C.POINTER(FitDesc), C.c_int32, ip, C.POINTER(RpropOptions),
                                   C.POINTER(Result)]
+    i64p = C.POINTER(C.c_int64)
+    L.gpedm_create_lagged.argtypes = [C.c_int, C.c_int64, dp, ip, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp,
+                                      C.POINTER(C.c_void_p)]
+    L.gpedm_lagged_info.argtypes = [C.c_void_p, i64p, dp, dp, dp, dp, ip]
+    L.gpedm_get_fit_stats.argtypes = [C.c_void_p, C.POINTER(FitStats)]
+    L.gpedm_fit_grid.argtypes = [C.c_int64, dp, ip, C.c_int32, C.c_int32, ip, ip, C.c_int32, C.c_double, C.c_int32, ip,
+                                 C.POINTER(RpropOptions), C.POINTER(Result), C.POINTER(FitStats)]
     L.gpedm_last_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.gpedm_launch_count.argtypes = [C.c_void_p]
     L.gpedm_launch_count.restype = C.c_int64

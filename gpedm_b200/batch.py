@@ -93,9 +93,36 @@ def grid_problems(y, Es, taus, pop=None, scaling="global"):
     return problems, meta
 
 
-def fit_grid(y, Es, taus, pop=None, ngpus=1, devices=None):
+def fit_grid(y, Es, taus, pop=None, ngpus=1, devices=None, scaling="global", modeprior=1.0):
     """fitGP(y, E, tau, predictmethod="loo") over an E x tau grid, returning one dict per cell with
-    the fitted modes and the leave-one-out R2 (the model-selection criterion of choosingE.Rmd)."""
+    the fitted modes and the leave-one-out R2 (the model-selection criterion of choosingE.Rmd).
+    One call into `gpedm_fit_grid`: the raw series is uploaded once per GPU and every cell's lags,
+    scaling and complete-row selection are built on the device."""
+    from ._lib import SCALE_CODES, FitStats
+    y = f64(y).ravel()
+    T = len(y)
+    cells = [(int(E), int(tau)) for E in Es for tau in taus]
+    n = len(cells)
+    Ea = np.ascontiguousarray([c[0] for c in cells], dtype=np.int32)
+    ta = np.ascontiguousarray([c[1] for c in cells], dtype=np.int32)
+    codes, levels = pop_codes(np.ones(T, dtype=np.int64) if pop is None else pop)
+    results = (Result * n)()
+    stats = (FitStats * n)()
+    dev = None if devices is None else np.ascontiguousarray(np.asarray(devices, dtype=np.int32))
+    check(lib().gpedm_fit_grid(T, dptr(y), iptr(codes), len(levels), n, iptr(Ea), iptr(ta), SCALE_CODES[scaling],
+                               float(modeprior), int(ngpus), iptr(dev), None, results, stats))
+    out = []
+    for (E, tau), r, st in zip(cells, results, stats):
+        r = r.to_dict()
+        out.append(dict(E=E, tau=tau, pars=r["pars"], iter=r["iter"], nevals=r["nevals"], ln_post=-r["nllpost"],
+                        lnL_LOO=r["lnL_LOO"], df=r["df"], R2_insample=st.R2_insample, R2_loo=st.R2_loo,
+                        rmse_insample=st.rmse_insample, rmse_loo=st.rmse_loo, N=int(st.n), status=r["status"]))
+    return out
+
+
+def fit_grid_hostprep(y, Es, taus, pop=None, ngpus=1, devices=None):
+    """Same grid with the training sets prepared on the host (`grid_problems`) and fitted through
+    `gpedm_fit_batch` - the cross-check of the on-device preparation."""
     problems, meta = grid_problems(y, Es, taus, pop)
     res = fit_batch(problems, ngpus=ngpus, devices=devices, want_loo=True)
     out = []

@@ -87,6 +87,43 @@ class GPModel:
         check(lib().gpedm_create(device, self.N, self.d, self.np_, dptr(X), dptr(Y), iptr(self.codes),
                                  dptr(self.rhomat), C.byref(self._h)))
 
+    @classmethod
+    def from_series(cls, y, E, tau=1, pop=None, scaling="global", rhomatrix=None, rhomatrix_names=None, device=0):
+        """Training set of fitGP(y, E, tau, scaling) prepared ON THE DEVICE from the raw series
+        (lags within population, centring/scaling, incomplete-row removal; reference
+        R/GPfunctions.R:1824-1857, :359-405, :445-451) - `gpedm_create_lagged`."""
+        from ._lib import SCALE_CODES
+        y = f64(y).ravel()
+        T = len(y)
+        self = cls.__new__(cls)
+        codes, levels = pop_codes(np.ones(T, dtype=np.int64) if pop is None else pop)
+        self.levels, self.np_ = levels, len(levels)
+        self.rhomat = _rhomat_in_code_order(rhomatrix, rhomatrix_names, levels)
+        self.device = device
+        self._h = C.c_void_p()
+        check(lib().gpedm_create_lagged(device, T, dptr(y), iptr(codes), self.np_, int(E), int(tau),
+                                        SCALE_CODES[scaling], dptr(self.rhomat), C.byref(self._h)))
+        self.N, self.d = int(lib().gpedm_n(self._h)), int(E)
+        G = self.np_ if scaling == "local" else 1
+        rows = np.empty(self.N, dtype=np.int64)
+        self.center = np.empty((self.d + 1, G), order="F")
+        self.scale = np.empty((self.d + 1, G), order="F")
+        self.Y = np.empty(self.N)
+        self.X = np.empty((self.N, self.d), order="F")
+        self.codes = np.empty(self.N, dtype=np.int32)
+        check(lib().gpedm_lagged_info(self._h, rows.ctypes.data_as(C.POINTER(C.c_int64)), dptr(self.center),
+                                      dptr(self.scale), dptr(self.Y), dptr(self.X), iptr(self.codes)))
+        self.rows = rows
+        return self
+
+    def fit_stats(self):
+        """In-sample / leave-one-out R2 and rmse in the original units of y, reduced on the device
+        (getR2, reference R/GPfunctions.R:1366-1370)."""
+        from ._lib import FitStats
+        st = FitStats()
+        check(lib().gpedm_get_fit_stats(self._h, C.byref(st)))
+        return st.to_dict()
+
     def set_data(self, Y, X, codes=None):
         """Re-upload host Y / X (/ population codes) into the resident handle (same shapes)."""
         Y = f64(Y).ravel()

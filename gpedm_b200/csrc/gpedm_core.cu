@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -23,6 +24,7 @@
 #include "kernels.cuh"
 #include "diag_block.cuh"
 #include "small_fit.cuh"
+#include "lag_prep.cuh"
 
 using namespace gpedm;
 
@@ -62,6 +64,7 @@ struct gpedm_fit_s {
   int* dpop = nullptr;
   double *bufA = nullptr, *bufB = nullptr, *bufC = nullptr;
   EvalParams* dparams = nullptr;
+  void* pinned = nullptr;         // one recycled pinned block holding hparams | hscal | hinfo
   EvalParams* hparams = nullptr;  // pinned
   double *dz = nullptr, *da = nullptr, *ddiagS = nullptr, *dpart = nullptr, *dlogdet = nullptr,
          *dtracepart = nullptr, *dscal = nullptr;
@@ -87,6 +90,10 @@ struct gpedm_fit_s {
   double cur_ve = 0, cur_sigma2 = 0, cur_rho = 0;
   std::vector<double> hY;  // host copy of Y (N)
   std::vector<int> hpop;
+  // set by gpedm_create_lagged: column statistics (E+1) x G used for the scaling, kept rows
+  double *dcenter = nullptr, *dscale = nullptr;
+  int sc_mode = 0, sc_groups = 1;
+  std::vector<int> rows;  // original row of each training row
 };
 
 static const int NSCAL = 8 + MAXD + 3;
@@ -173,47 +180,79 @@ extern "C" void gpedm_default_rprop_options(gpedm_rprop_options* o) {
   o->tol_df = 1e-7;
 }
 
+// Pinned host blocks (parameters up, scalars / status down) are recycled through a process-wide
+// free list: cudaMallocHost / cudaFreeHost cost up to 200 ms each (measured) when handles are created
+// and destroyed per fit, as a model-selection grid does.  Blocks are a few KB and never returned.
+static const size_t PINNED_BLOCK = 4096;
+static_assert(sizeof(EvalParams) + (8 + MAXD + 3) * 8 + 16 <= PINNED_BLOCK, "pinned block too small");
+static std::mutex g_pinned_mutex;
+static std::vector<void*> g_pinned_free;
+static void* pinned_acquire() {
+  {
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    if (!g_pinned_free.empty()) {
+      void* p = g_pinned_free.back();
+      g_pinned_free.pop_back();
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, PINNED_BLOCK, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  return p;
+}
+static void pinned_release(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_pinned_mutex);
+  g_pinned_free.push_back(p);
+}
+
 static void free_handle(gpedm_fit_s* h) {
   if (!h) return;
+  static const bool trace = getenv("GPEDM_TRACE_FREE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now();
   cudaSetDevice(h->device);
   if (h->stream) {
     cudaStreamSynchronize(h->stream);
     if (h->aux) cudaStreamSynchronize(h->aux);
     void* bufs[] = {h->dX, h->dY, h->drhotab, h->dpop, h->bufA, h->bufB, h->bufC, h->dparams, h->dz, h->da,
-                    h->ddiagS, h->dpart, h->dlogdet, h->dtracepart, h->dscal, h->dinfo};
+                    h->ddiagS, h->dpart, h->dlogdet, h->dtracepart, h->dscal, h->dinfo, h->dcenter, h->dscale};
     for (void* b : bufs)
       if (b) cudaFreeAsync(b, h->stream);
     cudaStreamSynchronize(h->stream);
   }
-  if (h->hparams) cudaFreeHost(h->hparams);
-  if (h->hscal) cudaFreeHost(h->hscal);
-  if (h->hinfo) cudaFreeHost(h->hinfo);
+  double t1 = now();
+  pinned_release(h->pinned);
+  double t2 = now();
   for (auto& g : h->graph_exec)
     if (g) cudaGraphExecDestroy(g);
+  double t3 = now();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : h->evPanel) cudaEventDestroy(e);
   for (auto& e : h->evTrail) cudaEventDestroy(e);
   for (auto& e : h->evCol) cudaEventDestroy(e);
   if (h->evFill) cudaEventDestroy(h->evFill);
-  if (h->fill) cudaStreamDestroy(h->fill);
   if (h->evFork) cudaEventDestroy(h->evFork);
   if (h->evJoin) cudaEventDestroy(h->evJoin);
+  double t4 = now();
+  if (h->fill) cudaStreamDestroy(h->fill);
   if (h->aux) cudaStreamDestroy(h->aux);
   if (h->stream) cudaStreamDestroy(h->stream);
+  double t5 = now();
+  if (trace)
+    fprintf(stderr, "[gpedm free] device bufs %.2f ms, pinned %.2f, graphs %.2f, events %.2f, streams %.2f\n", t1 - t0,
+            t2 - t1, t3 - t2, t4 - t3, t5 - t4);
   delete h;
 }
 
-static int gpedm_create_impl(int device, int64_t N, int32_t d, int32_t np, const double* X, const double* Y,
-                            const int32_t* pop, const double* rhomat, gpedm_handle* out) {
-  if (!out) return set_err(GPEDM_ERR_ARG, "out handle is NULL");
+// Allocate a handle for an N x d problem with np populations: device buffers, streams, events.
+// The training data (dX, dY, dpop, drhotab, hY, hpop, single_pop) are filled by the caller.
+static int alloc_handle(int device, int64_t N, int32_t d, int32_t np, bool has_rhomat, gpedm_handle* out) {
   *out = nullptr;
   if (N < 1 || N > (1 << 20)) return set_err(GPEDM_ERR_ARG, "N=%lld out of range", (long long)N);
   if (d < 1 || d > GPEDM_MAX_D) return set_err(GPEDM_ERR_ARG, "d=%d out of range 1..%d", d, GPEDM_MAX_D);
   if (np < 1) return set_err(GPEDM_ERR_ARG, "np=%d must be >= 1", np);
-  if (!X || !Y || !pop) return set_err(GPEDM_ERR_ARG, "X, Y and pop must be non-NULL");
-  for (int64_t i = 0; i < N; ++i)
-    if (pop[i] < 0 || pop[i] >= np) return set_err(GPEDM_ERR_ARG, "pop[%lld]=%d outside 0..np-1", (long long)i, pop[i]);
   int ndev = gpedm_device_count();
   if (ndev == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available (libgpedm_b200 has no CPU fallback)");
   if (device < 0 || device >= ndev) return set_err(GPEDM_ERR_ARG, "device %d out of range (have %d)", device, ndev);
@@ -229,12 +268,7 @@ static int gpedm_create_impl(int device, int64_t N, int32_t d, int32_t np, const
   h->d = d;
   h->np = np;
   h->p = d + 3;
-  h->has_rhomat = rhomat != nullptr;
-  h->hY.assign(Y, Y + N);
-  h->hpop.assign(pop, pop + N);
-  h->single_pop = true;
-  for (int64_t i = 1; i < N; ++i)
-    if (pop[i] != pop[0]) h->single_pop = false;
+  h->has_rhomat = has_rhomat;
   const size_t Np = h->Np, mat = Np * Np * sizeof(double);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     free_handle(h);
@@ -252,7 +286,7 @@ static int gpedm_create_impl(int device, int64_t N, int32_t d, int32_t np, const
   ALLOC(h->dX, (size_t)N * d * 8);
   ALLOC(h->dY, Np * 8);
   ALLOC(h->dpop, (size_t)N * 4);
-  if (rhomat) ALLOC(h->drhotab, (size_t)np * np * 8);
+  if (has_rhomat) ALLOC(h->drhotab, (size_t)np * np * 8);
   ALLOC(h->bufA, mat);
   ALLOC(h->bufB, mat);
   ALLOC(h->bufC, mat);
@@ -267,9 +301,15 @@ static int gpedm_create_impl(int device, int64_t N, int32_t d, int32_t np, const
   ALLOC(h->dinfo, 4);
   h->num_sms = (device < 64 && g_num_sms[device] > 0) ? g_num_sms[device] : 148;
 #undef ALLOC
-  cudaError_t e = cudaMallocHost((void**)&h->hparams, sizeof(EvalParams));
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hscal, NSCAL * 8);
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hinfo, 4);
+  h->pinned = pinned_acquire();
+  if (!h->pinned) {
+    free_handle(h);
+    return set_err(GPEDM_ERR_CUDA, "pinned host allocation failed");
+  }
+  h->hparams = (EvalParams*)h->pinned;
+  h->hscal = (double*)((char*)h->pinned + ((sizeof(EvalParams) + 15) / 16) * 16);
+  h->hinfo = (int*)(h->hscal + NSCAL);
+  cudaError_t e = cudaMemsetAsync(h->dY, 0, Np * 8, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e == cudaSuccess) {
     int lo = 0, hi = 0;
@@ -290,8 +330,32 @@ static int gpedm_create_impl(int device, int64_t N, int32_t d, int32_t np, const
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evTrail[i], cudaEventDisableTiming);
   }
   for (int i = 0; i <= GPEDM_NPHASE && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
-  if (e == cudaSuccess) e = cudaMemcpy(h->dX, X, (size_t)N * d * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemset(h->dY, 0, Np * 8);
+  if (e != cudaSuccess) {
+    free_handle(h);
+    return set_err(GPEDM_ERR_CUDA, "handle setup failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return 0;
+}
+
+static int gpedm_create_impl(int device, int64_t N, int32_t d, int32_t np, const double* X, const double* Y,
+                            const int32_t* pop, const double* rhomat, gpedm_handle* out) {
+  if (!out) return set_err(GPEDM_ERR_ARG, "out handle is NULL");
+  *out = nullptr;
+  if (N < 1 || N > (1 << 20)) return set_err(GPEDM_ERR_ARG, "N=%lld out of range", (long long)N);
+  if (np < 1) return set_err(GPEDM_ERR_ARG, "np=%d must be >= 1", np);
+  if (!X || !Y || !pop) return set_err(GPEDM_ERR_ARG, "X, Y and pop must be non-NULL");
+  for (int64_t i = 0; i < N; ++i)
+    if (pop[i] < 0 || pop[i] >= np) return set_err(GPEDM_ERR_ARG, "pop[%lld]=%d outside 0..np-1", (long long)i, pop[i]);
+  gpedm_fit_s* h = nullptr;
+  int rc = alloc_handle(device, N, d, np, rhomat != nullptr, &h);
+  if (rc) return rc;
+  h->hY.assign(Y, Y + N);
+  h->hpop.assign(pop, pop + N);
+  h->single_pop = true;
+  for (int64_t i = 1; i < N; ++i)
+    if (pop[i] != pop[0]) h->single_pop = false;
+  cudaError_t e = cudaMemcpy(h->dX, X, (size_t)N * d * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->dY, Y, (size_t)N * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->dpop, pop, (size_t)N * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && rhomat) e = cudaMemcpy(h->drhotab, rhomat, (size_t)np * np * 8, cudaMemcpyHostToDevice);
@@ -1052,6 +1116,25 @@ struct DevBuf {
   ~DevBuf() { cudaFree(p); }
   cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
 };
+// Stream-ordered allocation from the device's (cached) default pool: no implicit device
+// synchronisation, unlike cudaMalloc / cudaFree.  The stream must outlive the buffer.
+struct PoolBuf {
+  void* p = nullptr;
+  cudaStream_t st = nullptr;
+  explicit PoolBuf(cudaStream_t s = nullptr) : st(s) {}
+  ~PoolBuf() { if (p) cudaFreeAsync(p, st); }
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, std::max<size_t>(bytes, 16), st); }
+};
+struct StreamGuard {
+  cudaStream_t s = nullptr;
+  cudaError_t create() { return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); }
+  ~StreamGuard() {
+    if (s) {
+      cudaStreamSynchronize(s);
+      cudaStreamDestroy(s);
+    }
+  }
+};
 struct PinnedBuf {
   void* p = nullptr;
   ~PinnedBuf() { if (p) cudaFreeHost(p); }
@@ -1148,7 +1231,8 @@ static int leaveout_core(gpedm_fit_s* h, const std::vector<int>& members, const 
     long long nbk = goff[g + 1] - goff[g];
     boff[g + 1] = boff[g] + (nbk > 1 ? nbk * nbk : 0);
   }
-  DevBuf didx, dgoff, dboff, dwork, du, ddinv, dbad, dfocal, dfg, dg;
+  PoolBuf didx(h->stream), dgoff(h->stream), dboff(h->stream), dwork(h->stream), du(h->stream), ddinv(h->stream),
+      dbad(h->stream), dfocal(h->stream), dfg(h->stream), dg(h->stream);
   cudaError_t e = didx.alloc(nm * 4);
   if (e == cudaSuccess) e = dgoff.alloc((size_t)(ng + 1) * 4);
   if (e == cudaSuccess) e = dboff.alloc((size_t)(ng + 1) * 8);
@@ -1659,7 +1743,83 @@ struct BatchRecord {
   int32_t fit_index;
   int32_t valid;
   gpedm_result res;
+  gpedm_fit_stats st;  // filled by gpedm_fit_grid only
 };
+
+// Every GPU ends up with every fit's fixed-width record.  One GPU: a copy.  Several: ONE NCCL
+// all-gather (single process, one communicator per GPU); every GPU contributes `slab` records
+// (padded with valid=0).  No other collective exists on the path.
+static int exchange_records(const std::vector<int>& devs, const std::vector<std::vector<BatchRecord>>& per_gpu,
+                            int nfits, gpedm_result* results, gpedm_fit_stats* stats) {
+  const int ngpus = (int)devs.size();
+  if (ngpus == 1) {
+    for (auto& r : per_gpu[0]) {
+      results[r.fit_index] = r.res;
+      if (stats) stats[r.fit_index] = r.st;
+    }
+    return 0;
+  }
+  NcclApi nc;
+  if (!load_nccl(nc)) return set_err(GPEDM_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  size_t slab = 0;
+  for (int g = 0; g < ngpus; ++g) slab = std::max(slab, per_gpu[g].size());
+  if (slab == 0) slab = 1;
+  const size_t slab_bytes = slab * sizeof(BatchRecord);
+  std::vector<void*> comms(ngpus, nullptr);
+  int nrc = nc.CommInitAll(comms.data(), ngpus, devs.data());
+  if (nrc != 0)
+    return set_err(GPEDM_ERR_NCCL, "ncclCommInitAll failed: %s", nc.GetErrorString ? nc.GetErrorString(nrc) : "?");
+  std::vector<char*> dsend(ngpus, nullptr), drecv(ngpus, nullptr);
+  std::vector<cudaStream_t> sts(ngpus, nullptr);
+  cudaError_t e = cudaSuccess;
+  for (int g = 0; g < ngpus && e == cudaSuccess; ++g) {
+    e = cudaSetDevice(devs[g]);
+    if (e == cudaSuccess) e = cudaStreamCreate(&sts[g]);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dsend[g], slab_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&drecv[g], slab_bytes * ngpus);
+    std::vector<BatchRecord> pad(slab);
+    memset(pad.data(), 0, slab_bytes);
+    for (size_t q = 0; q < per_gpu[g].size(); ++q) pad[q] = per_gpu[g][q];
+    if (e == cudaSuccess) e = cudaMemcpy(dsend[g], pad.data(), slab_bytes, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) {
+    nc.GroupStart();
+    for (int g = 0; g < ngpus; ++g) {
+      cudaSetDevice(devs[g]);
+      nrc = nc.AllGather(dsend[g], drecv[g], slab_bytes, /*ncclChar*/ 0, comms[g], sts[g]);
+      if (nrc != 0) break;
+    }
+    int nrc2 = nc.GroupEnd();
+    if (nrc == 0) nrc = nrc2;
+    for (int g = 0; g < ngpus && e == cudaSuccess; ++g) {
+      cudaSetDevice(devs[g]);
+      e = cudaStreamSynchronize(sts[g]);
+    }
+  }
+  std::vector<BatchRecord> all(slab * ngpus);
+  if (e == cudaSuccess && nrc == 0) {
+    cudaSetDevice(devs[0]);
+    e = cudaMemcpy(all.data(), drecv[0], slab_bytes * ngpus, cudaMemcpyDeviceToHost);
+  }
+  for (int g = 0; g < ngpus; ++g) {
+    cudaSetDevice(devs[g]);
+    cudaFree(dsend[g]);
+    cudaFree(drecv[g]);
+    if (sts[g]) cudaStreamDestroy(sts[g]);
+    if (comms[g]) nc.CommDestroy(comms[g]);
+  }
+  if (nrc != 0) return set_err(GPEDM_ERR_NCCL, "ncclAllGather failed: %s", nc.GetErrorString ? nc.GetErrorString(nrc) : "?");
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "batch gather failed: %s", cudaGetErrorString(e));
+  int got = 0;
+  for (auto& r : all)
+    if (r.valid && r.fit_index >= 0 && r.fit_index < nfits) {
+      results[r.fit_index] = r.res;
+      if (stats) stats[r.fit_index] = r.st;
+      ++got;
+    }
+  if (got != nfits) return set_err(GPEDM_ERR_STATE, "batch gather returned %d of %d records", got, nfits);
+  return 0;
+}
 
 static int run_one_fit(int device, const gpedm_fit_desc& ds, const gpedm_rprop_options* opts, gpedm_result* res) {
   gpedm_handle h = nullptr;
@@ -1783,69 +1943,9 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
     if (got != (size_t)nfits) return set_err(GPEDM_ERR_STATE, "batch produced %zu of %d records", got, nfits);
   }
 
-  if (ngpus == 1) {
-    for (auto& r : per_gpu[0]) results[r.fit_index] = r.res;
-  } else {
-    // Exchange the fixed-width records with ONE NCCL all-gather (single process, one
-    // communicator per GPU).  Every GPU contributes `slab` records (padded with valid=0).
-    NcclApi nc;
-    if (!load_nccl(nc)) return set_err(GPEDM_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
-    size_t slab = 0;
-    for (int g = 0; g < ngpus; ++g) slab = std::max(slab, per_gpu[g].size());
-    if (slab == 0) slab = 1;
-    const size_t slab_bytes = slab * sizeof(BatchRecord);
-    std::vector<void*> comms(ngpus, nullptr);
-    int nrc = nc.CommInitAll(comms.data(), ngpus, devs.data());
-    if (nrc != 0)
-      return set_err(GPEDM_ERR_NCCL, "ncclCommInitAll failed: %s", nc.GetErrorString ? nc.GetErrorString(nrc) : "?");
-    std::vector<char*> dsend(ngpus, nullptr), drecv(ngpus, nullptr);
-    std::vector<cudaStream_t> sts(ngpus, nullptr);
-    cudaError_t e = cudaSuccess;
-    for (int g = 0; g < ngpus && e == cudaSuccess; ++g) {
-      e = cudaSetDevice(devs[g]);
-      if (e == cudaSuccess) e = cudaStreamCreate(&sts[g]);
-      if (e == cudaSuccess) e = cudaMalloc((void**)&dsend[g], slab_bytes);
-      if (e == cudaSuccess) e = cudaMalloc((void**)&drecv[g], slab_bytes * ngpus);
-      std::vector<BatchRecord> pad(slab);
-      memset(pad.data(), 0, slab_bytes);
-      for (size_t q = 0; q < per_gpu[g].size(); ++q) pad[q] = per_gpu[g][q];
-      if (e == cudaSuccess) e = cudaMemcpy(dsend[g], pad.data(), slab_bytes, cudaMemcpyHostToDevice);
-    }
-    if (e == cudaSuccess) {
-      nc.GroupStart();
-      for (int g = 0; g < ngpus; ++g) {
-        cudaSetDevice(devs[g]);
-        nrc = nc.AllGather(dsend[g], drecv[g], slab_bytes, /*ncclChar*/ 0, comms[g], sts[g]);
-        if (nrc != 0) break;
-      }
-      int nrc2 = nc.GroupEnd();
-      if (nrc == 0) nrc = nrc2;
-      for (int g = 0; g < ngpus && e == cudaSuccess; ++g) {
-        cudaSetDevice(devs[g]);
-        e = cudaStreamSynchronize(sts[g]);
-      }
-    }
-    std::vector<BatchRecord> all(slab * ngpus);
-    if (e == cudaSuccess && nrc == 0) {
-      cudaSetDevice(devs[0]);
-      e = cudaMemcpy(all.data(), drecv[0], slab_bytes * ngpus, cudaMemcpyDeviceToHost);
-    }
-    for (int g = 0; g < ngpus; ++g) {
-      cudaSetDevice(devs[g]);
-      cudaFree(dsend[g]);
-      cudaFree(drecv[g]);
-      if (sts[g]) cudaStreamDestroy(sts[g]);
-      if (comms[g]) nc.CommDestroy(comms[g]);
-    }
-    if (nrc != 0) return set_err(GPEDM_ERR_NCCL, "ncclAllGather failed: %s", nc.GetErrorString ? nc.GetErrorString(nrc) : "?");
-    if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "batch gather failed: %s", cudaGetErrorString(e));
-    int got = 0;
-    for (auto& r : all)
-      if (r.valid && r.fit_index >= 0 && r.fit_index < nfits) {
-        results[r.fit_index] = r.res;
-        ++got;
-      }
-    if (got != nfits) return set_err(GPEDM_ERR_STATE, "batch gather returned %d of %d records", got, nfits);
+  {
+    int rc = exchange_records(devs, per_gpu, nfits, results, nullptr);
+    if (rc) return rc;
   }
   for (int g = 0; g < ngpus; ++g)
     if (!errs[g].empty()) {
@@ -1857,6 +1957,284 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
         }
       return set_err(first_bad ? first_bad : GPEDM_ERR_STATE, "at least one fit failed: %s", errs[g].c_str());
     }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- lagged series / grids
+// Raw series resident on one device, shared by every grid cell fitted there.
+struct LagSeries {
+  int device = 0;
+  int T = 0, np = 1;
+  StreamGuard sg;  // declared before the buffers: destroyed after them
+  PoolBuf y, pop, rank, poprows, popoff;
+  std::vector<int> hpop;
+};
+
+static int upload_series(int device, int64_t T, const double* y, const int32_t* pop, int32_t np, LagSeries& S) {
+  if (!y || T < 2 || T > (1 << 24)) return set_err(GPEDM_ERR_ARG, "bad series (T=%lld)", (long long)T);
+  if (np < 1) return set_err(GPEDM_ERR_ARG, "np=%d must be >= 1", np);
+  S.device = device;
+  S.T = (int)T;
+  S.np = np;
+  S.hpop.assign((size_t)T, 0);
+  if (pop)
+    for (int64_t t = 0; t < T; ++t) {
+      if (pop[t] < 0 || pop[t] >= np) return set_err(GPEDM_ERR_ARG, "pop[%lld]=%d outside 0..np-1", (long long)t, pop[t]);
+      S.hpop[t] = pop[t];
+    }
+  // index bookkeeping only (no arithmetic on the data): position of each row inside its population
+  std::vector<int> rank((size_t)T), popoff(np + 1, 0), poprows((size_t)T), fillp(np, 0);
+  for (int64_t t = 0; t < T; ++t) popoff[S.hpop[t] + 1]++;
+  for (int g = 0; g < np; ++g) popoff[g + 1] += popoff[g];
+  for (int64_t t = 0; t < T; ++t) {
+    const int g = S.hpop[t];
+    rank[t] = fillp[g];
+    poprows[popoff[g] + fillp[g]] = (int)t;
+    fillp[g]++;
+  }
+  CU(cudaSetDevice(device));
+  CU(S.sg.create());
+  S.y.st = S.pop.st = S.rank.st = S.poprows.st = S.popoff.st = S.sg.s;
+  cudaError_t e = S.y.alloc((size_t)T * 8);
+  if (e == cudaSuccess) e = S.pop.alloc((size_t)T * 4);
+  if (e == cudaSuccess) e = S.rank.alloc((size_t)T * 4);
+  if (e == cudaSuccess) e = S.poprows.alloc((size_t)T * 4);
+  if (e == cudaSuccess) e = S.popoff.alloc((size_t)(np + 1) * 4);
+  cudaStream_t st = S.sg.s;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.y.p, y, (size_t)T * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.pop.p, S.hpop.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.rank.p, rank.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.poprows.p, poprows.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.popoff.p, popoff.data(), (size_t)(np + 1) * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "series upload failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// Build the training set of fitGP(y, E, tau, scaling) from the resident series into a new handle.
+static int create_from_series(const LagSeries& S, int32_t E, int32_t tau, int32_t scaling, const double* rhomat,
+                              gpedm_handle* out) {
+  *out = nullptr;
+  if (E < 1 || E > GPEDM_MAX_D) return set_err(GPEDM_ERR_ARG, "E=%d out of range 1..%d", E, GPEDM_MAX_D);
+  if (tau < 1) return set_err(GPEDM_ERR_ARG, "tau=%d must be >= 1", tau);
+  if (scaling < GPEDM_SCALE_NONE || scaling > GPEDM_SCALE_LOCAL) return set_err(GPEDM_ERR_ARG, "unknown scaling %d", scaling);
+  CU(cudaSetDevice(S.device));
+  const int G = scaling == GPEDM_SCALE_LOCAL ? S.np : 1;
+  const size_t nstat = (size_t)(E + 1) * G;
+  StreamGuard sg;
+  CU(sg.create());
+  cudaStream_t st = sg.s;
+  PoolBuf dcenter(st), dscale(st), drowmap(st), dcount(st);
+  cudaError_t e = dcenter.alloc(nstat * 8);
+  if (e == cudaSuccess) e = dscale.alloc(nstat * 8);
+  if (e == cudaSuccess) e = drowmap.alloc((size_t)S.T * 4);
+  if (e == cudaSuccess) e = dcount.alloc(4);
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "lag preparation failed: %s", cudaGetErrorString(e));
+  LagPrep P;
+  P.y = (const double*)S.y.p;
+  P.pop = (const int*)S.pop.p;
+  P.rank = (const int*)S.rank.p;
+  P.poprows = (const int*)S.poprows.p;
+  P.popoff = (const int*)S.popoff.p;
+  P.center = (double*)dcenter.p;
+  P.scale = (double*)dscale.p;
+  P.T = S.T;
+  P.E = E;
+  P.tau = tau;
+  P.np = S.np;
+  P.G = G;
+  P.mode = scaling;
+  int N = 0;
+  lag_stats_kernel<<<dim3(E + 1, G), 256, 0, st>>>(P);
+  lag_compact_kernel<<<1, 1024, 0, st>>>(P, (int*)drowmap.p, (int*)dcount.p);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&N, dcount.p, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "lag preparation failed: %s", cudaGetErrorString(e));
+  if (N < 1) return set_err(GPEDM_ERR_ARG, "no complete rows for E=%d tau=%d (series length %d)", E, tau, S.T);
+  gpedm_fit_s* h = nullptr;
+  int rc = alloc_handle(S.device, N, E, S.np, rhomat != nullptr, &h);
+  if (rc) return rc;
+  lag_fill_kernel<<<dim3(ceil_div(N, 256), E + 1), 256, 0, st>>>(P, (const int*)drowmap.p, N, h->dY, h->dX, h->dpop);
+  h->launches += 3;
+  h->hY.resize(N);
+  h->hpop.resize(N);
+  h->rows.resize(N);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->hY.data(), h->dY, (size_t)N * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->hpop.data(), h->dpop, (size_t)N * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->rows.data(), drowmap.p, (size_t)N * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rhomat) e = cudaMemcpyAsync(h->drhotab, rhomat, (size_t)S.np * S.np * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    free_handle(h);
+    return set_err(GPEDM_ERR_CUDA, "lag preparation failed: %s", cudaGetErrorString(e));
+  }
+  h->single_pop = true;
+  for (int i = 1; i < N; ++i)
+    if (h->hpop[i] != h->hpop[0]) h->single_pop = false;
+  // the handle keeps the column statistics (for gpedm_get_fit_stats / gpedm_lagged_info)
+  e = cudaMallocAsync((void**)&h->dcenter, nstat * 8, h->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&h->dscale, nstat * 8, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->dcenter, dcenter.p, nstat * 8, cudaMemcpyDeviceToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->dscale, dscale.p, nstat * 8, cudaMemcpyDeviceToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    free_handle(h);
+    return set_err(GPEDM_ERR_CUDA, "lag preparation failed: %s", cudaGetErrorString(e));
+  }
+  h->sc_mode = scaling;
+  h->sc_groups = G;
+  *out = h;
+  return 0;
+}
+
+static int gpedm_create_lagged_impl(int device, int64_t T, const double* y, const int32_t* pop, int32_t np, int32_t E,
+                                    int32_t tau, int32_t scaling, const double* rhomat, gpedm_handle* out) {
+  if (!out) return set_err(GPEDM_ERR_ARG, "out handle is NULL");
+  *out = nullptr;
+  int ndev = gpedm_device_count();
+  if (ndev == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available (libgpedm_b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(GPEDM_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+  LagSeries S;
+  int rc = upload_series(device, T, y, pop, np, S);
+  if (rc) return rc;
+  return create_from_series(S, E, tau, scaling, rhomat, out);
+}
+
+static int gpedm_lagged_info_impl(gpedm_handle h, int64_t* rows, double* center, double* scale, double* Y, double* X,
+                                  int32_t* pop) {
+  if (!h) return set_err(GPEDM_ERR_ARG, "NULL handle");
+  if (!h->dcenter) return set_err(GPEDM_ERR_STATE, "handle was not made by gpedm_create_lagged");
+  CU(cudaSetDevice(h->device));
+  const size_t nstat = (size_t)(h->d + 1) * h->sc_groups;
+  if (rows)
+    for (int64_t i = 0; i < h->N; ++i) rows[i] = h->rows[i];
+  if (center) CU(cudaMemcpy(center, h->dcenter, nstat * 8, cudaMemcpyDeviceToHost));
+  if (scale) CU(cudaMemcpy(scale, h->dscale, nstat * 8, cudaMemcpyDeviceToHost));
+  if (Y) memcpy(Y, h->hY.data(), (size_t)h->N * 8);
+  if (X) CU(cudaMemcpy(X, h->dX, (size_t)h->N * h->d * 8, cudaMemcpyDeviceToHost));
+  if (pop)
+    for (int64_t i = 0; i < h->N; ++i) pop[i] = h->hpop[i];
+  return 0;
+}
+
+static int gpedm_get_fit_stats_impl(gpedm_handle h, gpedm_fit_stats* out) {
+  if (!h || !out) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
+  CU(cudaSetDevice(h->device));
+  // the handle's scalar scratch (device + pinned host) is free between evaluations
+  fit_stats_kernel<<<1, 256, 0, h->stream>>>(h->dY, h->da, h->ddiagS, h->dpop, (int)h->N, h->cur_ve, h->dcenter,
+                                             h->dscale, h->d + 1, h->dcenter ? h->sc_mode : 0, h->dscal);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(h->hscal, h->dscal, 5 * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const double* v = h->hscal;
+  out->n = v[0];
+  out->obs_mean = v[1];
+  out->ss_total = v[2];
+  out->ss_insample = v[3];
+  out->ss_loo = v[4];
+  out->R2_insample = 1.0 - v[3] / v[2];
+  out->R2_loo = 1.0 - v[4] / v[2];
+  out->rmse_insample = sqrt(v[3] / v[0]);
+  out->rmse_loo = sqrt(v[4] / v[0]);
+  return 0;
+}
+
+// Default start of fitGP (reference R/GPfunctions.R:409, :425-429): pars = (0.1 x d, 0.001, 0.999, 0.5),
+// transformed with rhomin = 0 (so the rho coordinate starts at 0 for one or many populations).
+static void default_initparst(int d, double* t) {
+  for (int i = 0; i < d; ++i) t[i] = log(0.1);
+  t[d] = logit3(0.001, VEMIN, VEMAX);
+  t[d + 1] = logit3(1 - 0.001, SIGMA2MIN, SIGMA2MAX);
+  t[d + 2] = logit3(0.5, 0.0, 1.0);
+}
+
+static int gpedm_fit_grid_impl(int64_t T, const double* y, const int32_t* pop, int32_t np, int32_t ncells,
+                               const int32_t* E, const int32_t* tau, int32_t scaling, double modeprior, int32_t ngpus,
+                               const int32_t* devices, const gpedm_rprop_options* opts, gpedm_result* results,
+                               gpedm_fit_stats* stats) {
+  if (ncells < 0 || (ncells > 0 && (!E || !tau || !results || !y))) return set_err(GPEDM_ERR_ARG, "bad arguments");
+  if (ncells == 0) return 0;
+  int ndev = gpedm_device_count();
+  if (ndev == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available (libgpedm_b200 has no CPU fallback)");
+  if (ngpus < 1 || ngpus > ndev) return set_err(GPEDM_ERR_ARG, "ngpus=%d out of range (have %d devices)", ngpus, ndev);
+  std::vector<int> devs(ngpus);
+  for (int g = 0; g < ngpus; ++g) {
+    devs[g] = devices ? devices[g] : g;
+    if (devs[g] < 0 || devs[g] >= ndev) return set_err(GPEDM_ERR_ARG, "device %d out of range", devs[g]);
+  }
+  for (int c = 0; c < ncells; ++c)
+    if (E[c] < 1 || E[c] > GPEDM_MAX_D || tau[c] < 1) return set_err(GPEDM_ERR_ARG, "cell %d: bad E / tau", c);
+  // queue by descending estimated cost: N ~ T - E tau rows, d = E predictors
+  std::vector<int> order(ncells);
+  for (int i = 0; i < ncells; ++i) order[i] = i;
+  auto cost = [&](int c) {
+    const double n = std::max<double>(1.0, (double)T - (double)E[c] * tau[c]);
+    return n * n * n + 40.0 * E[c] * n * n;
+  };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+  const int W = g_batch_workers > 0 ? g_batch_workers : (T <= 4096 ? 3 : 1);
+  std::vector<LagSeries> series(ngpus);
+  for (int g = 0; g < ngpus; ++g) {  // the raw series goes to every GPU once
+    int rc = upload_series(devs[g], T, y, pop, np, series[g]);
+    if (rc) return rc;
+  }
+  std::atomic<int> next(0);
+  std::vector<std::vector<BatchRecord>> per_worker(ngpus * W), per_gpu(ngpus);
+  std::vector<std::string> werrs(ngpus * W);
+  auto worker = [&](int g, int w) {
+    const int wi = g * W + w;
+    cudaSetDevice(devs[g]);
+    for (;;) {
+      const int q = next.fetch_add(1);
+      if (q >= ncells) break;
+      const int c = order[q];
+      BatchRecord rec;
+      memset(&rec, 0, sizeof(rec));
+      rec.fit_index = c;
+      rec.valid = 1;
+      gpedm_handle h = nullptr;
+      int rc = create_from_series(series[g], E[c], tau[c], scaling, nullptr, &h);
+      if (rc == 0) {
+        double ip[GPEDM_MAX_P];
+        default_initparst(E[c], ip);
+        rc = gpedm_fit_rprop(h, ip, modeprior, nullptr, NAN, opts, &rec.res);
+        if (rc == 0) rc = gpedm_get_fit_stats(h, &rec.st);
+      }
+      rec.res.status = rc;
+      if (rc != 0 && werrs[wi].empty()) werrs[wi] = gpedm_last_error();
+      if (h) gpedm_destroy(h);
+      per_worker[wi].push_back(rec);
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    try {
+      for (int g = 0; g < ngpus; ++g)
+        for (int w = 0; w < W; ++w) th.emplace_back(worker, g, w);
+    } catch (...) {
+      next.store(ncells);
+      for (auto& t : th) t.join();
+      return set_err(GPEDM_ERR_STATE, "could not start grid worker threads");
+    }
+    for (auto& t : th) t.join();
+  }
+  std::string err;
+  for (int wi = 0; wi < ngpus * W; ++wi) {
+    per_gpu[wi / W].insert(per_gpu[wi / W].end(), per_worker[wi].begin(), per_worker[wi].end());
+    if (err.empty() && !werrs[wi].empty()) err = werrs[wi];
+  }
+  std::vector<gpedm_fit_stats> st_tmp(ncells);
+  int rc = exchange_records(devs, per_gpu, ncells, results, stats ? stats : st_tmp.data());
+  if (rc) return rc;
+  if (!err.empty()) {
+    int first_bad = 0;
+    for (int i = 0; i < ncells && !first_bad; ++i) first_bad = results[i].status;
+    return set_err(first_bad ? first_bad : GPEDM_ERR_STATE, "at least one grid cell failed: %s", err.c_str());
+  }
   return 0;
 }
 
@@ -1980,6 +2358,25 @@ extern "C" int gpedm_predict_sequential(gpedm_handle h, const double* time, doub
 
 extern "C" int gpedm_fit_batch(int32_t nfits, const gpedm_fit_desc* descs, int32_t ngpus, const int32_t* devices, const gpedm_rprop_options* opts, gpedm_result* results) {
   GPEDM_GUARDED(gpedm_fit_batch_impl(nfits, descs, ngpus, devices, opts, results));
+}
+
+extern "C" int gpedm_create_lagged(int device, int64_t T, const double* y, const int32_t* pop, int32_t np, int32_t E,
+                                   int32_t tau, int32_t scaling, const double* rhomat, gpedm_handle* out) {
+  GPEDM_GUARDED(gpedm_create_lagged_impl(device, T, y, pop, np, E, tau, scaling, rhomat, out));
+}
+extern "C" int gpedm_lagged_info(gpedm_handle h, int64_t* rows, double* center, double* scale, double* Y, double* X,
+                                 int32_t* pop) {
+  GPEDM_GUARDED(gpedm_lagged_info_impl(h, rows, center, scale, Y, X, pop));
+}
+extern "C" int gpedm_get_fit_stats(gpedm_handle h, gpedm_fit_stats* out) {
+  GPEDM_GUARDED(gpedm_get_fit_stats_impl(h, out));
+}
+extern "C" int gpedm_fit_grid(int64_t T, const double* y, const int32_t* pop, int32_t np, int32_t ncells,
+                              const int32_t* E, const int32_t* tau, int32_t scaling, double modeprior, int32_t ngpus,
+                              const int32_t* devices, const gpedm_rprop_options* opts, gpedm_result* results,
+                              gpedm_fit_stats* stats) {
+  GPEDM_GUARDED(gpedm_fit_grid_impl(T, y, pop, np, ncells, E, tau, scaling, modeprior, ngpus, devices, opts, results,
+                                    stats));
 }
 
 #ifdef GPEDM_DIAG_TIMING

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GPEDM_ABI_VERSION 1
+#define GPEDM_ABI_VERSION 2
 #define GPEDM_MAX_D 32              /* max number of predictors (columns of X) */
 #define GPEDM_MAX_P (GPEDM_MAX_D + 3) /* phi_1..d, ve, sigma2, rho */
 
@@ -192,6 +192,39 @@ typedef struct gpedm_fit_desc {
  * NCCL all-gather over NVLink (single process, ncclCommInitAll); no other collective. */
 int gpedm_fit_batch(int32_t nfits, const gpedm_fit_desc* descs, int32_t ngpus, const int32_t* devices,
                     const gpedm_rprop_options* opts, gpedm_result* results);
+
+/* ---- on-device data preparation + model-selection grids -------------------------------- */
+/* fitGP(data, y, E, tau, scaling) builds its training set from the raw series: lags inside each
+ * population (makelags, reference R/GPfunctions.R:1824-1857), centring / scaling (:359-405) and
+ * removal of incomplete rows (:445-451).  gpedm_create_lagged does this on the device, straight
+ * into the handle's buffers.  y: T raw values (NaN = missing); pop: T codes 0..np-1 in row order
+ * (NULL = one population); scaling: GPEDM_SCALE_*; predictors are the E lags tau, 2 tau, .. E tau
+ * of y.  The handle then behaves like one made by gpedm_create. */
+enum { GPEDM_SCALE_NONE = 0, GPEDM_SCALE_GLOBAL = 1, GPEDM_SCALE_LOCAL = 2 };
+int gpedm_create_lagged(int device, int64_t T, const double* y, const int32_t* pop, int32_t np, int32_t E,
+                        int32_t tau, int32_t scaling, const double* rhomat, gpedm_handle* out);
+/* What gpedm_create_lagged built: rows (gpedm_n entries: original row of each training row),
+ * center / scale ((E+1) x G column-major, column 0 = y, k = lag k; G = np for local scaling,
+ * else 1), the scaled training set Y (N), X (N x E), pop (N).  Any pointer may be NULL. */
+int gpedm_lagged_info(gpedm_handle h, int64_t* rows, double* center, double* scale, double* Y, double* X,
+                      int32_t* pop);
+
+/* In-sample and leave-one-out fit statistics in the ORIGINAL units of y (getR2, reference
+ * :1366-1370, on the back-transformed predictions :469-482), reduced on the device from the
+ * resident full evaluation.  For handles not made by gpedm_create_lagged the units are those of Y. */
+typedef struct gpedm_fit_stats {
+  double n, obs_mean, ss_total, ss_insample, ss_loo;
+  double R2_insample, R2_loo, rmse_insample, rmse_loo;
+} gpedm_fit_stats;
+int gpedm_get_fit_stats(gpedm_handle h, gpedm_fit_stats* out);
+
+/* The E x tau model-selection grid of vignettes/choosingE.Rmd:63-86 as one call: the raw series
+ * is uploaded once per GPU, every cell (E[c], tau[c]) is prepared on the device, fitted from the
+ * default start (:409) with predictmethod "loo" statistics, and the fixed-width records are
+ * exchanged as in gpedm_fit_batch.  results / stats: ncells entries. */
+int gpedm_fit_grid(int64_t T, const double* y, const int32_t* pop, int32_t np, int32_t ncells, const int32_t* E,
+                   const int32_t* tau, int32_t scaling, double modeprior, int32_t ngpus, const int32_t* devices,
+                   const gpedm_rprop_options* opts, gpedm_result* results, gpedm_fit_stats* stats);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 enum {

@@ -34,7 +34,7 @@ def test_header_symbols_exported(L):
 
 
 def test_abi_version_and_struct_layout(L):
-    assert L.gpedm_abi_version() == 1
+    assert L.gpedm_abi_version() == 2
     # gpedm_result: 8 doubles + 4 int32 + 3 * GPEDM_MAX_P doubles
     assert C.sizeof(_lib.Result) == 8 * 8 + 4 * 4 + 3 * 35 * 8
     opt = _lib.RpropOptions()
@@ -72,6 +72,10 @@ def test_argument_validation(L):
     assert b"pop[2]" in L.gpedm_last_error()
     assert L.gpedm_likegrad(None, None, 1.0, None, float("nan"), 0, None) == -1
     assert L.gpedm_fit_batch(-1, None, 1, None, None, None) == -1
+    assert L.gpedm_create_lagged(0, 10, dp(np.zeros(10)), None, 1, 2, 1, 1, None, None) == -1   # NULL out handle
+    assert L.gpedm_fit_grid(10, None, None, 1, 2, None, None, 1, 1.0, 1, None, None, None, None) == -1
+    assert L.gpedm_get_fit_stats(None, None) == -1
+    assert C.sizeof(_lib.FitStats) == 9 * 8
 
 
 def test_sources_build_for_sm100a():

@@ -555,3 +555,106 @@ def test_leaveout_blocks_on_device_vs_bruteforce(gpu_lib):
         assert np.max(np.abs(gm[ok] - om[ok])) <= 1e-9
         assert np.max(np.abs(np.sqrt(gv[ok] + ve) - np.sqrt(ov[ok] + ve))) <= 1e-7
     m.close()
+
+
+# ------------------------------------------------------------------ on-device data preparation
+def _host_prep(y, popv, E, tau, scaling):
+    """fitGP's lagging / scaling / complete-row selection on the host (gpedm_b200.fitgp, itself pinned to
+    the oracle and the README fits)."""
+    from gpedm_b200.fitgp import _lagmatrix, _mean, _sd, unique_stable
+    x = _lagmatrix(y, popv, E, tau)
+    cols = np.column_stack([y, x])
+    up = unique_stable(popv)
+    G_ = len(up) if scaling == "local" else 1
+    center, scale = np.zeros((E + 1, G_)), np.ones((E + 1, G_))
+    sc = cols.copy()
+    if scaling == "global":
+        for j in range(E + 1):
+            center[j, 0], scale[j, 0] = _mean(cols[:, j]), _sd(cols[:, j])
+        sc = (cols - center[:, 0][None, :]) / scale[:, 0][None, :]
+    elif scaling == "local":
+        for g, u in enumerate(up):
+            m = popv == u
+            for j in range(E + 1):
+                center[j, g], scale[j, g] = _mean(cols[m, j]), _sd(cols[m, j])
+            sc[m] = (cols[m] - center[:, g][None, :]) / scale[:, g][None, :]
+    ok = ~np.isnan(sc).any(axis=1)
+    return sc[ok, 0], sc[ok, 1:], np.where(ok)[0], center, scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scaling,npop,E,tau", [("global", 1, 3, 1), ("none", 1, 2, 2), ("local", 3, 2, 1),
+                                                ("global", 2, 4, 3), ("local", 2, 1, 1)])
+def test_create_lagged_matches_host_preparation(gpu_lib, scaling, npop, E, tau):
+    rng = np.random.default_rng(5 + E)
+    ys, pops = [], []
+    for k in range(npop):
+        ys.append(synth.thetalogistic(70 + 9 * k, 30 + k) * (1 + k))
+        pops += ["p%d" % k] * (70 + 9 * k)
+    y = np.concatenate(ys)
+    y[rng.choice(len(y), 4, replace=False)] = np.nan  # missing observations
+    popv = np.asarray(pops, dtype=object)
+    if npop > 1:  # interleave the populations row-wise: lags must follow each population's own order
+        seq = rng.permutation(popv)
+        nxt = {u: list(np.where(popv == u)[0]) for u in set(pops)}
+        perm = np.array([nxt[u].pop(0) for u in seq])
+        y, popv = y[perm], popv[perm]
+    Yh, Xh, rows, center, scale = _host_prep(y, popv, E, tau, scaling)
+    m = G.GPModel.from_series(y, E, tau, pop=popv, scaling=scaling)
+    assert m.N == len(Yh) and np.array_equal(m.rows, rows)
+    if scaling != "none":
+        np.testing.assert_allclose(m.center, center, rtol=1e-14, atol=1e-15)
+        np.testing.assert_allclose(m.scale, scale, rtol=1e-13)
+    np.testing.assert_allclose(m.Y, Yh, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(m.X, Xh, rtol=0, atol=1e-12)
+    # a fit on the device-prepared set equals a fit on the host-prepared set
+    p0 = batch.default_initparst(E, npop == 1)
+    r = m.fit_rprop(p0)
+    codes = G.core.pop_codes(popv)[0][rows]  # scaling groups are indexed in full-series order of appearance
+    mh = G.GPModel(Yh, Xh, popv[rows])
+    rh = mh.fit_rprop(p0)
+    assert r["iter"] == rh["iter"]
+    assert np.max(np.abs(r["pars"] - rh["pars"]) / np.maximum(1, np.abs(rh["pars"]))) <= 1e-8
+    assert rel(r["nllpost"], rh["nllpost"]) <= 1e-10
+    # device fit statistics vs getR2 on back-transformed host vectors
+    from gpedm_b200.fitgp import getR2
+    g = np.zeros(len(rows), dtype=int) if scaling != "local" else codes
+    c0, s0 = (center[0, g], scale[0, g]) if scaling != "none" else (0.0, 1.0)
+    obs = Yh * s0 + c0
+    st = m.fit_stats()
+    assert st["R2_insample"] == pytest.approx(getR2(obs, mh.vector(_lib.VEC_MEAN) * s0 + c0), rel=1e-9)
+    assert st["R2_loo"] == pytest.approx(getR2(obs, mh.vector(_lib.VEC_LOO_MEAN) * s0 + c0), rel=1e-9)
+    assert st["n"] == len(rows)
+    m.close()
+    mh.close()
+
+
+@pytest.mark.gpu
+def test_K1_from_raw_series_on_device(gpu_lib, thetalog2pop, oracle_cases):
+    """K1 (README.md:79-101) with the whole data preparation on the device: raw Abundance + Population
+    -> lags E=3 tau=1, local scaling, complete rows -> fit -> modes and LOO R2 of the README."""
+    tl = thetalog2pop
+    m = G.GPModel.from_series(np.asarray(tl["Abundance"], dtype=float), 3, 1, pop=np.asarray(tl["Population"], dtype=object),
+                              scaling="local")
+    assert m.N == 94
+    r = m.fit_rprop(batch.default_initparst(3, single_pop=False))
+    o = oracle_cases["K1"]
+    assert r["iter"] == o["iter"] == 38
+    assert np.max(np.abs(r["pars"] - np.asarray(o["pars"])) / np.maximum(1, np.abs(o["pars"]))) <= TOL_MODE
+    st = m.fit_stats()
+    assert st["R2_loo"] == pytest.approx(0.991238, abs=5e-7)        # README.md:99
+    assert st["R2_insample"] == pytest.approx(0.9933975, abs=5e-8)  # README.md:92
+    m.close()
+
+
+@pytest.mark.gpu
+def test_fit_grid_device_prep_equals_host_prep(gpu_lib):
+    y = synth.ricker(300, 33)
+    dev = G.fit_grid(y, [1, 2, 3], [1, 2], ngpus=1)
+    host = batch.fit_grid_hostprep(y, [1, 2, 3], [1, 2], ngpus=1)
+    assert [(a["E"], a["tau"]) for a in dev] == [(b["E"], b["tau"]) for b in host]
+    for a, b in zip(dev, host):
+        assert a["status"] == 0 and a["iter"] == b["iter"] and a["N"] == 300 - a["E"] * a["tau"]
+        assert np.max(np.abs(a["pars"] - b["pars"]) / np.maximum(1, np.abs(b["pars"]))) <= 1e-8
+        assert a["R2_loo"] == pytest.approx(b["R2_loo"], rel=1e-9)
+        assert a["R2_insample"] == pytest.approx(b["R2_insample"], rel=1e-9)
