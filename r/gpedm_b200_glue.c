@@ -164,6 +164,72 @@ SEXP gpedmb200_getcov(SEXP phi, SEXP sigma2, SEXP rho, SEXP X, SEXP pop, SEXP X2
   return out;
 }
 
+/* getcovinv: list(L, iKVs) of a symmetric positive definite matrix (reference R/GPfunctions.R:818-830;
+ * L is returned lower triangular, t(L) is the reference's upper factor) */
+SEXP gpedmb200_covinv(SEXP Sigma, SEXP device) {
+  int n = Rf_nrows(Sigma);
+  const char* names[] = {"L", "iKVs", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+  SEXP L = PROTECT(Rf_allocMatrix(REALSXP, n, n)), iK = PROTECT(Rf_allocMatrix(REALSXP, n, n));
+  check_status(gpedm_covinv(Rf_asInteger(device), n, REAL(Sigma), REAL(L), REAL(iK)));
+  SET_VECTOR_ELT(out, 0, L);
+  SET_VECTOR_ELT(out, 1, iK);
+  UNPROTECT(3);
+  return out;
+}
+
+/* fitGP fast path when x is the lag set of y: .Call("gpedmb200_create_lagged", y, popcodes_or_NULL, np, E, tau,
+ * scaling (0 none, 1 global, 2 local), rhomat_or_NULL, device) -> handle (lags / scaling / complete rows on the device) */
+SEXP gpedmb200_create_lagged(SEXP y, SEXP pop, SEXP np, SEXP E, SEXP tau, SEXP scaling, SEXP rhomat, SEXP device) {
+  gpedm_handle h = NULL;
+  check_status(gpedm_create_lagged(Rf_asInteger(device), (int64_t)Rf_length(y), REAL(y),
+                                   Rf_isNull(pop) ? NULL : INTEGER(pop), Rf_asInteger(np), Rf_asInteger(E),
+                                   Rf_asInteger(tau), Rf_asInteger(scaling), Rf_isNull(rhomat) ? NULL : REAL(rhomat),
+                                   &h));
+  SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, handle_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+static SEXP stats_to_vector(const gpedm_fit_stats* st) {
+  SEXP v = PROTECT(Rf_allocVector(REALSXP, 4));
+  REAL(v)[0] = st->R2_insample;
+  REAL(v)[1] = st->R2_loo;
+  REAL(v)[2] = st->rmse_insample;
+  REAL(v)[3] = st->rmse_loo;
+  UNPROTECT(1);
+  return v;
+}
+
+/* c(R2_insample, R2_loo, rmse_insample, rmse_loo) in the original units of y */
+SEXP gpedmb200_fit_stats(SEXP h) {
+  gpedm_fit_stats st;
+  check_status(gpedm_get_fit_stats(get_handle(h), &st));
+  return stats_to_vector(&st);
+}
+
+/* E x tau grid (vignettes/choosingE.Rmd:63-86): list of per-cell lists (fit result + stats) */
+SEXP gpedmb200_fit_grid(SEXP y, SEXP pop, SEXP np, SEXP E, SEXP tau, SEXP scaling, SEXP modeprior, SEXP ngpus) {
+  int nc = Rf_length(E);
+  gpedm_result* res = (gpedm_result*)R_alloc(nc, sizeof(gpedm_result));
+  gpedm_fit_stats* st = (gpedm_fit_stats*)R_alloc(nc, sizeof(gpedm_fit_stats));
+  check_status(gpedm_fit_grid((int64_t)Rf_length(y), REAL(y), Rf_isNull(pop) ? NULL : INTEGER(pop), Rf_asInteger(np), nc,
+                              INTEGER(E), INTEGER(tau), Rf_asInteger(scaling), Rf_asReal(modeprior),
+                              Rf_asInteger(ngpus), NULL, NULL, res, st));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, nc));
+  for (int c = 0; c < nc; ++c) {
+    const char* names[] = {"fit", "stats", ""};
+    SEXP cell = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(cell, 0, result_to_list(&res[c]));
+    SET_VECTOR_ELT(cell, 1, stats_to_vector(&st[c]));
+    SET_VECTOR_ELT(out, c, cell);
+    UNPROTECT(1);
+  }
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"gpedmb200_create", (DL_FUNC)&gpedmb200_create, 6},
     {"gpedmb200_likegrad", (DL_FUNC)&gpedmb200_likegrad, 6},
@@ -174,6 +240,10 @@ static const R_CallMethodDef CallEntries[] = {
     {"gpedmb200_predict_leaveout", (DL_FUNC)&gpedmb200_predict_leaveout, 6},
     {"gpedmb200_predict_sequential", (DL_FUNC)&gpedmb200_predict_sequential, 2},
     {"gpedmb200_getcov", (DL_FUNC)&gpedmb200_getcov, 10},
+    {"gpedmb200_covinv", (DL_FUNC)&gpedmb200_covinv, 2},
+    {"gpedmb200_create_lagged", (DL_FUNC)&gpedmb200_create_lagged, 8},
+    {"gpedmb200_fit_stats", (DL_FUNC)&gpedmb200_fit_stats, 1},
+    {"gpedmb200_fit_grid", (DL_FUNC)&gpedmb200_fit_grid, 8},
     {NULL, NULL, 0}};
 
 void R_init_gpedmb200(DllInfo* dll) {

@@ -50,3 +50,24 @@ getcov <- function(phi, sigma2, rho, X, X2, pop, pop2, rhomat = NULL) {
         as.integer(object$inputs$Primary), returnGPgrad)
 .predict_sequential <- function(object)
   .Call("gpedmb200_predict_sequential", object$handle, as.numeric(object$inputs$Time))
+
+# replaces getcovinv (R/GPfunctions.R:818-830); the reference returns the UPPER factor
+getcovinv <- function(Sigma) {
+  r <- .Call("gpedmb200_covinv", Sigma, 0L)
+  list(L = t(r$L), iKVs = r$iKVs)
+}
+
+# E x tau model-selection grid (vignettes/choosingE.Rmd:63-86) as one call: lags, scaling and complete-row
+# selection happen on the device, fits are sharded over `ngpus`
+fitGP_grid <- function(y, Es, taus, pop = NULL, scaling = c("global", "local", "none"), modeprior = 1, ngpus = 1L) {
+  scaling <- match.arg(scaling)
+  cells <- expand.grid(tau = taus, E = Es)
+  res <- .Call("gpedmb200_fit_grid", as.numeric(y), if (is.null(pop)) NULL else .pop_codes(pop),
+               if (is.null(pop)) 1L else length(unique(pop)), as.integer(cells$E), as.integer(cells$tau),
+               match(scaling, c("none", "global", "local")) - 1L, modeprior, as.integer(ngpus))
+  cells$R2_insample <- vapply(res, function(r) r$stats[1], 0)
+  cells$R2_loo <- vapply(res, function(r) r$stats[2], 0)
+  cells$ln_post <- vapply(res, function(r) -r$fit$nllpost, 0)
+  cells$iter <- vapply(res, function(r) r$fit$iter, 0L)
+  cells
+}

@@ -82,3 +82,24 @@ def test_sources_build_for_sm100a():
     flags = " ".join(_lib.NVCC_FLAGS)
     assert "arch=compute_100a,code=sm_100a" in flags and "-lineinfo" in flags
     assert os.path.exists(_lib.LIB_PATH)
+
+
+def test_r_glue_type_checks_against_header():
+    """R is not installed here, so r/gpedm_b200_glue.c cannot be built; type-check it with gcc against
+    include/gpedm.h and minimal stub declarations of the R C API (tests/r_stub/): every C-ABI call in the
+    glue must match the header's signature, and every .Call entry must be registered."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    glue = os.path.join(root, "r", "gpedm_b200_glue.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-Wno-cast-function-type",
+                        "-I" + os.path.join(root, "tests", "r_stub"), "-I" + os.path.join(root, "include"), glue],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(glue).read()
+    defined = set(re.findall(r"^SEXP (gpedmb200_\w+)\(", src, flags=re.M))
+    registered = set(re.findall(r'\{"(gpedmb200_\w+)", \(DL_FUNC\)&\1, \d+\}', src))
+    assert defined == registered and len(defined) >= 13
+    for name, nargs in re.findall(r'\{"(gpedmb200_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', src):
+        sig = re.search(r"^SEXP %s\(([^)]*)\)" % name, src, flags=re.M | re.S).group(1)
+        assert sig.count("SEXP") == int(nargs), name
