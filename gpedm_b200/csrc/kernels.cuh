@@ -346,7 +346,7 @@ __global__ void extract_diag_kernel(const double* __restrict__ S, size_t ld, int
 // dense N x N matrices, :539-542).  Off-diagonal entries count twice (symmetry).
 // tracepart[tile][q], q = 0..d-1 (phi), d (ve), d+1 (sigma2), d+2 (rho).
 template <int DC>
-__global__ void __launch_bounds__(256) grad_trace_kernel(const double* __restrict__ S, size_t ld, int N,
+__global__ void __launch_bounds__(256, DC <= 16 ? 3 : 1) grad_trace_kernel(const double* __restrict__ S, size_t ld, int N,
                                                           const double* __restrict__ X,
                                                           const int* __restrict__ pop,
                                                           const double* __restrict__ rhotab,
