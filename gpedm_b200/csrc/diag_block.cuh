@@ -150,15 +150,17 @@ __device__ __noinline__ void chol32_warp(double* s, double* rdiag, double* dvec,
   for (int c = 0; c < 32; ++c) a[c] = s[(base + lane) + (base + c) * DG_LD];
   double ajj = __shfl_sync(FULL, a[0], 0);
   double rs = fast_rsqrt(ajj);
+  // Branch-free bookkeeping: every lane keeps 1/L_jj and L_jj of ITS column (select, no divergent
+  // branch inside the latency-bound column loop) and the first bad pivot it saw; stores after the loop.
+  double rs_mine = 0.0, l_mine = 0.0;
+  int bad = 0x7fffffff;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const double l = a[j] * rs;  // L[lane][j]
     a[j] = l;
-    if (lane == j) {
-      if (!(ajj > 0.0) && (kblock * TB + base + j < n_valid)) atomicCAS(info, 0, kblock * TB + base + j + 1);
-      rdiag[base + j] = rs;
-      dvec[base + j] = l;
-    }
+    rs_mine = (lane == j) ? rs : rs_mine;
+    l_mine = (lane == j) ? l : l_mine;
+    bad = (!(ajj > 0.0) && j < bad) ? j : bad;  // uniform across the warp (ajj is a broadcast value)
     double ajj_n = 1.0, rs_n = 1.0;
     if (j + 1 < 32) {
       // lane j+1 owns the next pivot and can update it with its own l: start the broadcast + rsqrt now
@@ -178,6 +180,9 @@ __device__ __noinline__ void chol32_warp(double* s, double* rdiag, double* dvec,
     ajj = ajj_n;
     rs = rs_n;
   }
+  rdiag[base + lane] = rs_mine;
+  dvec[base + lane] = l_mine;
+  if (lane == 0 && bad != 0x7fffffff && kblock * TB + base + bad < n_valid) atomicCAS(info, 0, kblock * TB + base + bad + 1);
 #pragma unroll
   for (int c = 0; c < 32; ++c) s[(base + lane) + (base + c) * DG_LD] = (c <= lane) ? a[c] : 0.0;
 }

@@ -656,6 +656,13 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   {
     int DC = d <= 8 ? 8 : (d <= 16 ? 16 : 32);
     int smem = (4 * d * TB + 2 * TB + 8 * (DC + 3)) * 8 + 2 * TB * 4;
+    if (DC <= 16) {
+      // The kernel is compiled for 3 CTAs/SM (latency-bound: more resident warps help), but a CTA then
+      // runs ~1.26x longer than at 2 CTAs/SM (measured), so when the tile count quantises into the same
+      // number of waves either way, cap residency at 2 by padding the dynamic shared memory request.
+      const int w3 = ceil_div(h->ntiles, 3 * h->num_sms), w2 = ceil_div(h->ntiles, 2 * h->num_sms);
+      if (1.26 * w3 > w2) smem = std::max(smem, 80 * 1024);
+    }
     if (DC == 8)
       grad_trace_kernel<8><<<h->ntiles, 256, smem, st>>>(h->bufC, ld, N, h->dX, h->dpop, h->drhotab, h->da,
                                                          h->dparams, h->dtracepart);
