@@ -105,9 +105,9 @@ static int g_num_sms[64] = {};
 // GPEDM_DIAG_REF=1 selects the simple (slow) reference diagonal-block kernel, for A/B debugging.
 static const bool g_no_lookahead = getenv("GPEDM_NO_LOOKAHEAD") != nullptr && atoi(getenv("GPEDM_NO_LOOKAHEAD")) != 0;
 static const int g_group = getenv("GPEDM_POTRF_GROUP") ? std::max(1, atoi(getenv("GPEDM_POTRF_GROUP"))) : 0;
-static const int g_group_min = getenv("GPEDM_POTRF_GROUP_MIN") ? atoi(getenv("GPEDM_POTRF_GROUP_MIN")) : 24;
+static const int g_group_min = getenv("GPEDM_POTRF_GROUP_MIN") ? atoi(getenv("GPEDM_POTRF_GROUP_MIN")) : 16;
 static const bool g_no_half_tiles = getenv("GPEDM_NO_HALF_TILES") != nullptr && atoi(getenv("GPEDM_NO_HALF_TILES")) != 0;
-static const int g_fill_tail = getenv("GPEDM_FILL_TAIL") ? atoi(getenv("GPEDM_FILL_TAIL")) : 32;
+static const int g_fill_tail = getenv("GPEDM_FILL_TAIL") ? atoi(getenv("GPEDM_FILL_TAIL")) : 40;
 static const bool g_no_small_batch = getenv("GPEDM_NO_SMALL_BATCH") != nullptr && atoi(getenv("GPEDM_NO_SMALL_BATCH")) != 0;
 static const bool g_no_fill = getenv("GPEDM_NO_FILL") != nullptr && atoi(getenv("GPEDM_NO_FILL")) != 0;
 static const bool g_no_split = getenv("GPEDM_NO_SPLIT") != nullptr && atoi(getenv("GPEDM_NO_SPLIT")) != 0;
@@ -549,8 +549,9 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
       t.ld2 = ld;
       return launch_tiles(h, s_, t, 0, s_ == ax && !g_no_split && ntl * 4 <= 2 * h->num_sms);
     };
-    // group size: GPEDM_POTRF_GROUP if set, else 4 for large matrices (bulk-dominated), 2 otherwise
-    const int gsz = g_group > 0 ? g_group : (nb >= 96 ? 4 : 2);
+    // group size: GPEDM_POTRF_GROUP if set, else 4 from 64 block columns up (bulk-dominated; measured
+    // 20.46 -> 20.15 ms at N=8192 together with group_min 16 / fill_tail 40), 2 below (4.07 vs 4.17 ms at N=4096)
+    const int gsz = g_group > 0 ? g_group : (nb >= 64 ? 4 : 2);
     auto group_size = [&](int start) { return (nb - start - 1 >= g_group_min) ? gsz : 1; };
     // Early triangular inverse: level s, pair p (tile rows/cols [2ps, 2ps+2s)) only needs block
     // columns < 2s(p+1) of L and the diagonal-block inverses, so it can run as soon as the Cholesky
