@@ -16,6 +16,7 @@
 // (reference R/GPfunctions.R:826-829).
 #pragma once
 #include "dgemm_tile.cuh"
+#include "tile_stream.cuh"
 
 namespace gpedm {
 
@@ -306,6 +307,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
   double* dvec = rdiag + TB;        // L_jj, later reduction scratch
   double* colbuf = dvec + TB;       // [2][32] pivot-column broadcast buffer
   const int tid = threadIdx.x;
+#ifdef GPEDM_TIMELINE
+  const unsigned long long tl_t0 = tl_now();
+#endif
 
   DG_TS(0);
 #pragma unroll 8
@@ -342,6 +346,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
     Dkk[(size_t)r + (size_t)c * ldd] = (r >= c) ? s[r + c * DG_LD] : 0.0;
   }
   DG_TS(18);
+#ifdef GPEDM_TIMELINE
+  __syncthreads();
+  tl_log(tl_t0, 100 | (1 << 8));
+#endif
 }
 
 }  // namespace gpedm

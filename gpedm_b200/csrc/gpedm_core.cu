@@ -400,8 +400,10 @@ extern "C" int gpedm_last_phase_ms(gpedm_handle h, float* ms) {
 
 // ------------------------------------------------------------------------------- tile launches
 // layout: 0 = (MN, MN), 1 = (MN, K), 2 = (K, K) operand layouts (see dgemm_tile.cuh).
-static int launch_tiles(gpedm_fit_s* h, cudaStream_t st, const TileOp& op, int layout, bool split = false) {
-  if (op.ntiles <= 0) return 0;
+static int launch_tiles(gpedm_fit_s* h, cudaStream_t st, const TileOp& op_in, int layout, bool split = false) {
+  if (op_in.ntiles <= 0) return 0;
+  TileOp op = op_in;
+  op.tag = st == h->aux ? 1 : (st == h->fill ? 2 : 0);
   if (split && layout == 0)  // latency-critical launch with fewer tiles than SMs: 4 row strips per tile
     tile_once_kernel<false, false, GemmCfgSplit>
         <<<op.ntiles * (TB / GemmCfgSplit::TM), GemmCfgSplit::THREADS, GemmCfgSplit::SMEM_BYTES, st>>>(op);
@@ -2386,6 +2388,22 @@ extern "C" int gpedm_fit_grid(int64_t T, const double* y, const int32_t* pop, in
   GPEDM_GUARDED(gpedm_fit_grid_impl(T, y, pop, np, ncells, E, tau, scaling, modeprior, ngpus, devices, opts, results,
                                     stats));
 }
+
+#ifdef GPEDM_TIMELINE
+// Debug export: copy the CTA timeline records logged so far (4 x uint64 each) and reset the log.
+extern "C" int gpedm_debug_timeline(unsigned long long* out, unsigned int max_records, unsigned int* n_out) {
+  unsigned int n = 0;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(&n, g_tl_count, sizeof(n)));
+  if (n > TL_MAX) n = TL_MAX;
+  if (n > max_records) n = max_records;
+  if (out && n) CU(cudaMemcpyFromSymbol(out, g_tl_rec, (size_t)n * 4 * sizeof(unsigned long long)));
+  const unsigned int zero = 0;
+  CU(cudaMemcpyToSymbol(g_tl_count, &zero, sizeof(zero)));
+  if (n_out) *n_out = n;
+  return 0;
+}
+#endif
 
 #ifdef GPEDM_DIAG_TIMING
 extern "C" int gpedm_debug_diag_timing(long long* out) {

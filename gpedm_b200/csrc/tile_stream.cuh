@@ -18,6 +18,35 @@ enum TileOpType {
   OP_TRI_APPLY = 5  // U = X V  (X lower triangular, V = N x M)         (MN, K)
 };
 
+#ifdef GPEDM_TIMELINE
+// Debug build (-DGPEDM_TIMELINE): every CTA logs {start ns, end ns, SM id, op type | tag << 8} so a
+// host tool can reconstruct the SM occupancy of one evaluation (tools/timeline.py).
+constexpr unsigned int TL_MAX = 1u << 18;
+__device__ unsigned long long g_tl_rec[4 * TL_MAX];
+__device__ unsigned int g_tl_count;
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned int tl_smid() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tl_log(unsigned long long t0, int code) {
+  if (threadIdx.x == 0) {
+    const unsigned int i = atomicAdd(&g_tl_count, 1u);
+    if (i < TL_MAX) {
+      g_tl_rec[4 * i] = t0;
+      g_tl_rec[4 * i + 1] = tl_now();
+      g_tl_rec[4 * i + 2] = tl_smid();
+      g_tl_rec[4 * i + 3] = (unsigned long long)code;
+    }
+  }
+}
+#endif
+
 struct TileOp {
   int type;
   int ntiles;
@@ -29,6 +58,7 @@ struct TileOp {
   int nfull;     // trtri: number of full (s x s tile) pairs covered; a ragged last pair may follow
   int jlo, jhi;  // trail column range
   int mt;        // tri_apply: number of column tiles of V
+  int tag;       // which stream launched it (0 main, 1 chain, 2 fill): timeline builds only
   const double* P0;  // operand matrices (meaning depends on type)
   const double* P1;
   double* P2;
@@ -169,6 +199,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINCTA) tile_once_kernel(co
   extern __shared__ double smem[];
   constexpr int SPLIT_M = TB / Cfg::TM, SPLIT_N = TB / Cfg::TN;
   static_assert(SPLIT_M == 1 || !A_KMAJOR, "row-strip split is implemented for MN-major A only");
+#ifdef GPEDM_TIMELINE
+  const unsigned long long tl_t0 = tl_now();
+#endif
   TileWork w;
   if (!decode_tile<A_KMAJOR, B_KMAJOR, Cfg::BK>(op, blockIdx.x / (SPLIT_M * SPLIT_N), w)) return;
   size_t lda, ldb, ldc;
@@ -179,6 +212,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINCTA) tile_once_kernel(co
   double* Cp = w.C + roff + (size_t)coff * ldc;
   gemm_tile_mb<A_KMAJOR, B_KMAJOR, Cfg>(w.A + roff, lda, Bp, ldb, 0, w.nslab * Cfg::BK, (w.flags & 1) != 0,
                                         (w.flags & 2) ? Cp : nullptr, ldc, Cp, ldc, smem);
+#ifdef GPEDM_TIMELINE
+  __syncthreads();
+  tl_log(tl_t0, op.type | (op.tag << 8));
+#endif
 }
 
 }  // namespace gpedm
