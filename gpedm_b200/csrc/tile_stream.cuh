@@ -34,7 +34,7 @@ __device__ __forceinline__ unsigned int tl_smid() {
   asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ void tl_log(unsigned long long t0, int code) {
+__device__ __forceinline__ void tl_log(unsigned long long t0, long long code) {
   if (threadIdx.x == 0) {
     const unsigned int i = atomicAdd(&g_tl_count, 1u);
     if (i < TL_MAX) {
@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINCTA) tile_once_kernel(co
                                         (w.flags & 2) ? Cp : nullptr, ldc, Cp, ldc, smem);
 #ifdef GPEDM_TIMELINE
   __syncthreads();
-  tl_log(tl_t0, op.type | (op.tag << 8));
+  // code = op type | stream tag << 8 | k slabs << 16 | output rows << 40 | output cols << 52
+  tl_log(tl_t0, op.type | (op.tag << 8) | ((long long)w.nslab << 16) | ((long long)Cfg::TM << 40) | ((long long)Cfg::TN << 52));
 #endif
 }
 

@@ -34,7 +34,8 @@ nrec = cnt.value
 rec = buf[:4 * nrec].reshape(nrec, 4).astype(np.int64)
 t0 = rec[:, 0].min()
 st, en, sm, code = (rec[:, 0] - t0) * 1e-3, (rec[:, 1] - t0) * 1e-3, rec[:, 2], rec[:, 3]   # us
-typ, tag = code & 0xff, code >> 8
+typ, tag = code & 0xff, (code >> 8) & 0xff
+flop = 2.0 * ((code >> 40) & 0xfff) * ((code >> 52) & 0xfff) * ((code >> 16) & 0xffffff) * 16   # 2 TM TN (nslab BK)
 names = {"diag (chain)": (typ == 100), "panel (chain)": (typ == 0), "column updates (chain)": (typ == 1) & (tag == 1),
          "bulk trailing update": (typ == 1) & (tag == 0), "trtri early (fill stream)": ((typ == 2) | (typ == 3)) & (tag == 2),
          "trtri late (main stream)": ((typ == 2) | (typ == 3)) & (tag != 2), "lauum": (typ == 4)}
@@ -62,7 +63,10 @@ for b in range(nb):
     print(" ".join(["%12.2f" % (edges[b] * 1e-3)] + ["%12.2f" % v for v in vals] + ["%12.2f" % sum(vals)]))
 print("\nSM-ms per category (sum of CTA lifetimes / 1000):")
 for k in names:
-    print("  %-28s %9.2f SM-ms  = %5.2f ms of the whole GPU" % (k, tot[k] * 1e-3, tot[k] * 1e-3 / nsm))
+    gf = float(np.sum(flop[names[k]])) * 1e-9
+    print("  %-28s %9.2f SM-ms  = %5.2f ms of the whole GPU   %7.1f GFLOP executed -> %5.1f TFLOP/s while resident"
+          % (k, tot[k] * 1e-3, tot[k] * 1e-3 / nsm, gf, gf / max(tot[k] * 1e-6 / nsm, 1e-12) * 1e-3))
+print("  (executed flops count whole 128-wide tiles; the N^3 model of the evaluation is %.1f GFLOP)" % (float(len(Y)) ** 3 * 1e-9))
 busy = sum(tot.values()) * 1e-3
 print("  %-28s %9.2f SM-ms  = %5.2f ms of the whole GPU" % ("idle (span x SMs - busy)", nsm * T * 1e-3 - busy, T * 1e-3 - busy / nsm))
 # chain kernels: latency view
