@@ -1,0 +1,494 @@
+// libgpedm_b200 host orchestration - batched independent fits: NCCL record exchange, lockstep small fits, worker-thread scheduler.
+// Part of the single translation unit gpedm_core.cu (included in order; not a standalone header).
+#pragma once
+
+// ------------------------------------------------------------------------------- batched fits
+struct NcclApi {
+  void* lib = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static bool load_nccl(NcclApi& n) {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (n.lib) break;
+  }
+  if (!n.lib) return false;
+  n.CommInitAll = (int (*)(void**, int, const int*))dlsym(n.lib, "ncclCommInitAll");
+  n.CommDestroy = (int (*)(void*))dlsym(n.lib, "ncclCommDestroy");
+  n.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(n.lib, "ncclAllGather");
+  n.GroupStart = (int (*)())dlsym(n.lib, "ncclGroupStart");
+  n.GroupEnd = (int (*)())dlsym(n.lib, "ncclGroupEnd");
+  n.GetErrorString = (const char* (*)(int))dlsym(n.lib, "ncclGetErrorString");
+  return n.CommInitAll && n.CommDestroy && n.AllGather && n.GroupStart && n.GroupEnd;
+}
+
+
+// ------------------------------------------------------------------------------- batched small fits
+// All fits of a batch with N <= 128 advance in lockstep: one small_eval_kernel launch per Rprop
+// iteration evaluates every still-active fit (one CTA each); the scalar Rprop logic of
+// fmingrad_Rprop (reference R/GPfunctions.R:522-584) runs on the host per fit exactly as in
+// gpedm_fit_rprop.  A last launch with full = 1 at each fit's final parameters yields a and
+// diag(Sigma^-1), from which the in-sample and leave-one-out vectors follow in O(N).
+static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_fit_desc* descs,
+                           const gpedm_rprop_options* opts_in, gpedm_result* results) {
+  const int nf = (int)idx.size();
+  if (nf == 0) return 0;
+  CU(cudaSetDevice(device));
+  int rc = ensure_kernel_attrs(device);
+  if (rc) return rc;
+  gpedm_rprop_options o;
+  if (opts_in)
+    o = *opts_in;
+  else
+    gpedm_default_rprop_options(&o);
+  const double eta_minus = o.eta_minus - 1, eta_plus = o.eta_plus - 1;
+  // ---- pack inputs
+  std::vector<size_t> offX(nf), offN(nf), offR(nf);
+  size_t totX = 0, totN = 0, totR = 0;
+  int dmax = 1;
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    if (ds.N < 1 || ds.N > TB || ds.d < 1 || ds.d > GPEDM_MAX_D || ds.np < 1 || !ds.X || !ds.Y || !ds.pop || !ds.initparst)
+      return set_err(GPEDM_ERR_ARG, "bad descriptor for fit %d", idx[q]);
+    for (int64_t i = 0; i < ds.N; ++i)
+      if (ds.pop[i] < 0 || ds.pop[i] >= ds.np) return set_err(GPEDM_ERR_ARG, "fit %d: pop code outside 0..np-1", idx[q]);
+    offX[q] = totX;
+    offN[q] = totN;
+    offR[q] = totR;
+    totX += (size_t)ds.N * ds.d;
+    totN += (size_t)ds.N;
+    totR += ds.rhomat ? (size_t)ds.np * ds.np : 0;
+    dmax = std::max(dmax, (int)ds.d);
+  }
+  std::vector<double> hX(totX), hY(totN), hR(std::max<size_t>(totR, 1));
+  std::vector<int> hP(totN);
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    memcpy(&hX[offX[q]], ds.X, (size_t)ds.N * ds.d * 8);
+    memcpy(&hY[offN[q]], ds.Y, (size_t)ds.N * 8);
+    memcpy(&hP[offN[q]], ds.pop, (size_t)ds.N * 4);
+    if (ds.rhomat) memcpy(&hR[offR[q]], ds.rhomat, (size_t)ds.np * ds.np * 8);
+  }
+  DevBuf dX, dY, dP, dR, dFits, dParams, dScal, dA, dDiag, dInfo, dActive;
+  PinnedBuf pParams, pScal, pInfo;
+  cudaError_t e = dX.alloc(totX * 8);
+  if (e == cudaSuccess) e = dY.alloc(totN * 8);
+  if (e == cudaSuccess) e = dP.alloc(totN * 4);
+  if (e == cudaSuccess) e = dR.alloc(totR * 8);
+  if (e == cudaSuccess) e = dFits.alloc(sizeof(SmallFit) * nf);
+  if (e == cudaSuccess) e = dParams.alloc(sizeof(EvalParams) * nf);
+  if (e == cudaSuccess) e = dScal.alloc((size_t)NSCAL * 8 * nf);
+  if (e == cudaSuccess) e = dA.alloc(totN * 8);
+  if (e == cudaSuccess) e = dDiag.alloc(totN * 8);
+  if (e == cudaSuccess) e = dInfo.alloc((size_t)nf * 4);
+  if (e == cudaSuccess) e = dActive.alloc((size_t)nf * 4);
+  if (e == cudaSuccess) e = pParams.alloc(sizeof(EvalParams) * nf);
+  if (e == cudaSuccess) e = pScal.alloc((size_t)NSCAL * 8 * nf);
+  if (e == cudaSuccess) e = pInfo.alloc((size_t)nf * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(dX.p, hX.data(), totX * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dY.p, hY.data(), totN * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dP.p, hP.data(), totN * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && totR) e = cudaMemcpy(dR.p, hR.data(), totR * 8, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "small-fit batch setup failed: %s", cudaGetErrorString(e));
+  EvalParams* hparams = (EvalParams*)pParams.p;
+  double* hscal = (double*)pScal.p;
+  int* hinfo = (int*)pInfo.p;
+  std::vector<SmallFit> hfits(nf);
+  // light host-side stand-ins for a handle: only the fields the scalar head / tail of an evaluation reads
+  std::vector<gpedm_fit_s> meta(nf);
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    SmallFit& F = hfits[q];
+    F.X = (const double*)dX.p + offX[q];
+    F.Y = (const double*)dY.p + offN[q];
+    F.pop = (const int*)dP.p + offN[q];
+    F.rhotab = ds.rhomat ? (const double*)dR.p + offR[q] : nullptr;
+    F.scal = (double*)dScal.p + (size_t)q * NSCAL;
+    F.a_out = (double*)dA.p + offN[q];
+    F.diag_out = (double*)dDiag.p + offN[q];
+    F.info = (int*)dInfo.p + q;
+    F.N = (int)ds.N;
+    F.d = ds.d;
+    F.np = ds.np;
+    F.pad = 0;
+    gpedm_fit_s& m = meta[q];
+    m.N = ds.N;
+    m.d = ds.d;
+    m.np = ds.np;
+    m.p = ds.d + 3;
+    m.has_rhomat = ds.rhomat != nullptr;
+    m.single_pop = true;
+    for (int64_t i = 1; i < ds.N; ++i)
+      if (ds.pop[i] != ds.pop[0]) m.single_pop = false;
+    m.hparams = hparams + q;
+    m.hscal = hscal + (size_t)q * NSCAL;
+  }
+  CU(cudaMemcpy(dFits.p, hfits.data(), sizeof(SmallFit) * nf, cudaMemcpyHostToDevice));
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  const int DC = dmax <= 8 ? 8 : (dmax <= 16 ? 16 : 32);
+  std::vector<int> active;
+  auto launch = [&](int full) -> int {
+    const int na = (int)active.size();
+    if (na == 0) return 0;
+    cudaError_t e2 = cudaMemcpyAsync(dParams.p, hparams, sizeof(EvalParams) * nf, cudaMemcpyHostToDevice, st);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(dActive.p, active.data(), (size_t)na * 4, cudaMemcpyHostToDevice, st);
+    if (e2 != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "small-fit upload failed: %s", cudaGetErrorString(e2));
+    if (DC == 8)
+      small_eval_kernel<8><<<na, DG_THREADS, small_eval_smem_bytes<8>(), st>>>((const SmallFit*)dFits.p, (const EvalParams*)dParams.p, (const int*)dActive.p, full);
+    else if (DC == 16)
+      small_eval_kernel<16><<<na, DG_THREADS, small_eval_smem_bytes<16>(), st>>>((const SmallFit*)dFits.p, (const EvalParams*)dParams.p, (const int*)dActive.p, full);
+    else
+      small_eval_kernel<32><<<na, DG_THREADS, small_eval_smem_bytes<32>(), st>>>((const SmallFit*)dFits.p, (const EvalParams*)dParams.p, (const int*)dActive.p, full);
+    e2 = cudaMemcpyAsync(hscal, dScal.p, (size_t)NSCAL * 8 * nf, cudaMemcpyDeviceToHost, st);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(hinfo, dInfo.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+    if (e2 == cudaSuccess) e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "small-fit evaluation failed: %s", cudaGetErrorString(e2));
+    return 0;
+  };
+  struct State {
+    double pa[GPEDM_MAX_P], del[GPEDM_MAX_P], grad[GPEDM_MAX_P], panew[GPEDM_MAX_P];
+    double nll = 0, s = 0, df = 10;
+    int iter = 0, nevals = 0, status = 0;
+    bool done = false;
+  };
+  std::vector<State> stt(nf);
+  std::vector<HostPars> hp(nf);
+  // ---- initial evaluation (:545)
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    for (int i = 0; i < ds.d + 3; ++i) {
+      stt[q].pa[i] = stt[q].panew[i] = ds.initparst[i];
+      stt[q].del[i] = o.delta0;
+    }
+    host_transform(&meta[q], stt[q].panew, ds.modeprior, ds.fixedpars, ds.rhofixed, hp[q]);
+    fill_params(&meta[q], hp[q]);
+    active.push_back(q);
+  }
+  rc = launch(0);
+  bool first = true;
+  while (rc == 0) {
+    std::vector<int> next_active;
+    for (int q : active) {
+      State& S = stt[q];
+      const gpedm_fit_desc& ds = descs[idx[q]];
+      gpedm_result r;
+      finish_result(&meta[q], hp[q], false, &r);
+      S.nevals++;
+      if (hinfo[q] > 0) {
+        S.status = hinfo[q];
+        S.done = true;
+        continue;
+      }
+      const int p = ds.d + 3;
+      if (first) {
+        S.nll = r.nllpost;
+        for (int i = 0; i < p; ++i) S.grad[i] = r.grad[i];
+        S.s = r.gradnorm;
+      } else {
+        S.s = r.gradnorm;
+        S.df = fabs(r.nllpost / S.nll - 1);  // :565
+        for (int i = 0; i < p; ++i) {
+          const double gc = S.grad[i] * r.grad[i];
+          const double tdel = S.del[i] * (1 + eta_plus * (gc > 0) + eta_minus * (gc < 0));  // :569
+          S.del[i] = tdel < o.deltamin ? o.deltamin : (tdel > o.deltamax ? o.deltamax : tdel);
+          S.pa[i] = S.panew[i];
+          S.grad[i] = r.grad[i];
+        }
+        S.nll = r.nllpost;
+        S.iter++;
+      }
+      if (S.s > o.tol_grad && S.iter < o.maxiter && S.df > o.tol_df) {  // :556
+        for (int i = 0; i < p; ++i) S.panew[i] = S.pa[i] - sgn(S.grad[i]) * S.del[i];  // :559
+        host_transform(&meta[q], S.panew, ds.modeprior, ds.fixedpars, ds.rhofixed, hp[q]);
+        fill_params(&meta[q], hp[q]);
+        next_active.push_back(q);
+      } else {
+        S.done = true;
+      }
+    }
+    first = false;
+    active.swap(next_active);
+    if (active.empty()) break;
+    rc = launch(0);
+  }
+  // ---- final full evaluation at each fit's last parameters (:580)
+  std::vector<double> ha(totN), hd(totN);
+  if (rc == 0) {
+    active.clear();
+    for (int q = 0; q < nf; ++q) {
+      if (stt[q].status != 0) continue;
+      const gpedm_fit_desc& ds = descs[idx[q]];
+      host_transform(&meta[q], stt[q].pa, ds.modeprior, ds.fixedpars, ds.rhofixed, hp[q]);
+      fill_params(&meta[q], hp[q]);
+      active.push_back(q);
+    }
+    rc = launch(1);
+    if (rc == 0) {
+      e = cudaMemcpy(ha.data(), dA.p, totN * 8, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(hd.data(), dDiag.p, totN * 8, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = set_err(GPEDM_ERR_CUDA, "small-fit download failed: %s", cudaGetErrorString(e));
+    }
+  }
+  cudaStreamDestroy(st);
+  if (rc) return rc;
+  int first_bad = 0;
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    gpedm_result& R = results[idx[q]];
+    State& S = stt[q];
+    if (S.status == 0 && hinfo[q] > 0) S.status = hinfo[q];
+    if (S.status != 0) {
+      memset(&R, 0, sizeof(R));
+      R.status = S.status;
+      R.iter = S.iter;
+      R.nevals = S.nevals;
+      R.p = ds.d + 3;
+      if (!first_bad) first_bad = S.status;
+      continue;
+    }
+    finish_result(&meta[q], hp[q], true, &R);
+    R.iter = S.iter;
+    R.nevals = S.nevals + 1;
+    R.status = 0;
+    const double ve = hp[q].ve;
+    for (int64_t i = 0; i < ds.N; ++i) {
+      const double a = ha[offN[q] + i], sii = hd[offN[q] + i], y = ds.Y[i];
+      if (ds.want_loo && ds.loo_mean) ds.loo_mean[i] = y - a / sii;
+      if (ds.want_loo && ds.loo_var) ds.loo_var[i] = 1.0 / sii - ve;
+      if (ds.insamp_mean) ds.insamp_mean[i] = y - ve * a;
+      if (ds.insamp_var) ds.insamp_var[i] = ve - ve * ve * sii;
+    }
+  }
+  if (first_bad) return set_err(first_bad, "at least one small fit failed: covariance matrix not positive definite (pivot %d)", first_bad);
+  return 0;
+}
+
+// Fixed-width record exchanged by the final all-gather.
+struct BatchRecord {
+  int32_t fit_index;
+  int32_t valid;
+  gpedm_result res;
+  gpedm_fit_stats st;  // filled by gpedm_fit_grid only
+};
+
+// Every GPU ends up with every fit's fixed-width record.  One GPU: a copy.  Several: ONE NCCL
+// all-gather (single process, one communicator per GPU); every GPU contributes `slab` records
+// (padded with valid=0).  No other collective exists on the path.
+static int exchange_records(const std::vector<int>& devs, const std::vector<std::vector<BatchRecord>>& per_gpu,
+                            int nfits, gpedm_result* results, gpedm_fit_stats* stats) {
+  const int ngpus = (int)devs.size();
+  if (ngpus == 1) {
+    for (auto& r : per_gpu[0]) {
+      results[r.fit_index] = r.res;
+      if (stats) stats[r.fit_index] = r.st;
+    }
+    return 0;
+  }
+  NcclApi nc;
+  if (!load_nccl(nc)) return set_err(GPEDM_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  size_t slab = 0;
+  for (int g = 0; g < ngpus; ++g) slab = std::max(slab, per_gpu[g].size());
+  if (slab == 0) slab = 1;
+  const size_t slab_bytes = slab * sizeof(BatchRecord);
+  std::vector<void*> comms(ngpus, nullptr);
+  int nrc = nc.CommInitAll(comms.data(), ngpus, devs.data());
+  if (nrc != 0)
+    return set_err(GPEDM_ERR_NCCL, "ncclCommInitAll failed: %s", nc.GetErrorString ? nc.GetErrorString(nrc) : "?");
+  std::vector<char*> dsend(ngpus, nullptr), drecv(ngpus, nullptr);
+  std::vector<cudaStream_t> sts(ngpus, nullptr);
+  cudaError_t e = cudaSuccess;
+  for (int g = 0; g < ngpus && e == cudaSuccess; ++g) {
+    e = cudaSetDevice(devs[g]);
+    if (e == cudaSuccess) e = cudaStreamCreate(&sts[g]);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dsend[g], slab_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&drecv[g], slab_bytes * ngpus);
+    std::vector<BatchRecord> pad(slab);
+    memset(pad.data(), 0, slab_bytes);
+    for (size_t q = 0; q < per_gpu[g].size(); ++q) pad[q] = per_gpu[g][q];
+    if (e == cudaSuccess) e = cudaMemcpy(dsend[g], pad.data(), slab_bytes, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) {
+    nc.GroupStart();
+    for (int g = 0; g < ngpus; ++g) {
+      cudaSetDevice(devs[g]);
+      nrc = nc.AllGather(dsend[g], drecv[g], slab_bytes, /*ncclChar*/ 0, comms[g], sts[g]);
+      if (nrc != 0) break;
+    }
+    int nrc2 = nc.GroupEnd();
+    if (nrc == 0) nrc = nrc2;
+    for (int g = 0; g < ngpus && e == cudaSuccess; ++g) {
+      cudaSetDevice(devs[g]);
+      e = cudaStreamSynchronize(sts[g]);
+    }
+  }
+  std::vector<BatchRecord> all(slab * ngpus);
+  if (e == cudaSuccess && nrc == 0) {
+    cudaSetDevice(devs[0]);
+    e = cudaMemcpy(all.data(), drecv[0], slab_bytes * ngpus, cudaMemcpyDeviceToHost);
+  }
+  for (int g = 0; g < ngpus; ++g) {
+    cudaSetDevice(devs[g]);
+    cudaFree(dsend[g]);
+    cudaFree(drecv[g]);
+    if (sts[g]) cudaStreamDestroy(sts[g]);
+    if (comms[g]) nc.CommDestroy(comms[g]);
+  }
+  if (nrc != 0) return set_err(GPEDM_ERR_NCCL, "ncclAllGather failed: %s", nc.GetErrorString ? nc.GetErrorString(nrc) : "?");
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "batch gather failed: %s", cudaGetErrorString(e));
+  int got = 0;
+  for (auto& r : all)
+    if (r.valid && r.fit_index >= 0 && r.fit_index < nfits) {
+      results[r.fit_index] = r.res;
+      if (stats) stats[r.fit_index] = r.st;
+      ++got;
+    }
+  if (got != nfits) return set_err(GPEDM_ERR_STATE, "batch gather returned %d of %d records", got, nfits);
+  return 0;
+}
+
+static int run_one_fit(int device, const gpedm_fit_desc& ds, const gpedm_rprop_options* opts, gpedm_result* res) {
+  gpedm_handle h = nullptr;
+  int rc = gpedm_create(device, ds.N, ds.d, ds.np, ds.X, ds.Y, ds.pop, ds.rhomat, &h);
+  if (rc) {
+    memset(res, 0, sizeof(*res));
+    res->status = rc;
+    return rc;
+  }
+  rc = gpedm_fit_rprop(h, ds.initparst, ds.modeprior, ds.fixedpars, ds.rhofixed, opts, res);
+  if (rc == 0) {
+    if (ds.want_loo && ds.loo_mean) rc = gpedm_get_vector(h, GPEDM_VEC_LOO_MEAN, ds.loo_mean);
+    if (rc == 0 && ds.want_loo && ds.loo_var) rc = gpedm_get_vector(h, GPEDM_VEC_LOO_VAR, ds.loo_var);
+    if (rc == 0 && ds.insamp_mean) rc = gpedm_get_vector(h, GPEDM_VEC_MEAN, ds.insamp_mean);
+    if (rc == 0 && ds.insamp_var) rc = gpedm_get_vector(h, GPEDM_VEC_VAR, ds.insamp_var);
+  }
+  res->status = rc;
+  gpedm_destroy(h);
+  return rc;
+}
+
+static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int32_t ngpus, const int32_t* devices,
+                               const gpedm_rprop_options* opts, gpedm_result* results) {
+  if (nfits < 0 || (nfits > 0 && (!descs || !results))) return set_err(GPEDM_ERR_ARG, "bad arguments");
+  if (nfits == 0) return 0;
+  int ndev = gpedm_device_count();
+  if (ndev == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available (libgpedm_b200 has no CPU fallback)");
+  if (ngpus < 1 || ngpus > ndev) return set_err(GPEDM_ERR_ARG, "ngpus=%d out of range (have %d devices)", ngpus, ndev);
+  std::vector<int> devs(ngpus);
+  for (int g = 0; g < ngpus; ++g) {
+    devs[g] = devices ? devices[g] : g;
+    if (devs[g] < 0 || devs[g] >= ndev) return set_err(GPEDM_ERR_ARG, "device %d out of range", devs[g]);
+  }
+  // queue ordered by descending estimated cost ~ N^3 (+ d N^2)
+  std::vector<int> order(nfits);
+  for (int i = 0; i < nfits; ++i) order[i] = i;
+  auto cost = [&](int i) {
+    double n = (double)descs[i].N;
+    return n * n * n + 40.0 * descs[i].d * n * n;
+  };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+  // Fits with N <= 128 (one tile) advance in lockstep through the batched one-CTA-per-fit kernel,
+  // one host thread per GPU over a strided share; everything larger goes through the tiled
+  // pipeline, pulled from a shared queue by W worker threads per GPU.  Both kinds run concurrently.
+  std::vector<int> small_order, big_order;
+  for (int q = 0; q < nfits; ++q) (descs[order[q]].N <= TB && !g_no_small_batch ? small_order : big_order).push_back(order[q]);
+  if (small_order.size() < 2) {  // a single small fit gains nothing from the batched kernel
+    big_order = order;
+    small_order.clear();
+  }
+  const int nbig = (int)big_order.size();
+  std::atomic<int> next(0);
+  std::vector<std::vector<BatchRecord>> per_gpu(ngpus);
+  std::vector<std::string> errs(ngpus);
+  // W worker threads per GPU, each with its own handles / streams: independent fits interleave
+  // on one device, so the latency-bound stretches of one evaluation (the serial Cholesky chain)
+  // are filled by the bulk kernels of the other.
+  int64_t nmax = 0;
+  for (int i : big_order) nmax = std::max<int64_t>(nmax, descs[i].N);
+  // small problems leave most of the GPU idle -> interleave several fits; large ones already fill it
+  const int W = g_batch_workers > 0 ? g_batch_workers : (nmax <= 4096 ? 3 : 1);
+  std::vector<std::vector<BatchRecord>> per_worker(ngpus * (W + 1));  // slot W of each GPU: the small-fit thread
+  std::vector<std::string> werrs(ngpus * (W + 1));
+  auto worker = [&](int g, int w) {
+    const int wi = g * (W + 1) + w;
+    cudaSetDevice(devs[g]);
+    for (;;) {
+      int q = next.fetch_add(1);
+      if (q >= nbig) break;
+      int i = big_order[q];
+      BatchRecord rec;
+      memset(&rec, 0, sizeof(rec));
+      rec.fit_index = i;
+      rec.valid = 1;
+      int rc = run_one_fit(devs[g], descs[i], opts, &rec.res);
+      if (rc != 0 && werrs[wi].empty()) werrs[wi] = gpedm_last_error();
+      per_worker[wi].push_back(rec);
+    }
+  };
+  auto small_worker = [&](int g) {
+    const int wi = g * (W + 1) + W;
+    std::vector<int> mine;
+    for (size_t q = g; q < small_order.size(); q += ngpus) mine.push_back(small_order[q]);
+    if (mine.empty()) return;
+    std::vector<gpedm_result> tmp(nfits);
+    int rc = fit_batch_small(devs[g], mine, descs, opts, tmp.data());
+    if (rc != 0) werrs[wi] = gpedm_last_error();
+    for (int i : mine) {
+      BatchRecord rec;
+      memset(&rec, 0, sizeof(rec));
+      rec.fit_index = i;
+      rec.valid = 1;
+      rec.res = tmp[i];
+      if (rc < 0 && rec.res.status == 0) rec.res.status = rc;
+      per_worker[wi].push_back(rec);
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    try {
+      if (!small_order.empty())
+        for (int g = 0; g < ngpus; ++g) th.emplace_back(small_worker, g);
+      if (nbig > 0)
+        for (int g = 0; g < ngpus; ++g)
+          for (int w = 0; w < W; ++w) th.emplace_back(worker, g, w);
+    } catch (...) {
+      next.store(nbig);  // could not start every thread: let the started ones drain and stop
+      for (auto& t : th) t.join();
+      return set_err(GPEDM_ERR_STATE, "could not start batch worker threads");
+    }
+    for (auto& t : th) t.join();
+  }
+  for (int wi = 0; wi < ngpus * (W + 1); ++wi) {
+    const int g = wi / (W + 1);
+    per_gpu[g].insert(per_gpu[g].end(), per_worker[wi].begin(), per_worker[wi].end());
+    if (errs[g].empty() && !werrs[wi].empty()) errs[g] = werrs[wi];
+  }
+  {
+    size_t got = 0;
+    for (int g = 0; g < ngpus; ++g) got += per_gpu[g].size();
+    if (got != (size_t)nfits) return set_err(GPEDM_ERR_STATE, "batch produced %zu of %d records", got, nfits);
+  }
+
+  {
+    int rc = exchange_records(devs, per_gpu, nfits, results, nullptr);
+    if (rc) return rc;
+  }
+  for (int g = 0; g < ngpus; ++g)
+    if (!errs[g].empty()) {
+      int first_bad = 0;
+      for (int i = 0; i < nfits; ++i)
+        if (results[i].status != 0) {
+          first_bad = results[i].status;
+          break;
+        }
+      return set_err(first_bad ? first_bad : GPEDM_ERR_STATE, "at least one fit failed: %s", errs[g].c_str());
+    }
+  return 0;
+}

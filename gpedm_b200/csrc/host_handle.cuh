@@ -1,0 +1,348 @@
+// libgpedm_b200 host orchestration - the fit handle: device buffers, streams, events; creation / destruction / data upload.
+// Part of the single translation unit gpedm_core.cu (included in order; not a standalone header).
+#pragma once
+
+// ------------------------------------------------------------------------------- handle
+struct gpedm_fit_s {
+  int device = 0;
+  int64_t N = 0;
+  int Np = 0, nb = 0, ntiles = 0;
+  int d = 0, np = 1, p = 0;
+  bool has_rhomat = false;
+  bool single_pop = true;
+  double *dX = nullptr, *dY = nullptr, *drhotab = nullptr;
+  int* dpop = nullptr;
+  double *bufA = nullptr, *bufB = nullptr, *bufC = nullptr;
+  EvalParams* dparams = nullptr;
+  void* pinned = nullptr;         // one recycled pinned block holding hparams | hscal | hinfo
+  EvalParams* hparams = nullptr;  // pinned
+  double *dz = nullptr, *da = nullptr, *ddiagS = nullptr, *dpart = nullptr, *dlogdet = nullptr,
+         *dtracepart = nullptr, *dscal = nullptr;
+  double* hscal = nullptr;  // pinned
+  int* dinfo = nullptr;
+  int* hinfo = nullptr;  // pinned
+  int num_sms = 148;
+  cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // gradient-only / full / through-z variants
+  int64_t graph_launches[3] = {0, 0, 0};
+  const double* dsigma_in = nullptr;  // gpedm_covinv: factor this N x N matrix instead of assembling Sigma
+  int trtri_w_done[16] = {}, trtri_x_done[16] = {};  // per level: full pairs already launched this evaluation
+  cudaStream_t stream = nullptr;
+  cudaStream_t aux = nullptr;  // high-priority stream for the look-ahead chain (diag, panel, next column)
+  cudaStream_t fill = nullptr; // low-priority stream: early triangular-inverse levels filling the Cholesky tail
+  cudaEvent_t evFill = nullptr;
+  std::vector<cudaEvent_t> evCol;  // "block columns < c are final" checkpoints for the fill stream
+  std::vector<cudaEvent_t> evPanel, evTrail;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  cudaEvent_t ev[GPEDM_NPHASE + 1] = {};
+  float phase_ms[GPEDM_NPHASE] = {};
+  int64_t launches = 0;
+  bool have_full = false;  // L (bufA), L^-1 (bufB), Sigma^-1 (bufC), a, diagS valid for `cur`
+  double cur_ve = 0, cur_sigma2 = 0, cur_rho = 0;
+  std::vector<double> hY;  // host copy of Y (N)
+  std::vector<int> hpop;
+  // set by gpedm_create_lagged: column statistics (E+1) x G used for the scaling, kept rows
+  double *dcenter = nullptr, *dscale = nullptr;
+  int sc_mode = 0, sc_groups = 1;
+  std::vector<int> rows;  // original row of each training row
+};
+
+static const int NSCAL = 8 + MAXD + 3;
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+static bool g_attr_set[64] = {};
+static int g_num_sms[64] = {};
+// GPEDM_DIAG_REF=1 selects the simple (slow) reference diagonal-block kernel, for A/B debugging.
+static const bool g_no_lookahead = getenv("GPEDM_NO_LOOKAHEAD") != nullptr && atoi(getenv("GPEDM_NO_LOOKAHEAD")) != 0;
+static const int g_group = getenv("GPEDM_POTRF_GROUP") ? std::max(1, atoi(getenv("GPEDM_POTRF_GROUP"))) : 0;
+static const int g_group_min = getenv("GPEDM_POTRF_GROUP_MIN") ? atoi(getenv("GPEDM_POTRF_GROUP_MIN")) : 16;
+static const bool g_no_half_tiles = getenv("GPEDM_NO_HALF_TILES") != nullptr && atoi(getenv("GPEDM_NO_HALF_TILES")) != 0;
+static const int g_fill_tail = getenv("GPEDM_FILL_TAIL") ? atoi(getenv("GPEDM_FILL_TAIL")) : 40;
+static const bool g_no_small_batch = getenv("GPEDM_NO_SMALL_BATCH") != nullptr && atoi(getenv("GPEDM_NO_SMALL_BATCH")) != 0;
+static const bool g_no_fill = getenv("GPEDM_NO_FILL") != nullptr && atoi(getenv("GPEDM_NO_FILL")) != 0;
+static const bool g_no_split = getenv("GPEDM_NO_SPLIT") != nullptr && atoi(getenv("GPEDM_NO_SPLIT")) != 0;
+static const int g_graph_max_nb = getenv("GPEDM_GRAPH_MAX_NB") ? atoi(getenv("GPEDM_GRAPH_MAX_NB")) : 48;
+static const int g_batch_workers = getenv("GPEDM_BATCH_WORKERS_PER_GPU") ? atoi(getenv("GPEDM_BATCH_WORKERS_PER_GPU")) : 0;
+static const bool g_no_graph = getenv("GPEDM_NO_GRAPH") != nullptr && atoi(getenv("GPEDM_NO_GRAPH")) != 0;
+static const bool g_diag_ref = getenv("GPEDM_DIAG_REF") != nullptr && atoi(getenv("GPEDM_DIAG_REF")) != 0;
+static std::mutex g_attr_mutex;
+static int ensure_kernel_attrs(int device) {
+  std::lock_guard<std::mutex> lock(g_attr_mutex);  // batch workers create handles concurrently
+  if (device < 64 && g_attr_set[device]) return 0;
+  CU(cudaFuncSetAttribute(tile_once_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<false, false, GemmCfgSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          GemmCfgSplit::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<false, false, GemmCfgHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          GemmCfgHalf::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<false, true, GemmCfgHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          GemmCfgHalf::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_once_kernel<true, true, GemmCfgHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          GemmCfgHalf::SMEM_BYTES));
+  {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (device < 64) g_num_sms[device] = prop.multiProcessorCount;
+    // Handles are created and destroyed per fit (40 per model-selection grid): keep freed device
+    // memory cached in the stream-ordered pool instead of returning 1.6 GB to the driver each time.
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+  }
+  CU(cudaFuncSetAttribute(diag_potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(small_eval_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<8>()));
+  CU(cudaFuncSetAttribute(small_eval_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<16>()));
+  CU(cudaFuncSetAttribute(small_eval_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<32>()));
+  int trace_smem = (4 * MAXD * TB + 2 * TB + 8 * (MAXD + 3)) * 8 + 2 * TB * 4;
+  CU(cudaFuncSetAttribute(grad_trace_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
+  CU(cudaFuncSetAttribute(grad_trace_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
+  CU(cudaFuncSetAttribute(grad_trace_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
+  int asm_smem = 2 * MAXD * TB * 8 + 2 * TB * 4;
+  CU(cudaFuncSetAttribute(assemble_sigma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_smem));
+  CU(cudaFuncSetAttribute(cov_rect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_smem));
+  if (device < 64) g_attr_set[device] = true;
+  return 0;
+}
+
+extern "C" int gpedm_abi_version(void) { return GPEDM_ABI_VERSION; }
+extern "C" const char* gpedm_last_error(void) { return g_err; }
+extern "C" int gpedm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+extern "C" void gpedm_default_rprop_options(gpedm_rprop_options* o) {
+  o->delta0 = 0.1;
+  o->deltamin = 1e-6;
+  o->deltamax = 50.0;
+  o->eta_minus = 0.5;
+  o->eta_plus = 1.2;
+  o->maxiter = 200;
+  o->tol_grad = 1e-4;
+  o->tol_df = 1e-7;
+}
+
+// Pinned host blocks (parameters up, scalars / status down) are recycled through a process-wide
+// free list: cudaMallocHost / cudaFreeHost cost up to 200 ms each (measured) when handles are created
+// and destroyed per fit, as a model-selection grid does.  Blocks are a few KB and never returned.
+static const size_t PINNED_BLOCK = 4096;
+static_assert(sizeof(EvalParams) + (8 + MAXD + 3) * 8 + 16 <= PINNED_BLOCK, "pinned block too small");
+static std::mutex g_pinned_mutex;
+static std::vector<void*> g_pinned_free;
+static void* pinned_acquire() {
+  {
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    if (!g_pinned_free.empty()) {
+      void* p = g_pinned_free.back();
+      g_pinned_free.pop_back();
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, PINNED_BLOCK, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  return p;
+}
+static void pinned_release(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_pinned_mutex);
+  g_pinned_free.push_back(p);
+}
+
+static void free_handle(gpedm_fit_s* h) {
+  if (!h) return;
+  static const bool trace = getenv("GPEDM_TRACE_FREE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now();
+  cudaSetDevice(h->device);
+  if (h->stream) {
+    cudaStreamSynchronize(h->stream);
+    if (h->aux) cudaStreamSynchronize(h->aux);
+    void* bufs[] = {h->dX, h->dY, h->drhotab, h->dpop, h->bufA, h->bufB, h->bufC, h->dparams, h->dz, h->da,
+                    h->ddiagS, h->dpart, h->dlogdet, h->dtracepart, h->dscal, h->dinfo, h->dcenter, h->dscale};
+    for (void* b : bufs)
+      if (b) cudaFreeAsync(b, h->stream);
+    cudaStreamSynchronize(h->stream);
+  }
+  double t1 = now();
+  pinned_release(h->pinned);
+  double t2 = now();
+  for (auto& g : h->graph_exec)
+    if (g) cudaGraphExecDestroy(g);
+  double t3 = now();
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : h->evPanel) cudaEventDestroy(e);
+  for (auto& e : h->evTrail) cudaEventDestroy(e);
+  for (auto& e : h->evCol) cudaEventDestroy(e);
+  if (h->evFill) cudaEventDestroy(h->evFill);
+  if (h->evFork) cudaEventDestroy(h->evFork);
+  if (h->evJoin) cudaEventDestroy(h->evJoin);
+  double t4 = now();
+  if (h->fill) cudaStreamDestroy(h->fill);
+  if (h->aux) cudaStreamDestroy(h->aux);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  double t5 = now();
+  if (trace)
+    fprintf(stderr, "[gpedm free] device bufs %.2f ms, pinned %.2f, graphs %.2f, events %.2f, streams %.2f\n", t1 - t0,
+            t2 - t1, t3 - t2, t4 - t3, t5 - t4);
+  delete h;
+}
+
+// Allocate a handle for an N x d problem with np populations: device buffers, streams, events.
+// The training data (dX, dY, dpop, drhotab, hY, hpop, single_pop) are filled by the caller.
+static int alloc_handle(int device, int64_t N, int32_t d, int32_t np, bool has_rhomat, gpedm_handle* out) {
+  *out = nullptr;
+  if (N < 1 || N > (1 << 20)) return set_err(GPEDM_ERR_ARG, "N=%lld out of range", (long long)N);
+  if (d < 1 || d > GPEDM_MAX_D) return set_err(GPEDM_ERR_ARG, "d=%d out of range 1..%d", d, GPEDM_MAX_D);
+  if (np < 1) return set_err(GPEDM_ERR_ARG, "np=%d must be >= 1", np);
+  int ndev = gpedm_device_count();
+  if (ndev == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available (libgpedm_b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(GPEDM_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+  CU(cudaSetDevice(device));
+  int rc = ensure_kernel_attrs(device);
+  if (rc) return rc;
+  gpedm_fit_s* h = new gpedm_fit_s();
+  h->device = device;
+  h->N = N;
+  h->nb = ceil_div((int)N, TB);
+  h->Np = h->nb * TB;
+  h->ntiles = h->nb * (h->nb + 1) / 2;
+  h->d = d;
+  h->np = np;
+  h->p = d + 3;
+  h->has_rhomat = has_rhomat;
+  const size_t Np = h->Np, mat = Np * Np * sizeof(double);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    free_handle(h);
+    return set_err(GPEDM_ERR_CUDA, "stream creation failed");
+  }
+#define ALLOC(ptr, bytes)                                                                         \
+  do {                                                                                            \
+    cudaError_t e_ = cudaMallocAsync((void**)&(ptr), (bytes), h->stream);                         \
+    if (e_ != cudaSuccess) {                                                                      \
+      free_handle(h);                                                                             \
+      return set_err(GPEDM_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", (size_t)(bytes),       \
+                     cudaGetErrorString(e_));                                                     \
+    }                                                                                             \
+  } while (0)
+  ALLOC(h->dX, (size_t)N * d * 8);
+  ALLOC(h->dY, Np * 8);
+  ALLOC(h->dpop, (size_t)N * 4);
+  if (has_rhomat) ALLOC(h->drhotab, (size_t)np * np * 8);
+  ALLOC(h->bufA, mat);
+  ALLOC(h->bufB, mat);
+  ALLOC(h->bufC, mat);
+  ALLOC(h->dparams, sizeof(EvalParams));
+  ALLOC(h->dz, Np * 8);
+  ALLOC(h->da, Np * 8);
+  ALLOC(h->ddiagS, Np * 8);
+  ALLOC(h->dpart, (size_t)h->nb * Np * 8);
+  ALLOC(h->dlogdet, (size_t)h->nb * 8);
+  ALLOC(h->dtracepart, (size_t)h->ntiles * (MAXD + 3) * 8);
+  ALLOC(h->dscal, NSCAL * 8);
+  ALLOC(h->dinfo, 4);
+  h->num_sms = (device < 64 && g_num_sms[device] > 0) ? g_num_sms[device] : 148;
+#undef ALLOC
+  h->pinned = pinned_acquire();
+  if (!h->pinned) {
+    free_handle(h);
+    return set_err(GPEDM_ERR_CUDA, "pinned host allocation failed");
+  }
+  h->hparams = (EvalParams*)h->pinned;
+  h->hscal = (double*)((char*)h->pinned + ((sizeof(EvalParams) + 15) / 16) * 16);
+  h->hinfo = (int*)(h->hscal + NSCAL);
+  cudaError_t e = cudaMemsetAsync(h->dY, 0, Np * 8, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    e = cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->fill, cudaStreamNonBlocking, lo);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evFill, cudaEventDisableTiming);
+  h->evCol.resize(h->nb / 8 + 1, nullptr);
+  for (size_t i = 0; i < h->evCol.size() && e == cudaSuccess; ++i)
+    e = cudaEventCreateWithFlags(&h->evCol[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming);
+  h->evPanel.resize(h->nb, nullptr);
+  h->evTrail.resize(h->nb, nullptr);
+  for (int i = 0; i < h->nb && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&h->evPanel[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evTrail[i], cudaEventDisableTiming);
+  }
+  for (int i = 0; i <= GPEDM_NPHASE && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  if (e != cudaSuccess) {
+    free_handle(h);
+    return set_err(GPEDM_ERR_CUDA, "handle setup failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return 0;
+}
+
+static int gpedm_create_impl(int device, int64_t N, int32_t d, int32_t np, const double* X, const double* Y,
+                            const int32_t* pop, const double* rhomat, gpedm_handle* out) {
+  if (!out) return set_err(GPEDM_ERR_ARG, "out handle is NULL");
+  *out = nullptr;
+  if (N < 1 || N > (1 << 20)) return set_err(GPEDM_ERR_ARG, "N=%lld out of range", (long long)N);
+  if (np < 1) return set_err(GPEDM_ERR_ARG, "np=%d must be >= 1", np);
+  if (!X || !Y || !pop) return set_err(GPEDM_ERR_ARG, "X, Y and pop must be non-NULL");
+  for (int64_t i = 0; i < N; ++i)
+    if (pop[i] < 0 || pop[i] >= np) return set_err(GPEDM_ERR_ARG, "pop[%lld]=%d outside 0..np-1", (long long)i, pop[i]);
+  gpedm_fit_s* h = nullptr;
+  int rc = alloc_handle(device, N, d, np, rhomat != nullptr, &h);
+  if (rc) return rc;
+  h->hY.assign(Y, Y + N);
+  h->hpop.assign(pop, pop + N);
+  h->single_pop = true;
+  for (int64_t i = 1; i < N; ++i)
+    if (pop[i] != pop[0]) h->single_pop = false;
+  cudaError_t e = cudaMemcpy(h->dX, X, (size_t)N * d * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->dY, Y, (size_t)N * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->dpop, pop, (size_t)N * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && rhomat) e = cudaMemcpy(h->drhotab, rhomat, (size_t)np * np * 8, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    free_handle(h);
+    return set_err(GPEDM_ERR_CUDA, "handle setup failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return 0;
+}
+
+static int gpedm_set_data_impl(gpedm_handle h, const double* X, const double* Y, const int32_t* pop) {
+  if (!h || !X || !Y || !pop) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  for (int64_t i = 0; i < h->N; ++i)
+    if (pop[i] < 0 || pop[i] >= h->np) return set_err(GPEDM_ERR_ARG, "pop[%lld]=%d outside 0..np-1", (long long)i, pop[i]);
+  CU(cudaSetDevice(h->device));
+  h->have_full = false;
+  CU(cudaMemcpyAsync(h->dX, X, (size_t)h->N * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->dY, Y, (size_t)h->N * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->dpop, pop, (size_t)h->N * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->hY.assign(Y, Y + h->N);
+  h->hpop.assign(pop, pop + h->N);
+  h->single_pop = true;
+  for (int64_t i = 1; i < h->N; ++i)
+    if (pop[i] != pop[0]) h->single_pop = false;
+  return 0;
+}
+
+extern "C" int gpedm_destroy(gpedm_handle h) {
+  free_handle(h);
+  return 0;
+}
+extern "C" int64_t gpedm_n(gpedm_handle h) { return h ? h->N : -1; }
+extern "C" int64_t gpedm_launch_count(gpedm_handle h) { return h ? h->launches : -1; }
+extern "C" int gpedm_last_phase_ms(gpedm_handle h, float* ms) {
+  if (!h || !ms) return set_err(GPEDM_ERR_ARG, "NULL argument");
+  memcpy(ms, h->phase_ms, sizeof(h->phase_ms));
+  return 0;
+}
