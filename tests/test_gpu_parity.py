@@ -384,6 +384,18 @@ def test_batch_two_gpus_nccl_gather(gpu_lib):
     two = G.fit_batch(probs, ngpus=2)
     for a, b in zip(one, two):
         assert a["iter"] == b["iter"] and a["nllpost"] == b["nllpost"] and np.array_equal(a["pars"], b["pars"])
+    # the grid entry point (series uploaded once per GPU, device-side preparation) and a batch of
+    # one-tile fits (lockstep kernel, a strided share per GPU) through the same record exchange
+    g1 = G.fit_grid(y, [1, 2, 3], [1, 2], ngpus=1)
+    g2 = G.fit_grid(y, [1, 2, 3], [1, 2], ngpus=2)
+    for a, b in zip(g1, g2):
+        assert (a["E"], a["tau"], a["iter"], a["N"]) == (b["E"], b["tau"], b["iter"], b["N"])
+        assert a["ln_post"] == b["ln_post"] and a["R2_loo"] == b["R2_loo"] and np.array_equal(a["pars"], b["pars"])
+    small, _ = batch.grid_problems(synth.ricker(100, 6), [1, 2, 3], [1, 2])
+    s1 = G.fit_batch(small, ngpus=1, want_loo=True)
+    s2 = G.fit_batch(small, ngpus=2, want_loo=True)
+    for a, b in zip(s1, s2):
+        assert a["iter"] == b["iter"] and a["nllpost"] == b["nllpost"] and np.array_equal(a["loo_mean"], b["loo_mean"])
 
 
 def test_predict_iter_and_getconditionals(gpu_lib, thetalog2pop):
