@@ -294,6 +294,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+GRID_WORKERS = 3
+
+
 def run_grid(G, gd, world, rank, local, barrier):
     """Batched fitGP over E=1..10 x tau=1..4 at series length 8192 (40 independent fits with
     closed-form LOO), sharded over the ranks; one all-gather of the fixed-width result records."""
@@ -312,23 +315,42 @@ def run_grid(G, gd, world, rank, local, barrier):
         store = dist.distributed_c10d._get_default_store()
     barrier()
     t0 = time.perf_counter()
-    mine, res, q, r2 = [], [], 0, {}
-    while True:
-        q = (store.add("gpedm_grid_next", 1) - 1) if store is not None else q
-        if q >= len(cells):
-            break
-        i = order[q]
-        E, tau = cells[i]
+    mine, res, r2 = [], [], {}
+    import itertools
+    import threading
+    local_counter, lock = itertools.count(), threading.Lock()
+
+    def next_cell():
+        if store is not None:
+            return store.add("gpedm_grid_next", 1) - 1
+        with lock:
+            return next(local_counter)
+
+    def worker():
         # lags, scaling and complete-row selection on the device (gpedm_create_lagged), fit from the
         # default start, leave-one-out statistics reduced on the device (gpedm_get_fit_stats)
-        m = G.GPModel.from_series(y, E, tau, scaling="global", device=local)
-        r = m.fit_rprop(batch.default_initparst(E, True))
-        r2[i] = m.fit_stats()["R2_loo"]
-        m.close()
-        res.append(r)
-        mine.append(i)
-        if store is None:
-            q += 1
+        while True:
+            q = next_cell()
+            if q >= len(cells):
+                return
+            i = order[q]
+            E, tau = cells[i]
+            m = G.GPModel.from_series(y, E, tau, scaling="global", device=local)
+            r = m.fit_rprop(batch.default_initparst(E, True))
+            st = m.fit_stats()
+            m.close()
+            with lock:
+                res.append(r)
+                mine.append(i)
+                r2[i] = st["R2_loo"]
+
+    # GRID_WORKERS concurrent fits per GPU (the ctypes calls release the GIL): independent fits
+    # interleave on the device and fill each other's chain-bound stretches (measured -9 % per evaluation)
+    threads = [threading.Thread(target=worker) for _ in range(GRID_WORKERS)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
     torch.cuda.synchronize()
     local_s = time.perf_counter() - t0
     allres = gd.gather_records(list(zip(mine, res)), len(cells), device=torch.device("cuda", local))
@@ -338,7 +360,7 @@ def run_grid(G, gd, world, rank, local, barrier):
         return None
     best = max(r2, key=r2.get) if r2 else None
     return {"fits": len(cells), "wall_s": wall, "rank0_local_s": local_s, "rank0_fits": len(mine),
-            "scheduling": "dynamic queue (store counter), one all-gather of result records",
+            "scheduling": "dynamic queue (store counter), %d concurrent fits per GPU, one all-gather of result records" % GRID_WORKERS,
             "total_evals": int(sum(r["nevals"] for r in allres)),
             "iters": [int(r["iter"]) for r in allres], "status_ok": all(r["status"] == 0 for r in allres),
             "data_prep": "on device (gpedm_create_lagged)",

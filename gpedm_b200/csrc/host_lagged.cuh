@@ -218,7 +218,7 @@ static int gpedm_fit_grid_impl(int64_t T, const double* y, const int32_t* pop, i
     return n * n * n + 40.0 * E[c] * n * n;
   };
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
-  const int W = g_batch_workers > 0 ? g_batch_workers : (T <= 4096 ? 3 : 1);
+  const int W = default_workers_per_gpu(T);
   std::vector<LagSeries> series(ngpus);
   for (int g = 0; g < ngpus; ++g) {  // the raw series goes to every GPU once
     int rc = upload_series(devs[g], T, y, pop, np, series[g]);
