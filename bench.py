@@ -241,6 +241,35 @@ def run_ours(args):
         at_mode = {"value": 1e3 / ms_mode, "unit": UNIT, "ms_per_step": ms_mode, "fit_iter": int(fit["iter"]),
                    "fit_nevals": int(fit["nevals"])}
 
+    # ---- aggregate rate with several independent fits resident on the GPU (what a grid does): the
+    # evaluations of different fits interleave and fill each other's chain-bound stretches
+    concurrent = None
+    if world == 1:
+        import threading
+        others = [G.GPModel(Y, X, device=local) for _ in range(GRID_WORKERS - 1)]
+        models = [model] + others
+        for mdl in others:
+            mdl.likegrad(p0, 1.0, None, None, True)
+        ksteps = max(2, min(args.steps, 5))
+        out_ms = [0.0] * len(models)
+
+        def run(i):
+            out_ms[i] = models[i].bench_evals(p0, 1.0, ksteps)
+
+        torch.cuda.synchronize()
+        tc0 = time.perf_counter()
+        ths = [threading.Thread(target=run, args=(i,)) for i in range(len(models))]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - tc0
+        concurrent = {"fits_resident": len(models), "value": len(models) * ksteps / wall, "unit": UNIT,
+                      "steps_each": ksteps, "wall_s": wall, "device_ms_per_eval_each": out_ms}
+        for mdl in others:
+            mdl.close()
+
     grid = None
     if args.grid:
         grid = run_grid(G, gd, world, rank, local, barrier)
@@ -285,6 +314,8 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clocks, "nll": res["nllpost"]}
         if at_mode is not None:
             line["at_fitted_mode"] = at_mode
+        if concurrent is not None:
+            line["concurrent_fits"] = concurrent
         if grid is not None:
             line["grid"] = grid
         print(json.dumps(line))

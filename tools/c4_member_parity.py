@@ -39,7 +39,7 @@ else:
                oracle_fit_s=o["secs"], gpu_fit_s=g["secs"], iter=[g["iter"], o["iter"]],
                max_mode_err=float(np.max(np.abs(pg - po) / np.maximum(1, np.abs(po)))),
                stats_rel={k: abs(g["stats"][k] - o["stats"][k]) / max(1e-300, abs(o["stats"][k])) for k in keys},
-               predmean_max_abs_err=float(np.max(np.abs(np.array(g["predmean"]) - np.array(o["predmean"])))),
-               predsd_max_rel_err=float(np.max(np.abs(np.array(g["predsd"]) / np.array(o["predsd"]) - 1))))
+               predmean_max_abs_err=float(np.nanmax(np.abs(np.array(g["predmean"]) - np.array(o["predmean"])))),
+               predsd_max_rel_err=float(np.nanmax(np.abs(np.array(g["predsd"]) / np.array(o["predsd"]) - 1))))
     json.dump(rec, open(os.path.join(ROOT, "profiles", "r01_c4_member_parity_vs_oracle.json"), "w"), indent=1)
     print(json.dumps(rec, indent=1))
