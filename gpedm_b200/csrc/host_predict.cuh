@@ -156,6 +156,19 @@ static int leaveout_core(gpedm_fit_s* h, const std::vector<int>& members, const 
   return 0;
 }
 
+// Codes of the time values in order of first appearance (reference: unique(Time), :1142, :1201),
+// in O(N log N) instead of a linear search per row.  Returns the number of distinct values.
+static int time_codes(const double* time, int N, std::vector<int>& tcode) {
+  std::map<double, int> seen;
+  tcode.resize(N);
+  for (int i = 0; i < N; ++i) {
+    auto it = seen.find(time[i]);
+    if (it == seen.end()) it = seen.emplace(time[i], (int)seen.size()).first;
+    tcode[i] = it->second;
+  }
+  return (int)seen.size();
+}
+
 static int gpedm_predict_loo_impl(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary,
                                  double* mean, double* var, double* gpgrad) {
   if (!h || !mean || !var) return set_err(GPEDM_ERR_ARG, "NULL argument");
@@ -198,22 +211,10 @@ static int gpedm_predict_lto_impl(gpedm_handle h, int32_t exclradius, const doub
   for (int i = 0; i < nd; ++i)
     if (primary && !primary[i]) return set_err(GPEDM_ERR_ARG, "primary rows must precede augmentation rows");
   // timevals = unique(Time) in order of first appearance (:1142)
-  std::vector<double> timevals;
-  std::vector<int> tcode(N);
-  for (int i = 0; i < N; ++i) {
-    int c = -1;
-    for (size_t q = 0; q < timevals.size(); ++q)
-      if (timevals[q] == time[i]) {
-        c = (int)q;
-        break;
-      }
-    if (c < 0) {
-      c = (int)timevals.size();
-      timevals.push_back(time[i]);
-    }
-    tcode[i] = c;
-  }
-  const int nt = (int)timevals.size();
+  std::vector<int> tcode;
+  const int nt = time_codes(time, N, tcode);
+  std::vector<std::vector<int>> rows_at(nt);  // rows of each time value, ascending
+  for (int j = 0; j < N; ++j) rows_at[tcode[j]].push_back(j);
   std::vector<int> members, goff(1, 0), focal, fgroup;
   for (int i = 0; i < nd; ++i) {
     mean[i] = NAN;
@@ -222,11 +223,12 @@ static int gpedm_predict_lto_impl(gpedm_handle h, int32_t exclradius, const doub
   std::vector<int> fpos;
   for (int t = 0; t < nt; ++t) {
     int lo = std::max(0, t - exclradius), hi = std::min(nt - 1, t + exclradius);  // :1155-1156
-    for (int j = 0; j < N; ++j)
-      if (tcode[j] >= lo && tcode[j] <= hi) members.push_back(j);  // complement of `train`, :1158
+    const size_t start = members.size();
+    for (int c = lo; c <= hi; ++c) members.insert(members.end(), rows_at[c].begin(), rows_at[c].end());
+    std::sort(members.begin() + start, members.end());  // complement of `train` in row order, :1158
     goff.push_back((int)members.size());
-    for (int j = 0; j < nd; ++j)
-      if (tcode[j] == t) {  // :1157 focal rows among primary
+    for (int j : rows_at[t])
+      if (j < nd) {  // :1157 focal rows among primary
         focal.push_back(j);
         fgroup.push_back(t);
         fpos.push_back(j);
@@ -252,21 +254,8 @@ static int gpedm_predict_sequential_impl(gpedm_handle h, const double* time, dou
   CU(cudaSetDevice(h->device));
   const int N = (int)h->N, d = h->d;
   // time-major stable ordering by order of first appearance of each time value (:1201)
-  std::vector<double> timevals;
-  std::vector<int> tcode(N);
-  for (int i = 0; i < N; ++i) {
-    int c = -1;
-    for (size_t q = 0; q < timevals.size(); ++q)
-      if (timevals[q] == time[i]) {
-        c = (int)q;
-        break;
-      }
-    if (c < 0) {
-      c = (int)timevals.size();
-      timevals.push_back(time[i]);
-    }
-    tcode[i] = c;
-  }
+  std::vector<int> tcode;
+  time_codes(time, N, tcode);
   std::vector<int> perm(N);
   for (int i = 0; i < N; ++i) perm[i] = i;
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return tcode[a] < tcode[b]; });
