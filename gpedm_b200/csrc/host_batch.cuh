@@ -274,9 +274,14 @@ static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_
 // Concurrent fits per GPU.  Independent fits interleave on one device and fill each other's
 // chain-bound stretches: measured at N ~ 8190 (8 grid cells, one B200) 20.18 ms per evaluation with one
 // worker, 18.73 with two, 18.37 with three; memory is 3 N^2 doubles per resident fit.
-static int default_workers_per_gpu(int64_t nmax) {
+// Three concurrent fits stretch every single fit ~2.7x, so with few fits per GPU (the 40-cell grid on 8
+// GPUs) the longest fit would bound the wall time: fewer workers then.
+static int default_workers_per_gpu(int64_t nmax, int nfits, int ngpus) {
   if (g_batch_workers > 0) return g_batch_workers;
-  return nmax <= 12288 ? 3 : (nmax <= 24576 ? 2 : 1);
+  const int by_memory = nmax <= 12288 ? 3 : (nmax <= 24576 ? 2 : 1);
+  const double per_gpu = (double)nfits / std::max(1, ngpus);
+  const int by_count = nmax <= 4096 ? 3 : (per_gpu >= 8 ? 3 : (per_gpu >= 4 ? 2 : 1));
+  return std::min(by_memory, by_count);
 }
 
 // Fixed-width record exchanged by the final all-gather.
@@ -421,14 +426,20 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
   int64_t nmax = 0;
   for (int i : big_order) nmax = std::max<int64_t>(nmax, descs[i].N);
   // small problems leave most of the GPU idle -> interleave several fits; large ones already fill it
-  const int W = default_workers_per_gpu(nmax);
+  const int W = default_workers_per_gpu(nmax, nbig, ngpus);
   std::vector<std::vector<BatchRecord>> per_worker(ngpus * (W + 1));  // slot W of each GPU: the small-fit thread
   std::vector<std::string> werrs(ngpus * (W + 1));
+  // The queue is ordered by descending cost.  The first pick of every worker is static and interleaved
+  // across GPUs (worker w of GPU g takes entry w * ngpus + g) so that the heaviest fits start on
+  // different devices; everything after that is pulled dynamically.
+  next.store(std::min(nbig, ngpus * W));
   auto worker = [&](int g, int w) {
     const int wi = g * (W + 1) + w;
     cudaSetDevice(devs[g]);
+    bool first = true;
     for (;;) {
-      int q = next.fetch_add(1);
+      int q = first ? w * ngpus + g : next.fetch_add(1);
+      first = false;
       if (q >= nbig) break;
       int i = big_order[q];
       BatchRecord rec;

@@ -215,10 +215,12 @@ static int gpedm_fit_grid_impl(int64_t T, const double* y, const int32_t* pop, i
   for (int i = 0; i < ncells; ++i) order[i] = i;
   auto cost = [&](int c) {
     const double n = std::max<double>(1.0, (double)T - (double)E[c] * tau[c]);
-    return n * n * n + 40.0 * E[c] * n * n;
+    // iterations to convergence grow with the number of length scales (measured 27..58 for E <= 7,
+    // up to 105 for E = 8..10 on the Ricker grid): weight the per-evaluation cost accordingly
+    return (n * n * n + 40.0 * E[c] * n * n) * (1.0 + 0.15 * E[c]);
   };
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
-  const int W = default_workers_per_gpu(T);
+  const int W = default_workers_per_gpu(T, ncells, ngpus);
   std::vector<LagSeries> series(ngpus);
   for (int g = 0; g < ngpus; ++g) {  // the raw series goes to every GPU once
     int rc = upload_series(devs[g], T, y, pop, np, series[g]);
@@ -227,11 +229,14 @@ static int gpedm_fit_grid_impl(int64_t T, const double* y, const int32_t* pop, i
   std::atomic<int> next(0);
   std::vector<std::vector<BatchRecord>> per_worker(ngpus * W), per_gpu(ngpus);
   std::vector<std::string> werrs(ngpus * W);
+  next.store(std::min((int)ncells, ngpus * W));  // first picks are static, interleaved across GPUs (see gpedm_fit_batch)
   auto worker = [&](int g, int w) {
     const int wi = g * W + w;
     cudaSetDevice(devs[g]);
+    bool first = true;
     for (;;) {
-      const int q = next.fetch_add(1);
+      const int q = first ? w * ngpus + g : next.fetch_add(1);
+      first = false;
       if (q >= ncells) break;
       const int c = order[q];
       BatchRecord rec;

@@ -8,7 +8,7 @@ y = synth.ricker(8192, 1004)
 Es = [int(a) for a in sys.argv[1:]] or [7, 8, 9, 10]
 for rep in range(2):
     t = time.perf_counter()
-    res = G.fit_grid(y, Es, [1, 2], ngpus=1)
+    res = G.fit_grid(y, Es, [int(t) for t in os.environ.get('TAUS', '1,2').split(',')], ngpus=1)
     wall = time.perf_counter() - t
     ev = sum(r["nevals"] for r in res)
     print(json.dumps(dict(workers=os.environ.get("GPEDM_BATCH_WORKERS_PER_GPU", "default"), rep=rep, cells=len(res), wall_s=round(wall, 3),
