@@ -311,39 +311,69 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
   const unsigned long long tl_t0 = tl_now();
 #endif
 
+  // The tile moves between global and shared memory as its 10 lower 32x32 blocks, two rows per thread
+  // (16-byte accesses).  Nothing reads the part of L_kk above the diagonal blocks (panel / trailing /
+  // inverse kernels take D_kk and the off-diagonal tiles), and the upper part of the D_kk tile in
+  // the X buffer is zeroed once when the handle is created and never written again.
+  auto lower_block_elem = [](int idx, int& r, int& c, bool& on_diag) {
+    const int b = idx >> 9, e = idx & 511;  // block 0..9 (row-major over the lower triangle), 512 row pairs each
+    const int bi = (b >= 6) ? 3 : ((b >= 3) ? 2 : ((b >= 1) ? 1 : 0)), bj = b - bi * (bi + 1) / 2;
+    r = 32 * bi + 2 * (e & 15);
+    c = 32 * bj + (e >> 4);
+    on_diag = bi == bj;
+  };
   DG_TS(0);
-#pragma unroll 8
-  for (int idx = tid; idx < TB * TB; idx += DG_THREADS) {
-    int r = idx & 127, c = idx >> 7;
-    s[r + c * DG_LD] = Akk[(size_t)r + (size_t)c * lda];
+#pragma unroll 5
+  for (int idx = tid; idx < 10 * 512; idx += DG_THREADS) {
+    int r, c;
+    bool dg;
+    lower_block_elem(idx, r, c, dg);
+    *reinterpret_cast<double2*>(&s[r + c * DG_LD]) = *reinterpret_cast<const double2*>(&Akk[(size_t)r + (size_t)c * lda]);
   }
   __syncthreads();
   DG_TS(1);
   diag_cholesky_smem(s, rdiag, dvec, colbuf, kblock, n_valid, info);
   // ---------------- write L, log-determinant part ----------------
-  for (int idx = tid; idx < TB * TB; idx += DG_THREADS) {
-    int r = idx & 127, c = idx >> 7;
-    Akk[(size_t)r + (size_t)c * lda] = (r >= c) ? s[r + c * DG_LD] : 0.0;
+#pragma unroll 5
+  for (int idx = tid; idx < 10 * 512; idx += DG_THREADS) {
+    int r, c;
+    bool dg;
+    lower_block_elem(idx, r, c, dg);
+    double2 v = *reinterpret_cast<const double2*>(&s[r + c * DG_LD]);
+    if (dg) {
+      if (r < c) v.x = 0.0;
+      if (r + 1 < c) v.y = 0.0;
+    }
+    *reinterpret_cast<double2*>(&Akk[(size_t)r + (size_t)c * lda]) = v;
   }
   {
+    // sum of log L_jj over the valid rows: shuffle tree per warp, then the 4 warp partials in order
     double v = 0.0;
     if (tid < TB && kblock * TB + tid < n_valid) v = log(dvec[tid]);
     __syncthreads();
-    if (tid < TB) dvec[tid] = v;
-    __syncthreads();
-    for (int off = 64; off > 0; off >>= 1) {
-      if (tid < off) dvec[tid] += dvec[tid + off];
-      __syncthreads();
+    if (tid < TB) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if ((tid & 31) == 0) dvec[tid >> 5] = v;
     }
-    if (tid == 0) logdet_part[kblock] = dvec[0];
+    __syncthreads();
+    if (tid == 0) logdet_part[kblock] = ((dvec[0] + dvec[1]) + dvec[2]) + dvec[3];
   }
   DG_TS(14);
 
   diag_invert_smem(s, w, rdiag);
   DG_TS(17);
-  for (int idx = tid; idx < TB * TB; idx += DG_THREADS) {
-    int r = idx & 127, c = idx >> 7;
-    Dkk[(size_t)r + (size_t)c * ldd] = (r >= c) ? s[r + c * DG_LD] : 0.0;
+#pragma unroll 5
+  for (int idx = tid; idx < 10 * 512; idx += DG_THREADS) {
+    int r, c;
+    bool dg;
+    lower_block_elem(idx, r, c, dg);
+    double2 v = *reinterpret_cast<const double2*>(&s[r + c * DG_LD]);
+    if (dg) {
+      if (r < c) v.x = 0.0;
+      if (r + 1 < c) v.y = 0.0;
+    }
+    *reinterpret_cast<double2*>(&Dkk[(size_t)r + (size_t)c * ldd]) = v;
   }
   DG_TS(18);
 #ifdef GPEDM_TIMELINE

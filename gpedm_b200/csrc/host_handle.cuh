@@ -260,6 +260,9 @@ static int alloc_handle(int device, int64_t N, int32_t d, int32_t np, bool has_r
   h->hscal = (double*)((char*)h->pinned + ((sizeof(EvalParams) + 15) / 16) * 16);
   h->hinfo = (int*)(h->hscal + NSCAL);
   cudaError_t e = cudaMemsetAsync(h->dY, 0, Np * 8, h->stream);
+  // the X buffer: its diagonal tiles are only ever written on and below the diagonal blocks
+  // (diag_block_kernel), the rest of them must read as zero in the tile products
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->bufB, 0, mat, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e == cudaSuccess) {
     int lo = 0, hi = 0;
