@@ -74,3 +74,27 @@ for k in ("diag (chain)", "panel (chain)", "column updates (chain)"):
     mask = names[k]
     if mask.any():
         print("  %-28s %d CTAs, mean CTA lifetime %.1f us" % (k, int(mask.sum()), float(np.mean((en - st)[mask]))))
+
+# ---- chain view: union of the intervals covered by chain CTAs (diag, panel, aux-stream updates) vs the gaps
+chain = (typ == 100) | (typ == 0) | ((typ == 1) & (tag == 1))
+iv = sorted(zip(st[chain], en[chain]))
+cov, gaps, cur_s, cur_e = 0.0, [], iv[0][0], iv[0][1]
+for a, b in iv[1:]:
+    if a > cur_e:
+        cov += cur_e - cur_s
+        gaps.append(a - cur_e)
+        cur_s, cur_e = a, b
+    else:
+        cur_e = max(cur_e, b)
+cov += cur_e - cur_s
+gaps = np.array(gaps)
+print("\nchain view: first chain CTA starts at %.1f us, last ends at %.1f us; covered by >= 1 chain CTA %.1f us;"
+      " %d gaps with no chain CTA resident, total %.1f us (median %.2f us, max %.1f us)"
+      % (iv[0][0], cur_e, cov, len(gaps), gaps.sum(), float(np.median(gaps)) if len(gaps) else 0.0, gaps.max() if len(gaps) else 0.0))
+big = []
+cur_e = iv[0][1]
+for a, b in iv[1:]:
+    if a > cur_e and a - cur_e >= 15.0:
+        big.append((round(cur_e, 1), round(a - cur_e, 1)))
+    cur_e = max(cur_e, b)
+print("gaps >= 15 us (start us, length us):", big)
