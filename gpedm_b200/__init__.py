@@ -3,6 +3,6 @@ reference's own API names.  All numerics run in libgpedm_b200.so (hand-written C
 include/gpedm.h); there is no CPU fallback."""
 from ._lib import GPEDMError, build, lib  # noqa: F401
 from .core import (GPModel, fmingrad_Rprop, fp64_peak, getcov, getcovinv, getlikegrad, logit)  # noqa: F401
-from .fitgp import (GP, fitGP, getconditionals, getR2, getR2pop, makelags, predict, predict_iter,  # noqa: F401
-                    predict_seq, summary, update)
+from .fitgp import (GP, fitGP, getconditionals, getR2, getR2pop, getrhomatrix, makelags, predict,  # noqa: F401
+                    predict_iter, predict_seq, summary, update)
 from .batch import fit_batch, fit_grid  # noqa: F401

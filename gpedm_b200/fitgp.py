@@ -181,7 +181,7 @@ class GP(dict):
 def fitGP(data=None, y=None, x=None, pop=None, time=None, E=None, tau=None, scaling="global", initpars=None,
           modeprior=1, fixedpars=None, rhofixed=None, rhomatrix=None, rhomatrix_names=None, augdata=None,
           linprior="none", predictmethod=None, newdata=None, xnew=None, popnew=None, timenew=None, ynew=None,
-          returnGPgrad=False, exclradius=0, device=0):
+          returnGPgrad=False, exclradius=0, device=0, _prep_only=False):
     """Fit a GP model (reference fitGP, R/GPfunctions.R:221-520)."""
     call = dict(data=data, y=y, x=x, pop=pop, time=time, E=E, tau=tau, scaling=scaling, initpars=initpars,
                 modeprior=modeprior, fixedpars=fixedpars, rhofixed=rhofixed, rhomatrix=rhomatrix,
@@ -271,6 +271,8 @@ def fitGP(data=None, y=None, x=None, pop=None, time=None, E=None, tau=None, scal
             m = popd == u
             yds[m] = (yd[m] - ymeans[u]) / ysds[u]
             xds[m] = (xd[m] - xmeans[u][None, :]) / xsds[u][None, :]
+    if _prep_only:  # the section getrhomatrix duplicates from fitGP (R/rhomatrix.R:26-160)
+        return dict(yds=yds, xds=xds, popd=popd, timed=timed, primary=primary, up=up, d=d)
     if initpars is None:  # :408-410
         initpars = np.concatenate([np.full(d, 0.1), [0.001, 1 - 0.001, 0.5]])
     initpars = np.array(initpars, dtype=np.float64)
@@ -639,3 +641,44 @@ def summary(obj):
     if "outsampfitstats" in obj:
         lines.append("Out-of-sample R-squared: %.7g" % obj["outsampfitstats"]["R2"])
     return "\n".join(lines)
+
+
+def getrhomatrix(data=None, y=None, x=None, pop=None, time=None, E=None, tau=None, scaling="global",
+                 initpars=None, modeprior=1, fixedpars=None, augdata=None, ngpus=1, devices=None):
+    """Pairwise dynamic-correlation matrix (reference getrhomatrix, R/rhomatrix.R:22-186): the data
+    preparation of fitGP, then a two-population hierarchical fit for every pair of populations
+    (`:169-182`, scaling "none" on the already scaled data) whose rho fills a symmetric matrix with unit
+    diagonal.  The np(np-1)/2 pair fits are independent: ONE `gpedm_fit_batch` call (lockstep
+    one-CTA-per-fit kernel when a pair has <= 128 rows, sharded over `ngpus`).  Returns
+    (rhomatrix, names), directly usable as fitGP(rhomatrix=..., rhomatrix_names=...)."""
+    from .batch import fit_batch
+    pr = fitGP(data=data, y=y, x=x, pop=pop, time=time, E=E, tau=tau, scaling=scaling, augdata=augdata,
+               _prep_only=True)
+    up, d = pr["up"], pr["d"]
+    n_pop = len(up)
+    if n_pop == 1:
+        raise ValueError("There must be more than 1 population to get a pairwise matrix.")
+    ip = np.concatenate([np.full(d, 0.1), [0.001, 1 - 0.001, 0.5]]) if initpars is None else np.array(initpars, dtype=np.float64)
+    if len(ip) != d + 3:
+        raise ValueError("initpars must have number of predictors + 3 entries")
+    fp = np.full(d + 2, np.nan) if fixedpars is None else np.asarray(fixedpars, dtype=np.float64)
+    if len(fp) != d + 2:
+        raise ValueError("Length of fixedpars must be number of predictors + 2 (phi, ve, sigma2)")
+    fi = ~np.isnan(fp)
+    ip[:d + 2][fi] = fp[fi]
+    with np.errstate(divide="ignore"):  # :425-426 (rhomin = 0 in the initial transform; two populations: rho stays free)
+        initparst = np.concatenate([np.log(ip[:d]), [logit(ip[d], VEMIN, VEMAX), logit(ip[d + 1], SIGMA2MIN, SIGMA2MAX),
+                                                     logit(ip[d + 2], 0.0, 1.0)]])
+    complete = ~(np.isnan(pr["yds"]) | np.isnan(pr["xds"]).any(axis=1))  # :446 inside each pair's fitGP
+    pairs, problems = [], []
+    for i in range(n_pop - 1):
+        for j in range(i + 1, n_pop):
+            rows = np.where(((pr["popd"] == up[i]) | (pr["popd"] == up[j])) & complete)[0]
+            pairs.append((i, j))
+            problems.append(dict(Y=pr["yds"][rows], X=pr["xds"][rows], pop=pr["popd"][rows], initparst=initparst,
+                                 fixedpars=None if fixedpars is None else fp, modeprior=float(modeprior)))
+    res = fit_batch(problems, ngpus=ngpus, devices=devices)
+    rhomat = np.zeros((n_pop, n_pop))
+    for (i, j), r in zip(pairs, res):
+        rhomat[i, j] = r["pars"][d + 2]
+    return rhomat + rhomat.T + np.eye(n_pop), list(up)

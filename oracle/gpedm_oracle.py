@@ -420,7 +420,7 @@ def _as_matrix(data, keys):
 def fitGP(data=None, y=None, x=None, pop=None, time=None, E=None, tau=None, scaling="global",
           initpars=None, modeprior=1, fixedpars=None, rhofixed=None, rhomatrix=None,
           rhomatrix_names=None, augdata=None, predictmethod=None, newdata=None, xnew=None,
-          popnew=None, timenew=None, ynew=None, returnGPgrad=False, exclradius=0):
+          popnew=None, timenew=None, ynew=None, returnGPgrad=False, exclradius=0, _prep_only=False):
     """R/GPfunctions.R:221-520 (linprior not restated: it only pre-processes y with lm())."""
     if (E is None) != (tau is None):
         raise ValueError("Both E and tau must be supplied if generating lags internally.")
@@ -508,6 +508,8 @@ def fitGP(data=None, y=None, x=None, pop=None, time=None, E=None, tau=None, scal
             xds[m] = (xd[m] - xmeans[u][None, :]) / xsds[u][None, :]
     else:
         raise ValueError("scaling must be one of global, local, none")
+    if _prep_only:  # the section getrhomatrix duplicates from fitGP (R/rhomatrix.R:26-160)
+        return dict(yds=yds, xds=xds, popd=popd, timed=timed, primary=primary, up=up, d=d)
     if initpars is None:  # :408-410
         initpars = np.concatenate([np.full(d, 0.1), [0.001, 1 - 0.001, 0.5]])
     initpars = np.array(initpars, dtype=np.float64)
@@ -909,3 +911,25 @@ def loglik_ld(phi, sigma2, rho, ve, X, Y, Pop, rhomat=None, rhomat_names=None):
     Linv = solve_lower_ld(L, np.eye(N, dtype=ld))
     dinv = np.sum(Linv * Linv, axis=0)
     return like, a, dinv
+
+
+def getrhomatrix(data=None, y=None, x=None, pop=None, time=None, E=None, tau=None, scaling="global",
+                 initpars=None, modeprior=1, fixedpars=None, augdata=None):
+    """R/rhomatrix.R:22-186: the data preparation of fitGP, then one two-population fit per pair of
+    populations (scaling "none" on the already scaled data, :169-182); rho of pair (i, j) fills a
+    symmetric matrix with unit diagonal.  Returns (rhomatrix, names)."""
+    pr = fitGP(data=data, y=y, x=x, pop=pop, time=time, E=E, tau=tau, scaling=scaling, augdata=augdata,
+               _prep_only=True)
+    up = pr["up"]
+    n_pop = len(up)
+    if n_pop == 1:
+        raise ValueError("There must be more than 1 population to get a pairwise matrix.")
+    rhomat = np.zeros((n_pop, n_pop))
+    for i in range(n_pop - 1):
+        for j in range(i + 1, n_pop):
+            ind = np.where((pr["popd"] == up[i]) | (pr["popd"] == up[j]))[0]
+            fit = fitGP(y=pr["yds"][ind], x=pr["xds"][ind], pop=pr["popd"][ind], time=pr["timed"][ind],
+                        scaling="none", initpars=None if initpars is None else np.array(initpars, dtype=np.float64),
+                        modeprior=modeprior, fixedpars=fixedpars)
+            rhomat[i, j] = fit["pars"][pr["d"] + 2]
+    return rhomat + rhomat.T + np.eye(n_pop), list(up)

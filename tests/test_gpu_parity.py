@@ -670,3 +670,26 @@ def test_fit_grid_device_prep_equals_host_prep(gpu_lib):
         assert np.max(np.abs(a["pars"] - b["pars"]) / np.maximum(1, np.abs(b["pars"]))) <= 1e-8
         assert a["R2_loo"] == pytest.approx(b["R2_loo"], rel=1e-9)
         assert a["R2_insample"] == pytest.approx(b["R2_insample"], rel=1e-9)
+
+
+def test_getrhomatrix_vs_oracle(gpu_lib, thetalog2pop):
+    """getrhomatrix: all pair fits in one gpedm_fit_batch call (one-CTA-per-fit kernel for pairs with <= 128
+    rows) against the oracle's loop of two-population fitGP calls (R/rhomatrix.R:169-182), plus the K1 pin."""
+    R, names = G.getrhomatrix(thetalog2pop, y="Abundance", pop="Population", E=3, tau=1, scaling="local")
+    assert names == ["PopA", "PopB"] and round(R[0, 1], 6) == 0.327254 and R[0, 1] == R[1, 0]   # README.md:86
+    rng = np.random.default_rng(12)
+    ys, pops = [], []
+    for k, theta in enumerate([1.0, 2.5, 2.6, 4.0]):
+        ys.append(synth.thetalogistic(60 + 20 * k, 40 + k, theta=theta))   # pairs of 120..200 rows: both batch paths
+        pops += ["site%d" % k] * (60 + 20 * k)
+    data = dict(y=np.concatenate(ys), pop=np.asarray(pops, dtype=object))
+    Ro, no = O.getrhomatrix(data, y="y", pop="pop", E=2, tau=1, scaling="local", fixedpars=[np.nan, np.nan, 0.01, np.nan])
+    Rg, ng = G.getrhomatrix(data, y="y", pop="pop", E=2, tau=1, scaling="local", fixedpars=[np.nan, np.nan, 0.01, np.nan])
+    assert ng == no and np.array_equal(Rg, Rg.T) and np.all(np.diag(Rg) == 1.0)
+    assert np.max(np.abs(Rg - Ro)) <= TOL_MODE
+    # and the matrix plugs back into fitGP as the reference intends (vignettes/hierarchical.Rmd:180-190)
+    g = G.fitGP(data, y="y", pop="pop", E=2, tau=1, scaling="local", rhomatrix=Rg, rhomatrix_names=ng)
+    o = O.fitGP(data, y="y", pop="pop", E=2, tau=1, scaling="local", rhomatrix=Ro, rhomatrix_names=no)
+    assert g["iter"] == o["iter"]
+    assert np.max(np.abs(g["pars"] - o["pars"]) / np.maximum(1, np.abs(o["pars"]))) <= TOL_MODE
+    g.close()

@@ -153,3 +153,12 @@ def test_K4_predict_iter_readme_444_456(thetalog2pop):
         assert digits(got, ref, 7), (got, ref)
     for got, ref in zip(r["predsd"], want_sd):
         assert digits(got, ref, 7), (got, ref)
+
+
+def test_getrhomatrix_pair_equals_K1_rho(thetalog2pop):
+    """getrhomatrix (R/rhomatrix.R:22-186) on the two-population README data is ONE pair fit on the
+    locally scaled data, i.e. the K1 model: its off-diagonal must be the README's rho (README.md:86)."""
+    R, names = O.getrhomatrix(thetalog2pop, y="Abundance", pop="Population", E=3, tau=1, scaling="local")
+    assert names == ["PopA", "PopB"] and R.shape == (2, 2)
+    assert R[0, 0] == R[1, 1] == 1.0 and R[0, 1] == R[1, 0]
+    assert round(R[0, 1], 6) == 0.327254
