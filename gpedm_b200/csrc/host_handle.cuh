@@ -60,6 +60,9 @@ static const bool g_no_half_tiles = getenv("GPEDM_NO_HALF_TILES") != nullptr && 
 static const int g_fill_tail = getenv("GPEDM_FILL_TAIL") ? atoi(getenv("GPEDM_FILL_TAIL")) : 40;
 static const bool g_no_small_batch = getenv("GPEDM_NO_SMALL_BATCH") != nullptr && atoi(getenv("GPEDM_NO_SMALL_BATCH")) != 0;
 static const bool g_no_fill = getenv("GPEDM_NO_FILL") != nullptr && atoi(getenv("GPEDM_NO_FILL")) != 0;
+// 32-row strips are used on the chain when (tiles x 4 strips) <= (factor / 2) x SMs; factors in halves
+static const int g_split_update2 = getenv("GPEDM_SPLIT_UPDATE2") ? atoi(getenv("GPEDM_SPLIT_UPDATE2")) : 4;
+static const int g_split_panel2 = getenv("GPEDM_SPLIT_PANEL2") ? atoi(getenv("GPEDM_SPLIT_PANEL2")) : 4;
 static const bool g_no_split = getenv("GPEDM_NO_SPLIT") != nullptr && atoi(getenv("GPEDM_NO_SPLIT")) != 0;
 static const int g_graph_max_nb = getenv("GPEDM_GRAPH_MAX_NB") ? atoi(getenv("GPEDM_GRAPH_MAX_NB")) : 48;
 static const int g_batch_workers = getenv("GPEDM_BATCH_WORKERS_PER_GPU") ? atoi(getenv("GPEDM_BATCH_WORKERS_PER_GPU")) : 0;

@@ -153,7 +153,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
       t.jlo = jlo;
       t.P2 = h->bufA;
       t.ld2 = ld;
-      return launch_tiles(h, s_, t, 0, s_ == ax && !g_no_split && ntl * 4 <= 2 * h->num_sms);
+      return launch_tiles(h, s_, t, 0, s_ == ax && !g_no_split && ntl * 4 * 2 <= g_split_update2 * h->num_sms);
     };
     // group size: GPEDM_POTRF_GROUP if set, else 4 from 64 block columns up (bulk-dominated; measured
     // 20.46 -> 20.15 ms at N=8192 together with group_min 16 / fill_tail 40), 2 below (4.07 vs 4.17 ms at N=4096)
@@ -190,7 +190,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
           pan.P1 = h->bufB;
           pan.P2 = h->bufA;
           pan.ld1 = pan.ld2 = ld;
-          int rc = launch_tiles(h, ax, pan, 0, !g_no_split && pan.ntiles * 4 <= 2 * h->num_sms);
+          int rc = launch_tiles(h, ax, pan, 0, !g_no_split && pan.ntiles * 4 * 2 <= g_split_panel2 * h->num_sms);
           if (rc) return rc;
         }
       }
