@@ -278,10 +278,16 @@ static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_
 // GPUs) the longest fit would bound the wall time: fewer workers then.
 static int default_workers_per_gpu(int64_t nmax, int nfits, int ngpus) {
   if (g_batch_workers > 0) return g_batch_workers;
-  const int by_memory = nmax <= 12288 ? 3 : (nmax <= 24576 ? 2 : 1);
-  const double per_gpu = (double)nfits / std::max(1, ngpus);
-  const int by_count = nmax <= 4096 ? 3 : (per_gpu >= 8 ? 3 : (per_gpu >= 4 ? 2 : 1));
-  return std::min(by_memory, by_count);
+  // The smaller the fits, the less of the GPU one evaluation fills and the more of them interleave
+  // (measured aggregate evaluations/s on one B200, `tools/mid_batch_bench.py`: N~325: 2.3 k with one
+  // worker, 6.4 k with 3, 10.8 k with 12; N~1025: 2.9 k with 3, 4.2 k with 8; N~2040: 1.76 k with 6;
+  // N~4090: 279 with 3, 338 with 5; N~8190: 49.6 / 53.4 / 54.4 with 1 / 2 / 3).
+  int w = nmax <= 640 ? 12 : nmax <= 1536 ? 8 : nmax <= 3072 ? 6 : nmax <= 6144 ? 5 : nmax <= 12288 ? 3 : nmax <= 24576 ? 2 : 1;
+  if (nmax > 6144) {  // large fits: also bound the stretch of the longest fit (see above)
+    const double per_gpu = (double)nfits / std::max(1, ngpus);
+    w = std::min(w, per_gpu >= 8 ? 3 : (per_gpu >= 4 ? 2 : 1));
+  }
+  return std::max(1, std::min(w, nfits));
 }
 
 // Fixed-width record exchanged by the final all-gather.
