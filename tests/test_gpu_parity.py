@@ -42,8 +42,9 @@ def make_case(seed, N, d, npop):
 
 
 # ------------------------------------------------------------------ getlikegrad
-@pytest.mark.parametrize("N,d,npop", [(2, 1, 1), (94, 3, 2), (128, 2, 1), (129, 4, 2), (300, 4, 1), (700, 5, 3),
-                                       (1000, 10, 1), (1301, 32, 5)])
+@pytest.mark.parametrize("N,d,npop", [(1, 1, 1), (2, 1, 1), (94, 3, 2), (127, 3, 2), (128, 2, 1), (129, 4, 2), (255, 3, 2),
+                                       (256, 5, 1), (257, 2, 3), (300, 4, 1), (512, 8, 2), (641, 6, 4), (700, 5, 3),
+                                       (1000, 10, 1), (1301, 32, 5), (2049, 16, 2)])
 def test_likegrad_parity(gpu_lib, N, d, npop):
     Y, X, pop, parst = make_case(N + d, N, d, npop)
     ref = oracle_eval(parst, Y, X, pop)
