@@ -694,3 +694,32 @@ def test_getrhomatrix_vs_oracle(gpu_lib, thetalog2pop):
     assert g["iter"] == o["iter"]
     assert np.max(np.abs(g["pars"] - o["pars"]) / np.maximum(1, np.abs(o["pars"]))) <= TOL_MODE
     g.close()
+
+
+@pytest.mark.parametrize("N,M,d,npop,use_rhomat", [(130, 1, 2, 1, False), (257, 129, 3, 2, False), (500, 260, 4, 3, True),
+                                                   (700, 300, 5, 3, False)])
+def test_predict_new_parity_shapes(gpu_lib, N, M, d, npop, use_rhomat):
+    """predict.GP newdata block + getGPgrad (R/GPfunctions.R:1012-1036, :1863-1865) at sizes straddling the
+    128-tiles, with several populations and a pairwise rho matrix: mean and GP gradient against the FP64
+    oracle, variance against the extended-precision oracle (the reference's own formula loses digits)."""
+    Y, X, pop, parst = make_case(100 + N, N, d, npop)
+    rng = np.random.default_rng(N)
+    Xn = rng.standard_normal((M, d))
+    popn = rng.integers(0, npop, M)
+    R = names = None
+    if use_rhomat:
+        R = np.array([[1, .3, .6], [.3, 1, .2], [.6, .2, 1.]])
+        names = [0, 1, 2]
+    ref = oracle_eval(parst, Y, X, pop, rhomatrix=R, names=names)
+    phi, ve, s2, rho = ref["pars"][:d], ref["pars"][d], ref["pars"][d + 1], ref["pars"][d + 2]
+    om, ov, og = O.predict_newdata_core(phi, s2, rho, ve, X, Y, pop, ref["covm"]["iKVs"], Xn, popn, R, names, d > 1)
+    tm, tv = O.predict_newdata_ld(phi, s2, rho, ve, X, Y, pop, Xn, popn, R, names)
+    m = G.GPModel(Y, X, pop, R, names)
+    m.likegrad(parst, 1, None, None, returngradonly=False)
+    gm, gv, gg = m.predict_new(Xn, popn, d > 1)
+    assert np.max(np.abs(gm - om)) <= TOL_MEAN
+    fsd_t, fsd_g = np.sqrt(np.asarray(tv, dtype=float)), np.sqrt(gv)
+    assert np.max(np.abs(fsd_g - fsd_t) / fsd_t) <= TOL_FSD
+    if d > 1:
+        assert np.max(np.abs(gg - og)) <= 1e-8 * max(1.0, np.max(np.abs(og)))
+    m.close()
