@@ -77,7 +77,7 @@ EXPORTS = [
     "gpedm_abi_version", "gpedm_last_error", "gpedm_device_count", "gpedm_default_rprop_options",
     "gpedm_create", "gpedm_set_data", "gpedm_destroy", "gpedm_n", "gpedm_likegrad", "gpedm_fit_rprop", "gpedm_get_vector",
     "gpedm_get_matrix", "gpedm_getcov", "gpedm_covinv", "gpedm_predict_new", "gpedm_predict_loo", "gpedm_predict_lto",
-    "gpedm_predict_sequential", "gpedm_fit_batch", "gpedm_create_lagged", "gpedm_lagged_info",
+    "gpedm_predict_sequential", "gpedm_fit_batch", "gpedm_last_gather_status", "gpedm_create_lagged", "gpedm_lagged_info",
     "gpedm_get_fit_stats", "gpedm_fit_grid", "gpedm_last_phase_ms", "gpedm_launch_count",
     "gpedm_fp64_peak", "gpedm_bench_evals",
 ]

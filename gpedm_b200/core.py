@@ -33,12 +33,17 @@ def unique_stable(v):
     return out
 
 
-def pop_codes(pop, levels=None):
-    """Population labels -> int32 codes 0..np-1 in order of first appearance (or given levels)."""
+def pop_codes(pop, levels=None, unseen_ok=False):
+    """Population labels -> int32 codes 0..np-1 in order of first appearance (or given levels).
+    unseen_ok: labels absent from `levels` (new-data populations the model was not trained on) get the
+    sentinel code np, which getcov treats as the reference does (R/GPfunctions.R:796-811): popsame = 0
+    against every training row, i.e. the rho cross-covariance, or 1 under a rhomatrix."""
     pop = np.asarray(pop, dtype=object)
     if levels is None:
         levels = unique_stable(pop)
     lut = {u: i for i, u in enumerate(levels)}
+    if unseen_ok:
+        return np.array([lut.get(p, len(levels)) for p in pop], dtype=np.int32), list(levels)
     try:
         codes = np.array([lut[p] for p in pop], dtype=np.int32)
     except KeyError as e:
@@ -199,7 +204,7 @@ class GPModel:
         M = Xnew.shape[0]
         if Xnew.shape[1] != self.d:
             raise ValueError("Xnew must have %d columns" % self.d)
-        codes = np.zeros(M, dtype=np.int32) if popnew is None else pop_codes(popnew, self.levels)[0]
+        codes = np.zeros(M, dtype=np.int32) if popnew is None else pop_codes(popnew, self.levels, unseen_ok=True)[0]
         mean, var = np.empty(M), np.empty(M)
         grad = np.empty((M, self.d), order="F") if returnGPgrad else None
         check(lib().gpedm_predict_new(self._h, M, dptr(Xnew), iptr(codes), dptr(mean), dptr(var), dptr(grad)))
@@ -260,7 +265,7 @@ def getcov(phi, sigma2, rho, X, X2, pop, pop2, rhomat=None, rhomat_names=None, d
     X, X2 = f64(X), f64(X2)
     phi = f64(phi).ravel()
     codes, levels = pop_codes(pop)
-    codes2, _ = pop_codes(pop2, levels)
+    codes2, _ = pop_codes(pop2, levels, unseen_ok=True)
     R = _rhomat_in_code_order(rhomat, rhomat_names, levels)
     N, M = X.shape[0], X2.shape[0]
     Cd = np.empty((M, N), order="F")

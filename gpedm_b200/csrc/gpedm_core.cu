@@ -4,6 +4,7 @@
 // (:522-584) run on the host; everything that touches N x N data runs in the kernels of
 // kernels.cuh.  There is no CPU fallback for any N^2 / N^3 step.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler injects itself
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
@@ -47,11 +48,13 @@ extern "C" int gpedm_fp64_peak(int device, int which, double* tflops) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   const int nsm = prop.multiProcessorCount;
-  double* dout = nullptr;
-  CU(cudaMalloc((void**)&dout, (size_t)nsm * 4 * 256 * 8));
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0));
-  CU(cudaEventCreate(&e1));
+  DevBuf dbuf;
+  CU(dbuf.alloc((size_t)nsm * 4 * 256 * 8));
+  double* dout = (double*)dbuf.p;
+  EventGuard g0, g1;
+  CU(g0.create());
+  CU(g1.create());
+  cudaEvent_t e0 = g0.e, e1 = g1.e;
   float best = 1e30f;
   const int iters = which == 0 ? 4000 : 20000;
   const int ctas = which == 0 ? nsm : nsm * 4;
@@ -70,9 +73,6 @@ extern "C" int gpedm_fp64_peak(int device, int which, double* tflops) {
   CU(cudaGetLastError());
   double fl = which == 0 ? (double)ctas * 8 * 32.0 * iters * 512.0 : (double)ctas * 256 * 16.0 * iters * 2.0;
   *tflops = fl / best * 1e-9;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(dout);
   return 0;
 }
 
@@ -83,9 +83,10 @@ extern "C" int gpedm_bench_evals(gpedm_handle h, const double* parst, double mod
   host_transform(h, parst, modeprior, nullptr, NAN, hp);
   fill_params(h, hp);
   h->have_full = false;
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0));
-  CU(cudaEventCreate(&e1));
+  EventGuard g0, g1;
+  CU(g0.create());
+  CU(g1.create());
+  cudaEvent_t e0 = g0.e, e1 = g1.e;
   CU(cudaEventRecord(e0, h->stream));
   for (int s = 0; s < steps; ++s) {
     int rc = enqueue_eval(h, false);
@@ -97,8 +98,6 @@ extern "C" int gpedm_bench_evals(gpedm_handle h, const double* parst, double mod
   float ms;
   CU(cudaEventElapsedTime(&ms, e0, e1));
   *ms_per_eval = ms / steps;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   collect_phase_times(h);
   if (*h->hinfo > 0) return set_err(*h->hinfo, "covariance matrix not positive definite at row %d", *h->hinfo);
   return 0;
@@ -160,6 +159,8 @@ extern "C" int gpedm_predict_sequential(gpedm_handle h, const double* time, doub
 extern "C" int gpedm_fit_batch(int32_t nfits, const gpedm_fit_desc* descs, int32_t ngpus, const int32_t* devices, const gpedm_rprop_options* opts, gpedm_result* results) {
   GPEDM_GUARDED(gpedm_fit_batch_impl(nfits, descs, ngpus, devices, opts, results));
 }
+
+extern "C" int gpedm_last_gather_status(void) { return g_last_gather_status.load(); }
 
 extern "C" int gpedm_create_lagged(int device, int64_t T, const double* y, const int32_t* pop, int32_t np, int32_t E,
                                    int32_t tau, int32_t scaling, const double* rhomat, gpedm_handle* out) {

@@ -54,3 +54,18 @@ struct PinnedBuf {
   ~PinnedBuf() { if (p) cudaFreeHost(p); }
   cudaError_t alloc(size_t bytes) { return cudaMallocHost(&p, std::max<size_t>(bytes, 16)); }
 };
+struct EventGuard {
+  cudaEvent_t e = nullptr;
+  cudaError_t create() { return cudaEventCreate(&e); }
+  ~EventGuard() { if (e) cudaEventDestroy(e); }
+};
+// NVTX phase ranges: host-side ranges around the enqueue of each phase of an
+// evaluation and around the public entry points; profilers attribute the launches inside to them.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  static void next(const char* name) {  // close the current phase, open the next
+    nvtxRangePop();
+    nvtxRangePushA(name);
+  }
+};

@@ -158,6 +158,7 @@ static inline double sgn(double x) { return (x > 0) - (x < 0); }
 
 extern "C" int gpedm_fit_rprop(gpedm_handle h, const double* initparst, double modeprior, const double* fixedpars,
                                double rhofixed, const gpedm_rprop_options* opts, gpedm_result* out) {
+  NvtxRange nvtx_entry("gpedm:fit_rprop");
   if (!h || !initparst || !out) return set_err(GPEDM_ERR_ARG, "NULL argument");
   gpedm_rprop_options o;
   if (opts)
@@ -286,7 +287,11 @@ static int gpedm_getcov_impl(int device, int32_t d, const double* phi, double si
                             const double* X, const int32_t* pop, int64_t M, const double* X2, const int32_t* pop2,
                             int32_t np, const double* rhomat, double* Cd_out) {
   if (!phi || !X || !pop || !X2 || !pop2 || !Cd_out) return set_err(GPEDM_ERR_ARG, "NULL argument");
-  if (d < 1 || d > GPEDM_MAX_D || N < 1 || M < 1) return set_err(GPEDM_ERR_ARG, "bad sizes");
+  if (d < 1 || d > GPEDM_MAX_D || N < 1 || M < 1 || np < 1) return set_err(GPEDM_ERR_ARG, "bad sizes");
+  for (int64_t i = 0; i < N; ++i)
+    if (pop[i] < 0 || pop[i] >= np) return set_err(GPEDM_ERR_ARG, "pop[%lld] outside 0..np-1", (long long)i);
+  for (int64_t i = 0; i < M; ++i)  // code np = a population that does not occur in `pop` (:796-811)
+    if (pop2[i] < 0 || pop2[i] > np) return set_err(GPEDM_ERR_ARG, "pop2[%lld] outside 0..np", (long long)i);
   int ndev = gpedm_device_count();
   if (ndev == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available (libgpedm_b200 has no CPU fallback)");
   CU(cudaSetDevice(device));

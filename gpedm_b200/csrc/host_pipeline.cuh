@@ -118,6 +118,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   cudaStream_t st = h->stream;
   const int nb = h->nb, Np = h->Np, N = (int)h->N, d = h->d;
   const size_t ld = Np;
+  NvtxRange nvtx_phase("gpedm:assemble");
   CU(cudaMemcpyAsync(h->dparams, h->hparams, sizeof(EvalParams), cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(h->dinfo, 0, 4, st));
   CU(record_phase_event(h->ev[0], st));
@@ -131,6 +132,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     h->launches++;
   }
   CU(record_phase_event(h->ev[1], st));
+  NvtxRange::next("gpedm:potrf");
   // --- Cholesky, right-looking over 128-wide block columns, with look-ahead and grouped updates.
   // Steps are processed in groups [g0, g1) of G block columns (G = GPEDM_POTRF_GROUP while the
   // trailing matrix is large, 1 near the end); [g1, g2) is the next group.
@@ -228,6 +230,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     }
   }
   CU(record_phase_event(h->ev[2], st));
+  NvtxRange::next("gpedm:trtri");
   // --- triangular inverse X = L^-1 by recursive doubling (diagonal blocks already in bufB): whatever the
   // fill stream has not done yet, level by level
   {
@@ -235,6 +238,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     if (rc) return rc;
   }
   CU(record_phase_event(h->ev[3], st));
+  NvtxRange::next("gpedm:vec");
   // --- z = X Y
   trmv_n_part_kernel<<<h->ntiles, 256, 0, st>>>(h->bufB, ld, h->dY, h->dpart, ld);
   reduce_parts_kernel<<<ceil_div(Np, 256), 256, 0, st>>>(h->dpart, ld, nb, 0, h->dz, Np);
@@ -249,6 +253,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   reduce_parts_kernel<<<ceil_div(Np, 256), 256, 0, st>>>(h->dpart, ld, nb, 1, h->da, Np);
   h->launches += 2;
   CU(record_phase_event(h->ev[4], st));
+  NvtxRange::next("gpedm:lauum");
   // --- S = Sigma^-1 = X^T X (lower tiles) into bufC
   {
     TileOp lu = make_op(OP_LAUUM, h->ntiles, nb);
@@ -259,6 +264,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     if (rc) return rc;
   }
   CU(record_phase_event(h->ev[5], st));
+  NvtxRange::next("gpedm:trace");
   // --- gradient trace terms + scalar reductions
   {
     int DC = d <= 8 ? 8 : (d <= 16 ? 16 : 32);

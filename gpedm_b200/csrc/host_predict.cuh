@@ -5,11 +5,13 @@
 // ------------------------------------------------------------------------------- prediction
 static int gpedm_predict_new_impl(gpedm_handle h, int64_t M, const double* Xnew, const int32_t* popnew, double* mean,
                                  double* var, double* gpgrad) {
+  NvtxRange nvtx_entry("gpedm:predict_new");
   if (!h || !Xnew || !popnew || !mean || !var) return set_err(GPEDM_ERR_ARG, "NULL argument");
   if (M < 1) return set_err(GPEDM_ERR_ARG, "M must be >= 1");
   if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
   for (int64_t i = 0; i < M; ++i)
-    if (popnew[i] < 0 || popnew[i] >= h->np) return set_err(GPEDM_ERR_ARG, "popnew[%lld] outside 0..np-1", (long long)i);
+    if (popnew[i] < 0 || popnew[i] > h->np)  // code np = a population not present in the training set
+      return set_err(GPEDM_ERR_ARG, "popnew[%lld] outside 0..np", (long long)i);
   CU(cudaSetDevice(h->device));
   const int d = h->d;
   const int64_t CH = 4096;  // new points per chunk
@@ -171,6 +173,7 @@ static int time_codes(const double* time, int N, std::vector<int>& tcode) {
 
 static int gpedm_predict_loo_impl(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary,
                                  double* mean, double* var, double* gpgrad) {
+  NvtxRange nvtx_entry("gpedm:predict_loo");
   if (!h || !mean || !var) return set_err(GPEDM_ERR_ARG, "NULL argument");
   if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
   if (exclradius < 0) return set_err(GPEDM_ERR_ARG, "exclradius must be >= 0");
@@ -202,6 +205,7 @@ static int gpedm_predict_loo_impl(gpedm_handle h, int32_t exclradius, const doub
 
 static int gpedm_predict_lto_impl(gpedm_handle h, int32_t exclradius, const double* time, const int32_t* primary,
                                  double* mean, double* var, double* gpgrad) {
+  NvtxRange nvtx_entry("gpedm:predict_lto");
   if (!h || !mean || !var || !time) return set_err(GPEDM_ERR_ARG, "NULL argument (time is required)");
   if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
   if (exclradius < 0) return set_err(GPEDM_ERR_ARG, "exclradius must be >= 0");
@@ -249,6 +253,7 @@ static int gpedm_predict_lto_impl(gpedm_handle h, int32_t exclradius, const doub
 }
 
 static int gpedm_predict_sequential_impl(gpedm_handle h, const double* time, double* ymean, double* ysd2) {
+  NvtxRange nvtx_entry("gpedm:predict_sequential");
   if (!h || !time || !ymean || !ysd2) return set_err(GPEDM_ERR_ARG, "NULL argument");
   if (!h->have_full) return set_err(GPEDM_ERR_STATE, "no full evaluation resident");
   CU(cudaSetDevice(h->device));

@@ -35,10 +35,13 @@ __device__ __forceinline__ double cov_entry(const double* xi, const double* xj, 
     dist = __dadd_rn(dist, __dmul_rn(diff, diff));
   }
   double v = __dmul_rn(sigma2, exp(-dist));
-  if (rhotab != nullptr)
-    v = __dmul_rn(v, rhotab[pi + pj * np]);
-  else if (pi != pj)
-    v = __dmul_rn(v, rho);
+  if (rhotab != nullptr) {
+    // a new point of a population absent from the training set carries code np: the reference's Rmat
+    // loop (:799-808) only visits training populations, so its entries keep the initial 1
+    if (pi < np) v = __dmul_rn(v, rhotab[pi + pj * np]);
+  } else if (pi != pj) {
+    v = __dmul_rn(v, rho);  // code np never equals a training code: popsame = 0, the rho branch (:811)
+  }
   return v;
 }
 

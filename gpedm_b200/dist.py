@@ -40,18 +40,37 @@ def unpack_record(rec):
 
 
 def gather_records(local, nfits, device=None):
-    """All-gather (one collective) of each rank's result records.  local: list of (index, result dict).
+    """All-gather of each rank's result records.  local: list of (index, result dict).
     Returns the list of nfits result dicts on every rank.  Works with any initialised
-    torch.distributed backend; without an initialised process group it is the identity."""
+    torch.distributed backend; without an initialised process group it is the identity.
+
+    The ranks may hold ANY split of the fits (a dynamic work queue hands short fits to whichever rank
+    is free, so one rank can finish far more than nfits/world of them): the per-rank record counts are
+    exchanged first and the record slab is sized to the largest of them.  Every fit must be reported by
+    exactly one rank; a missing or duplicated index raises instead of returning a hole."""
     import torch
     import torch.distributed as dist
+    for i, _ in local:
+        if not 0 <= i < nfits:
+            raise ValueError("gather_records: fit index %d outside 0..%d" % (i, nfits - 1))
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         out = [None] * nfits
         for i, r in local:
+            if out[i] is not None:
+                raise ValueError("gather_records: fit %d reported twice" % i)
             out[i] = r
+        _check_complete(out)
         return out
     world = dist.get_world_size()
-    slab = (nfits + world - 1) // world + 1
+    cnt = torch.tensor([len(local)], dtype=torch.int64)
+    if device is not None:
+        cnt = cnt.to(device)
+    counts = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    if sum(counts) != nfits:
+        raise RuntimeError("gather_records: ranks hold %s records, expected %d in total" % (counts, nfits))
+    slab = max(1, max(counts))
     buf = np.full((slab, RECORD_WIDTH + 1), np.nan)
     buf[:, 0] = -1
     for q, (i, r) in enumerate(local):
@@ -62,9 +81,42 @@ def gather_records(local, nfits, device=None):
     allt = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(allt, t)
     out = [None] * nfits
-    for part in allt:
-        for rec in part.cpu().numpy():
-            if rec[0] >= 0:
-                i, r = unpack_record(rec)
-                out[i] = r
+    for part, n in zip(allt, counts):
+        for rec in part.cpu().numpy()[:n]:
+            i, r = unpack_record(rec)
+            if out[i] is not None:
+                raise RuntimeError("gather_records: fit %d reported by two ranks" % i)
+            out[i] = r
+    _check_complete(out)
     return out
+
+
+def _check_complete(out):
+    missing = [i for i, r in enumerate(out) if r is None]
+    if missing:
+        raise RuntimeError("gather_records: no rank reported fits %s" % missing)
+
+
+class WorkQueue:
+    """Dynamic hand-out of fit indices 0..n-1 to the ranks of a process group through an atomic counter
+    in the group's store (control plane only; no data-path collective).  Each instance uses its own
+    store key (a per-process-group sequence number, identical on every rank because every rank
+    constructs its queues in the same order), so a second grid in the same job starts from zero."""
+    _seq = 0
+
+    def __init__(self, n, store=None, start=0):
+        import itertools
+        import threading
+        WorkQueue._seq += 1
+        self.n, self.store, self.start = n, store, start
+        self.key = "gpedm_queue_%d" % WorkQueue._seq
+        self._local, self._lock = itertools.count(), threading.Lock()
+
+    def next(self):
+        """Next unclaimed index, or None when the queue is exhausted."""
+        if self.store is not None:
+            q = self.start + self.store.add(self.key, 1) - 1
+        else:
+            with self._lock:
+                q = self.start + next(self._local)
+        return q if q < self.n else None

@@ -142,7 +142,8 @@ int gpedm_covinv(int device, int64_t n, const double* Sigma, double* L_out, doub
 
 /* ---- predict.GP numerical cores -------------------------------------------------------- */
 /* newdata (reference R/GPfunctions.R:1012-1036 + getGPgrad :1863-1865).  Xnew: M x d
- * column-major (already scaled), popnew codes.  mean, var: length M (var is the latent
+ * column-major (already scaled), popnew codes 0..np (np = a population absent from the training set:
+ * rho cross-covariance, or 1 under a rhomatrix, as getcov :796-811 gives).  mean, var: length M (var is the latent
  * variance `yvar`; predfsd = sqrt(var), predsd = sqrt(var + ve), :1041-1042).
  * gpgrad: M x d column-major or NULL. */
 int gpedm_predict_new(gpedm_handle h, int64_t M, const double* Xnew, const int32_t* popnew, double* mean,
@@ -189,9 +190,16 @@ typedef struct gpedm_fit_desc {
 /* Shards `nfits` fits over `ngpus` devices (devices[] may be NULL = 0..ngpus-1): one worker
  * thread per GPU pulling from a shared queue ordered by estimated cost; results[] (nfits) is
  * filled on return.  With ngpus > 1 the fixed-width result records are exchanged with one
- * NCCL all-gather over NVLink (single process, ncclCommInitAll); no other collective. */
+ * NCCL all-gather over NVLink (single process, ncclCommInitAll once per process and device list);
+ * no other collective. */
 int gpedm_fit_batch(int32_t nfits, const gpedm_fit_desc* descs, int32_t ngpus, const int32_t* devices,
                     const gpedm_rprop_options* opts, gpedm_result* results);
+/* The worker threads of every GPU live in the calling process, so results[] is always delivered from
+ * host memory; the NCCL all-gather additionally leaves every record on every GPU and is verified
+ * against the host copy.  Status of the collective of the most recent gpedm_fit_batch / gpedm_fit_grid:
+ * 0 = done and verified, 1 = not needed (one GPU), < 0 = NCCL unavailable or failed (records were still
+ * delivered; set GPEDM_REQUIRE_NCCL=1 to turn this into a failure of the call). */
+int gpedm_last_gather_status(void);
 
 /* ---- on-device data preparation + model-selection grids -------------------------------- */
 /* fitGP(data, y, E, tau, scaling) builds its training set from the raw series: lags inside each

@@ -913,6 +913,77 @@ def loglik_ld(phi, sigma2, rho, ve, X, Y, Pop, rhomat=None, rhomat_names=None):
     return like, a, dinv
 
 
+def _condition_ld(Sigma, Cd, Y, sigma2, focal, train):
+    """Extended-precision conditional of rows `focal` on rows `train`:
+    mean = Cd[f,t] Sigma[t,t]^-1 Y[t],  var = sigma2 - diag(Cd[f,t] Sigma[t,t]^-1 Cd[t,f])  via a
+    long-double Cholesky and triangular solves (no explicit inverse, no cancellation-prone products)."""
+    ld = np.longdouble
+    if len(train) == 0:
+        return np.zeros(len(focal), dtype=ld), np.full(len(focal), ld(sigma2))
+    L = chol_lower_ld(Sigma[np.ix_(train, train)])
+    z = solve_lower_ld(L, np.asarray(Y, dtype=ld)[train])
+    V = solve_lower_ld(L, Cd[np.ix_(train, focal)])
+    return V.T @ z, ld(sigma2) - np.sum(V * V, axis=0)
+
+
+def predict_leaveout_ld(method, phi, sigma2, rho, ve, X, Y, Pop, Time, Primary, exclradius=0, rhomat=None,
+                        rhomat_names=None):
+    """Extended-precision truth for the loo (R/GPfunctions.R:1056-1086) and lto (:1140-1176) loops:
+    the same excluded sets, every refactorisation done in 80-bit.  Returns (ymean, yvar) as long double."""
+    ld = np.longdouble
+    Pop = np.asarray(Pop, dtype=object)
+    Time = np.asarray(Time)
+    Primary = np.asarray(Primary, dtype=bool)
+    N = len(Y)
+    Cd = getcov_ld(phi, sigma2, rho, X, X, Pop, Pop, rhomat, rhomat_names)
+    Sigma = Cd + ld(ve) * np.eye(N, dtype=ld)
+    nd = int(np.sum(Primary))
+    ymean, yvar = np.full(nd, np.nan, dtype=ld), np.full(nd, np.nan, dtype=ld)
+    if method == "loo":
+        key = [str(p) + str(t) for p, t in zip(Pop, Time)]
+        aug = np.where(~Primary)[0]
+        for i in range(nd):
+            excl = [j for j in range(i - exclradius, i + exclradius + 1) if 0 <= j < N and Pop[j] == Pop[i]]
+            ek = {key[j] for j in excl}
+            dups = [j for j in aug if key[j] in ek]
+            keep = np.setdiff1d(np.arange(N), np.array(excl + dups, dtype=int))
+            m, v = _condition_ld(Sigma, Cd, Y, sigma2, np.array([i]), keep)
+            ymean[i], yvar[i] = m[0], v[0]
+    else:
+        timevals = unique_stable(Time.tolist())
+        nt = len(timevals)
+        Tp = Time[Primary]
+        for i in range(nt):
+            excl = [timevals[j] for j in range(i - exclradius, i + exclradius + 1) if 0 <= j < nt]
+            ind = np.where(Tp == timevals[i])[0]
+            train = np.where(~np.isin(Time, excl))[0]
+            ymean[ind], yvar[ind] = _condition_ld(Sigma, Cd, Y, sigma2, ind, train)
+    return ymean, yvar
+
+
+def predict_sequential_ld(phi, sigma2, rho, ve, X, Y, Pop, Time, rhomat=None, rhomat_names=None):
+    """Extended-precision truth for the sequential loop (R/GPfunctions.R:1196-1245): the rows of time
+    value i conditioned on every row of an EARLIER time value (what the successive Schur downdates of
+    :1228-1233 amount to), each conditioning done from scratch in 80-bit.  Returns (ymean, ysd2) with the
+    reference's first-time-step quirk (ymean 0, ysd = sigma2 + ve, :1216, :1236)."""
+    ld = np.longdouble
+    Pop = np.asarray(Pop, dtype=object)
+    Time = np.asarray(Time)
+    N = len(Y)
+    Cd = getcov_ld(phi, sigma2, rho, X, X, Pop, Pop, rhomat, rhomat_names)
+    Sigma = Cd + ld(ve) * np.eye(N, dtype=ld)
+    timevals = unique_stable(Time.tolist())
+    ymean = np.zeros(N, dtype=ld)
+    ysd2 = np.full(N, ld(sigma2) + ld(ve))
+    for i in range(1, len(timevals)):
+        ind = np.where(Time == timevals[i])[0]
+        train = np.where(np.isin(Time, timevals[:i]))[0]
+        m, v = _condition_ld(Sigma, Cd, Y, sigma2, ind, train)
+        ymean[ind] = m
+        ysd2[ind] = np.sqrt(np.abs(v) + ld(ve))
+    return ymean, ysd2
+
+
 def getrhomatrix(data=None, y=None, x=None, pop=None, time=None, E=None, tau=None, scaling="global",
                  initpars=None, modeprior=1, fixedpars=None, augdata=None):
     """R/rhomatrix.R:22-186: the data preparation of fitGP, then one two-population fit per pair of
