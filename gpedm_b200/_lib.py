@@ -75,7 +75,7 @@ SCALE_CODES = {"none": 0, "global": 1, "local": 2}
 # every symbol include/gpedm.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "gpedm_abi_version", "gpedm_last_error", "gpedm_device_count", "gpedm_default_rprop_options",
-    "gpedm_create", "gpedm_set_data", "gpedm_destroy", "gpedm_n", "gpedm_likegrad", "gpedm_fit_rprop", "gpedm_get_vector",
+    "gpedm_create", "gpedm_set_data", "gpedm_destroy", "gpedm_n", "gpedm_d", "gpedm_likegrad", "gpedm_fit_rprop", "gpedm_get_vector",
     "gpedm_get_matrix", "gpedm_getcov", "gpedm_covinv", "gpedm_predict_new", "gpedm_predict_loo", "gpedm_predict_lto",
     "gpedm_predict_sequential", "gpedm_fit_batch", "gpedm_last_gather_status", "gpedm_create_lagged", "gpedm_lagged_info",
     "gpedm_get_fit_stats", "gpedm_fit_grid", "gpedm_last_phase_ms", "gpedm_launch_count",
@@ -123,6 +123,8 @@ def lib():
     L.gpedm_destroy.argtypes = [C.c_void_p]
     L.gpedm_n.argtypes = [C.c_void_p]
     L.gpedm_n.restype = C.c_int64
+    L.gpedm_d.argtypes = [C.c_void_p]
+    L.gpedm_d.restype = C.c_int32
     L.gpedm_likegrad.argtypes = [C.c_void_p, dp, C.c_double, dp, C.c_double, C.c_int, C.POINTER(Result)]
     L.gpedm_fit_rprop.argtypes = [C.c_void_p, dp, C.c_double, dp, C.c_double, C.POINTER(RpropOptions),
                                   C.POINTER(Result)]

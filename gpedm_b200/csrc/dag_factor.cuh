@@ -1,0 +1,441 @@
+// Persistent, dependency-driven factorisation kernel: Cholesky (left-looking by tiles) and the
+// triangular inverse X = L^-1 (row form) as ONE launch per evaluation.
+//
+// Replaces LAPACK dpotrf + the dtrtri half of dpotri behind Matrix::chol / chol2inv (reference
+// R/GPfunctions.R:826-829).  Round 1 ran these as ~600 stream-ordered launches (diagonal block,
+// panel, grouped trailing updates on three priority streams); the serial chain of the Cholesky -
+// and the SMs its kernels could not get while long low-priority CTAs were resident - cost 2-4 ms
+// of the 20 ms evaluation at N = 8182 and most of the step below N = 4096.  Here one CTA per SM stays
+// resident and pulls TASKS (one 128 x 128 output tile each) from an ordered list:
+//
+//   DIAG (j)      T = A_jj - sum_{k<j} L_jk L_jk^T ;  L_jj = chol(T) ;  D_j = L_jj^-1   (in shared memory)
+//   POTRF (i,j)   T = A_ij - sum_{k<j} L_ik L_jk^T ;  L_ij = T D_j^T                    (i > j)
+//   TRTRI (i,j)   T = sum_{k=j}^{i-1} L_ik X_kj ;     X_ij = -D_i T                     (i > j, X_jj = D_j)
+//
+// Every tile is written exactly once, by one CTA, after ONE long k loop (the DMMA contraction of
+// dgemm_tile.cuh at its long-k rate) followed by a 128^3 epilogue product against the diagonal-block
+// inverse.  Dependencies are per-tile ready flags in global memory (release/acquire at gpu scope):
+// the k loop polls the flags of the operand tiles it is about to stream, so a CTA pre-accumulates
+// everything that is already final and only its last k tiles wait for the chain.  Tasks are claimed in
+// list order through an atomic counter and every dependency of a task precedes it in the list, so the
+// lowest unfinished task is always held by a running CTA whose inputs are complete: no deadlock,
+// whatever else shares the GPU.  The list interleaves the rows of the inverse two block columns
+// behind the Cholesky, so CTAs that would wait for the chain find inverse tiles whose inputs have
+// long been final.
+// Results are bit-reproducible: each tile's summation order is fixed (k ascending), scheduling
+// only decides when a tile is computed, never how.
+#pragma once
+#include "dgemm_tile.cuh"
+#include "diag_block.cuh"
+
+namespace gpedm {
+
+constexpr int DAG_THREADS = 256;
+using DagCfg = GemmCfgT<2, 4, 16, 4>;
+constexpr int DAG_NS = DagCfg::NSTAGE;
+// shared memory (doubles): [0, P): operand ring of the k loop, 4 stages x (A slab + B slab); the same
+// region then holds the resident tile T (128 x 132, column-major) for the epilogue / the in-CTA
+// Cholesky.  [P, P+E): ring of the one streamed operand of the epilogue (4 x 16 x 132), aliased by
+// the diagonal-block scratch (64 x 68 + pivots).
+constexpr int DAG_P = DAG_NS * (DagCfg::SLAB_A + DagCfg::SLAB_B);
+constexpr int DAG_ESLAB = 16 * DG_LD;
+constexpr int DAG_E = DAG_NS * DAG_ESLAB;
+static_assert(DAG_P >= TB * DG_LD, "resident tile must fit the operand ring");
+static_assert(DAG_E >= 64 * DG_WLD + 2 * TB + 64, "diag scratch must fit the epilogue ring");
+constexpr int DAG_SMEM_BYTES = (DAG_P + DAG_E) * (int)sizeof(double);
+
+enum DagTaskType { DAG_DIAG = 0, DAG_POTRF = 1, DAG_TRTRI = 2 };
+
+struct DagArgs {
+  double* A;      // Sigma (lower tiles) -> L, in place
+  double* X;      // L^-1 (lower tiles; diagonal tiles = D_j)
+  size_t ld;
+  int nb, n_valid;
+  double* W;      // scratch (lower tiles): running partial sums of TRTRI tiles that are computed in pieces
+  const int4* tasks;  // {type, i, j, kt0 | kt1 << 10 | piece << 20 | last << 30}: k tiles [kt0, kt1) of the tile
+  int ntasks;
+  // [0]: task counter; then four nb*nb int arrays: L final, X final, pieces done of L tile, pieces done of X tile
+  int* sync;
+  double* logdet_part;
+  int* info;
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// One lane polls, the warp follows (__syncwarp orders the other lanes' later reads after the acquire).
+#ifdef GPEDM_TIMELINE
+#define DAG_TL(...) __VA_ARGS__
+#else
+#define DAG_TL(...)
+#endif
+__device__ __forceinline__ void warp_wait_flag(const int* f, int lane DAG_TL(, unsigned long long& waited)) {
+  if (lane == 0) {
+    if (ld_acquire(f) == 0) {
+      DAG_TL(const unsigned long long w0 = tl_now();)
+      while (ld_acquire(f) == 0) __nanosleep(32);
+      DAG_TL(waited += tl_now() - w0;)
+    }
+  }
+  __syncwarp();
+}
+
+// Ring state shared by the k loop and the epilogue: slabs issued / consumed since the kernel started
+// (identical in every thread), so stage and mbarrier parity carry over from task to task.
+struct DagRing {
+  uint64_t* full;
+  uint64_t* empty;
+  unsigned gi, gc;
+};
+
+// The k loop of one task: acc (+)= (+/-) sum over `nkt` 128-wide k tiles of A B, operands streamed through the
+// mbarrier ring (see gemm_tile_mb in dgemm_tile.cuh).  A is MN-major; B is MN-major (Cholesky) or K-major
+// (inverse).  Operand tile kt is final once fa[kt] / fb[kt * fsb] are set.  Most of them already are when
+// the task starts: every warp scans the flags once (32 per load round, acquire) and only the k tiles past
+// the first unset flag are polled as the loop reaches them - the ones right behind the chain.
+template <bool B_KMAJOR>
+__device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][2], DagRing& ring, double* sA, double* sB,
+                                          const double* __restrict__ Ap, const double* __restrict__ Bp, size_t ld,
+                                          int nkt, const int* fa, const int* fb, int fsb, bool active, unsigned sgn,
+                                          int tid DAG_TL(, unsigned long long& tl_wait)) {
+  using Cfg = DagCfg;
+  constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, PREF = NS - 2;
+  constexpr int SLAB_A = Cfg::SLAB_A, SLAB_B = Cfg::SLAB_B;
+  constexpr int LD_A = Cfg::LD_MN_A, LD_B = Cfg::LD_MN_B, LD_K = Cfg::LD_K;
+  constexpr int SPT = TB / BK;  // slabs per k tile
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = (warp % Cfg::WM) * (MT * 8), n0 = (warp / Cfg::WM) * (NT * 8);
+  int nready = 0;
+  for (int base = 0; base < nkt; base += 32) {
+    const int kt = base + lane;
+    int ok = 1;
+    if (kt < nkt) ok = ld_acquire(fa + kt) & ld_acquire(fb + kt * fsb);
+    const unsigned m = __ballot_sync(0xffffffffu, ok != 0);
+    const int fz = __ffs(~m) - 1;  // first lane whose flags are not both set; -1 if none
+    if (fz >= 0) {
+      nready = base + fz;
+      break;
+    }
+    nready = base + 32;
+  }
+  nready = nready < nkt ? nready : nkt;
+  __syncwarp();  // the other lanes' acquires order every lane's later operand reads
+  const int nk = nkt * SPT;
+  auto issue = [&](int j) {  // copy slab j of this task into ring stage gi % NS
+    const int s = ring.gi % NS, r = ring.gi / NS;
+    if (r > 0) mbar_wait(&ring.empty[s], (unsigned)((r - 1) & 1));
+    if ((j & (SPT - 1)) == 0 && j / SPT >= nready) {  // first slab of a k tile not yet known to be final
+      const int kt = j / SPT;
+      warp_wait_flag(fa + kt, lane DAG_TL(, tl_wait));
+      warp_wait_flag(fb + kt * fsb, lane DAG_TL(, tl_wait));
+    }
+    load_slab<Cfg, false, Cfg::TM>(sA + s * SLAB_A, Ap, ld, j * BK, tid);
+    load_slab<Cfg, B_KMAJOR, Cfg::TN>(sB + s * SLAB_B, Bp, ld, j * BK, tid);
+    mbar_cp_async_arrive(&ring.full[s]);
+    ring.gi++;
+  };
+#pragma unroll
+  for (int j = 0; j < PREF; ++j)
+    if (j < nk) issue(j);
+  for (int kt = 0; kt < nk; ++kt) {
+    if (kt + PREF < nk) issue(kt + PREF);
+    const int s = ring.gc % NS;
+    mbar_wait(&ring.full[s], (unsigned)((ring.gc / NS) & 1));
+    if (active) {
+      const double* a_s = sA + s * SLAB_A;
+      const double* b_s = sB + s * SLAB_B;
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        double av[MT], bv[NT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) av[i] = flip_sign(a_s[(k4 * 4 + t) * LD_A + m0 + 8 * i + g], sgn);
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          bv[j] = B_KMAJOR ? b_s[(n0 + 8 * j + g) * LD_K + k4 * 4 + t] : b_s[(k4 * 4 + t) * LD_B + n0 + 8 * j + g];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.empty[s]);
+    ring.gc++;
+  }
+}
+
+__global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArgs a) {
+  extern __shared__ double smem[];
+  using Cfg = DagCfg;
+  constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, PREF = NS - 2;
+  constexpr int SLAB_A = Cfg::SLAB_A;
+  __shared__ uint64_t full_bar[NS], empty_bar[NS];
+  __shared__ int s_task;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = (warp % Cfg::WM) * (MT * 8), n0 = (warp / Cfg::WM) * (NT * 8);
+  double* sA = smem;
+  double* sB = smem + NS * SLAB_A;
+  double* T = smem;               // resident tile, aliases the operand ring
+  double* sE = smem + DAG_P;      // epilogue ring / diag scratch
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], DAG_THREADS);
+      mbar_init(&empty_bar[s], DAG_THREADS / 32);
+    }
+  }
+  __syncthreads();
+  DagRing ring{full_bar, empty_bar, 0u, 0u};
+  const int nb = a.nb;
+  const size_t ld = a.ld;
+  int* counter = a.sync;
+  int* flagL = a.sync + 1;
+  int* flagX = flagL + nb * nb;
+  int* progL = flagX + nb * nb;
+  int* progX = progL + nb * nb;
+
+  for (;;) {
+    if (tid == 0) s_task = atomicAdd(counter, 1);
+    __syncthreads();
+    const int tix = s_task;
+    if (tix >= a.ntasks) break;
+    const int4 tk = a.tasks[tix];
+    const int type = tk.x, ti = tk.y, tj = tk.z;
+    const int kt0 = tk.w & 1023, kt1 = (tk.w >> 10) & 1023, piece = (tk.w >> 20) & 1023;
+    const bool last = (tk.w >> 30) & 1;
+    DAG_TL(const unsigned long long tl_t0 = tl_now(); unsigned long long tl_wait = 0;)
+
+    // ---------------- operands of the k loop
+    const double* Ap;
+    const double* Bp;
+    const int *fa, *fb;
+    int fsb, nkt;  // flag stride of the B operand, number of 128-wide k tiles of this piece
+    double* Cg;    // output tile in global memory
+    const bool is_trtri = type == DAG_TRTRI;
+    const double* Cin;  // where the accumulator starts from (nullptr = zero)
+    double* Cpart;      // where a non-final piece leaves its partial result
+    int* prog;
+    if (!is_trtri) {
+      Ap = a.A + (size_t)ti * TB + (size_t)kt0 * TB * ld;
+      Bp = a.A + (size_t)tj * TB + (size_t)kt0 * TB * ld;
+      fa = flagL + ti * nb + kt0;
+      fb = flagL + tj * nb + kt0;
+      fsb = 1;
+      Cg = a.A + (size_t)ti * TB + (size_t)tj * TB * ld;
+      Cin = Cg;  // in place: Sigma tile, then Sigma - partial sums
+      Cpart = Cg;
+      prog = progL + ti * nb + tj;
+    } else {
+      Ap = a.A + (size_t)ti * TB + (size_t)(tj + kt0) * TB * ld;
+      Bp = a.X + (size_t)(tj + kt0) * TB + (size_t)tj * TB * ld;
+      fa = flagL + ti * nb + tj + kt0;
+      fb = flagX + (tj + kt0) * nb + tj;
+      fsb = nb;
+      Cg = a.X + (size_t)ti * TB + (size_t)tj * TB * ld;
+      Cpart = a.W + (size_t)ti * TB + (size_t)tj * TB * ld;
+      Cin = piece > 0 ? Cpart : nullptr;
+      prog = progX + ti * nb + tj;
+    }
+    nkt = kt1 - kt0;
+    if (piece > 0) {  // the previous piece of this tile must have left its partial result
+      if (lane == 0) {
+        if (ld_acquire(prog) < piece) {
+          DAG_TL(const unsigned long long w0 = tl_now();)
+          while (ld_acquire(prog) < piece) __nanosleep(32);
+          DAG_TL(tl_wait += tl_now() - w0;)
+        }
+      }
+      __syncwarp();
+    }
+    // the strictly upper 64 x 32 warp tiles of a diagonal task are never read: skip their DMMAs
+    const bool active = !(type == DAG_DIAG && n0 > m0 + MT * 8 - 1);
+
+    double acc[MT][NT][2];
+    if (Cin != nullptr) {  // __ldcg: a partial result may have been written by another SM
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) acc[i][j][e] = __ldcg(Cin + (size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ld);
+    } else {
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
+    if (!is_trtri)
+      dag_kloop<false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fb, fsb, active, 0x80000000u, tid DAG_TL(, tl_wait));
+    else
+      dag_kloop<true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fb, fsb, true, 0u, tid DAG_TL(, tl_wait));
+    if (!last) {
+      // ---------------- non-final piece: leave the partial result, publish the piece count
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Cpart[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ld] = acc[i][j][e];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        st_release(prog, piece + 1);
+      }
+      DAG_TL(tl_log(tl_t0, (210 + type) | ((long long)ti << 8) | ((long long)tj << 20) | ((long long)nkt << 32) | ((long long)(tl_wait > 0xfffff ? 0xfffff : tl_wait) << 44));)
+      continue;
+    }
+    __syncthreads();  // every warp is done with the operand ring: T may overwrite it
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) T[(m0 + 8 * i + g) + (n0 + 8 * j + 2 * t + e) * DG_LD] = acc[i][j][e];
+    __syncthreads();
+
+    if (type == DAG_DIAG) {
+      // ---------------- in-CTA Cholesky + inverse of the diagonal block (diag_block.cuh)
+      double* w = sE;
+      double* rdiag = w + 64 * DG_WLD;
+      double* dvec = rdiag + TB;
+      double* colbuf = dvec + TB;
+      diag_cholesky_smem<DAG_THREADS>(T, rdiag, dvec, colbuf, tj, a.n_valid, a.info);
+      auto lower_block_elem = [](int idx, int& r, int& c, bool& on_diag) {
+        const int b = idx >> 9, e = idx & 511;
+        const int bi = (b >= 6) ? 3 : ((b >= 3) ? 2 : ((b >= 1) ? 1 : 0)), bj = b - bi * (bi + 1) / 2;
+        r = 32 * bi + 2 * (e & 15);
+        c = 32 * bj + (e >> 4);
+        on_diag = bi == bj;
+      };
+#pragma unroll 4
+      for (int idx = tid; idx < 10 * 512; idx += DAG_THREADS) {
+        int r, c;
+        bool dg;
+        lower_block_elem(idx, r, c, dg);
+        double2 v = *reinterpret_cast<const double2*>(&T[r + c * DG_LD]);
+        if (dg) {
+          if (r < c) v.x = 0.0;
+          if (r + 1 < c) v.y = 0.0;
+        }
+        *reinterpret_cast<double2*>(&Cg[(size_t)r + (size_t)c * ld]) = v;
+      }
+      {
+        double v = 0.0;
+        if (tid < TB && tj * TB + tid < a.n_valid) v = log(dvec[tid]);
+        __syncthreads();
+        if (tid < TB) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+          if ((tid & 31) == 0) dvec[tid >> 5] = v;
+        }
+        __syncthreads();
+        if (tid == 0) a.logdet_part[tj] = ((dvec[0] + dvec[1]) + dvec[2]) + dvec[3];
+      }
+      diag_invert_smem<DAG_THREADS>(T, w, rdiag);
+      double* Dg = a.X + (size_t)tj * TB * (ld + 1);
+#pragma unroll 4
+      for (int idx = tid; idx < 10 * 512; idx += DAG_THREADS) {
+        int r, c;
+        bool dg;
+        lower_block_elem(idx, r, c, dg);
+        double2 v = *reinterpret_cast<const double2*>(&T[r + c * DG_LD]);
+        if (dg) {
+          if (r < c) v.x = 0.0;
+          if (r + 1 < c) v.y = 0.0;
+        }
+        *reinterpret_cast<double2*>(&Dg[(size_t)r + (size_t)c * ld]) = v;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        st_release(flagL + tj * nb + tj, 1);
+        st_release(flagX + tj * nb + tj, 1);
+      }
+      // timeline code: 200 + type | i << 8 | j << 20 | k tiles << 32 | ns spent waiting for flags (warp 0) << 44
+      DAG_TL(tl_log(tl_t0, (200 + type) | ((long long)ti << 8) | ((long long)tj << 20) | ((long long)nkt << 32) | ((long long)(tl_wait > 0xfffff ? 0xfffff : tl_wait) << 44));)
+      continue;
+    }
+
+    // ---------------- epilogue product against the diagonal-block inverse
+    //   POTRF: C = T D_j^T   (A operand = T resident, B operand = D_j streamed, B[k][n] = D_j[n][k])
+    //   TRTRI: C = -D_i T    (A operand = D_i streamed,  B operand = T resident)
+    // D is lower triangular: DMMAs whose D fragment is identically zero are skipped.
+    const int dblk = is_trtri ? ti : tj;
+    const double* Dg = a.X + (size_t)dblk * TB * (ld + 1);
+    warp_wait_flag(flagL + dblk * nb + dblk, lane DAG_TL(, tl_wait));
+    auto issue_e = [&](int j) {
+      const int s = ring.gi % NS, r = ring.gi / NS;
+      if (r > 0) mbar_wait(&ring.empty[s], (unsigned)((r - 1) & 1));
+      load_slab<Cfg, false, TB>(sE + s * DAG_ESLAB, Dg, ld, j * BK, tid);
+      mbar_cp_async_arrive(&ring.full[s]);
+      ring.gi++;
+    };
+    constexpr int NKE = TB / BK;
+#pragma unroll
+    for (int j = 0; j < PREF; ++j) issue_e(j);
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = 0; kt < NKE; ++kt) {
+      if (kt + PREF < NKE) issue_e(kt + PREF);
+      const int s = ring.gc % NS;
+      mbar_wait(&ring.full[s], (unsigned)((ring.gc / NS) & 1));
+      const double* e_s = sE + s * DAG_ESLAB;
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        const int kk = kt * BK + k4 * 4;  // first k of this DMMA step
+        double av[MT], bv[NT];
+        if (is_trtri) {
+#pragma unroll
+          for (int i = 0; i < MT; ++i) av[i] = flip_sign(e_s[(k4 * 4 + t) * DG_LD + m0 + 8 * i + g], 0x80000000u);
+#pragma unroll
+          for (int j = 0; j < NT; ++j) bv[j] = T[(n0 + 8 * j + g) * DG_LD + kk + t];
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+            if (m0 + 8 * i + 7 >= kk) {  // D_i[m][k] = 0 for k > m
+#pragma unroll
+              for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+            }
+        } else {
+#pragma unroll
+          for (int i = 0; i < MT; ++i) av[i] = T[(kk + t) * DG_LD + m0 + 8 * i + g];
+#pragma unroll
+          for (int j = 0; j < NT; ++j) bv[j] = e_s[(k4 * 4 + t) * DG_LD + n0 + 8 * j + g];
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+            if (n0 + 8 * j + 7 >= kk) {  // D_j[n][k] = 0 for k > n
+#pragma unroll
+              for (int i = 0; i < MT; ++i) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+            }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ring.empty[s]);
+      ring.gc++;
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) Cg[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ld] = acc[i][j][e];
+    __syncthreads();  // all stores of the tile issued; T is free again for the next task's ring
+    if (tid == 0) {
+      __threadfence();
+      st_release((is_trtri ? flagX : flagL) + ti * nb + tj, 1);
+    }
+    DAG_TL(tl_log(tl_t0, (200 + type) | ((long long)ti << 8) | ((long long)tj << 20) | ((long long)nkt << 32) | ((long long)(tl_wait > 0xfffff ? 0xfffff : tl_wait) << 44));)
+  }
+}
+
+}  // namespace gpedm

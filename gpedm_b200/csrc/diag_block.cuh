@@ -83,9 +83,9 @@ __device__ __forceinline__ void tile_mma_multi(double (&c)[RG][2], const double*
 }
 
 // One level of the recursive doubling (block size sz, RG = tiles per warp).
-template <int RG>
+template <int RG, int NTHR = DG_THREADS>
 __device__ __forceinline__ void doubling_level(double* s, double* w, int sz, int warp, int g, int t) {
-  constexpr int NW = DG_THREADS / 32;
+  constexpr int NW = NTHR / 32;
   const int tps = sz >> 3;              // 8x8 tiles per block edge
   const int gpp = tps * tps / RG;       // tile groups per pair
   const int ngroups = (TB / (2 * sz)) * gpp;
@@ -190,12 +190,14 @@ __device__ __noinline__ void chol32_warp(double* s, double* rdiag, double* dvec,
 
 // Cholesky of the 128x128 tile held in shared memory `s` (stride DG_LD), in place (lower part = L;
 // the part above the diagonal is left undefined except inside the 32x32 diagonal blocks, which are
-// zeroed).  rdiag <- 1/L_jj, dvec <- L_jj.  All DG_THREADS threads of the CTA must call it.
+// zeroed).  rdiag <- 1/L_jj, dvec <- L_jj.  All NTHR threads of the CTA must call it (NTHR = 512 in the
+// standalone diagonal-block / small-fit kernels, 256 inside the persistent factorisation kernel).
+template <int NTHR = DG_THREADS>
 __device__ __forceinline__ void diag_cholesky_smem(double* s, double* rdiag, double* dvec, double* colbuf, int kblock,
                                                    int n_valid, int* info) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  constexpr int NW = DG_THREADS / 32;
+  constexpr int NW = NTHR / 32;
   // ---------------- Cholesky, 4 block columns of width 32 ----------------
   if (warp == 0) chol32_warp(s, rdiag, dvec, colbuf, 0, lane, kblock, n_valid, info);
   __syncthreads();
@@ -226,10 +228,10 @@ __device__ __forceinline__ void diag_cholesky_smem(double* s, double* rdiag, dou
     }
     __syncthreads();
     DG_TS(3 + 3 * kb);
-    // trailing update, phase A: the next diagonal block (16 tiles, one per warp)
-    {
+    // trailing update, phase A: the next diagonal block (16 tiles, one per warp with 16 warps)
+    for (int tl = warp; tl < 16; tl += NW) {
       const int nb0 = base + 32;
-      const int row0 = nb0 + 8 * (warp >> 2), col0 = nb0 + 8 * (warp & 3);
+      const int row0 = nb0 + 8 * (tl >> 2), col0 = nb0 + 8 * (tl & 3);
       double* cp = s + (row0 + g) + (col0 + 2 * t) * DG_LD;
       double c0 = cp[0], c1 = cp[DG_LD];
       tile_mma<true>(c0, c1, s + row0 + base * DG_LD, DG_LD, s + col0 + base * DG_LD, DG_LD, 32, 0x80000000u, g, t);
@@ -265,6 +267,7 @@ __device__ __forceinline__ void diag_cholesky_smem(double* s, double* rdiag, dou
 
 // In-place inverse of the lower-triangular factor held in `s` (needs rdiag from diag_cholesky_smem):
 // on return the lower part of `s` is L^-1.  `w` is a 64 x DG_WLD scratch.
+template <int NTHR = DG_THREADS>
 __device__ __forceinline__ void diag_invert_smem(double* s, double* w, const double* rdiag) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -291,10 +294,10 @@ __device__ __forceinline__ void diag_invert_smem(double* s, double* w, const dou
   __syncthreads();
   DG_TS(15);
   // ---------------- recursive doubling: block sizes 8, 16, 32, 64 ----------------
-  doubling_level<1>(s, w, 8, warp, g, t);    //  8 tiles
-  doubling_level<1>(s, w, 16, warp, g, t);   // 16 tiles
-  doubling_level<2>(s, w, 32, warp, g, t);   // 32 tiles, 2 per warp
-  doubling_level<4>(s, w, 64, warp, g, t);   // 64 tiles, 4 per warp
+  doubling_level<1, NTHR>(s, w, 8, warp, g, t);    //  8 tiles
+  doubling_level<1, NTHR>(s, w, 16, warp, g, t);   // 16 tiles
+  doubling_level<2, NTHR>(s, w, 32, warp, g, t);   // 32 tiles, 2 per warp
+  doubling_level<4, NTHR>(s, w, 64, warp, g, t);   // 64 tiles, 4 per warp
 }
 
 __global__ void __launch_bounds__(DG_THREADS, 1)

@@ -24,6 +24,7 @@
 #include "../../include/gpedm.h"
 #include "kernels.cuh"
 #include "diag_block.cuh"
+#include "dag_factor.cuh"
 #include "small_fit.cuh"
 #include "lag_prep.cuh"
 

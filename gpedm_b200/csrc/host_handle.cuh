@@ -21,6 +21,9 @@ struct gpedm_fit_s {
   double* hscal = nullptr;  // pinned
   int* dinfo = nullptr;
   int* hinfo = nullptr;  // pinned
+  int4* dtasks = nullptr;  // task list of the persistent factorisation kernel (dag_factor.cuh)
+  int ntasks = 0;
+  int* dsync = nullptr;    // its task counter + per-tile ready flags, zeroed at the start of every evaluation
   int num_sms = 148;
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // gradient-only / full / through-z variants
   int64_t graph_launches[3] = {0, 0, 0};
@@ -68,6 +71,13 @@ static const int g_graph_max_nb = getenv("GPEDM_GRAPH_MAX_NB") ? atoi(getenv("GP
 static const int g_batch_workers = getenv("GPEDM_BATCH_WORKERS_PER_GPU") ? atoi(getenv("GPEDM_BATCH_WORKERS_PER_GPU")) : 0;
 static const bool g_no_graph = getenv("GPEDM_NO_GRAPH") != nullptr && atoi(getenv("GPEDM_NO_GRAPH")) != 0;
 static const bool g_diag_ref = getenv("GPEDM_DIAG_REF") != nullptr && atoi(getenv("GPEDM_DIAG_REF")) != 0;
+// GPEDM_NO_DAG=1: round-1 stream-ordered Cholesky / recursive inverse instead of the persistent task kernel
+static const bool g_no_dag = getenv("GPEDM_NO_DAG") != nullptr && atoi(getenv("GPEDM_NO_DAG")) != 0;
+// rows of the inverse are queued this many block columns behind the Cholesky
+static const int g_dag_lead = getenv("GPEDM_DAG_LEAD") ? std::max(0, atoi(getenv("GPEDM_DAG_LEAD"))) : 2;
+// k tiles per piece of a long tile (512 = never split)
+static const int g_dag_chunk = getenv("GPEDM_DAG_CHUNK") ? std::min(512, std::max(1, atoi(getenv("GPEDM_DAG_CHUNK")))) : 16;
+static const int g_dag_lag = getenv("GPEDM_DAG_LAG") ? std::max(1, atoi(getenv("GPEDM_DAG_LAG"))) : 2;
 static std::mutex g_attr_mutex;
 static int ensure_kernel_attrs(int device) {
   std::lock_guard<std::mutex> lock(g_attr_mutex);  // batch workers create handles concurrently
@@ -98,6 +108,7 @@ static int ensure_kernel_attrs(int device) {
   }
   CU(cudaFuncSetAttribute(diag_potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
   CU(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(dag_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM_BYTES));
   CU(cudaFuncSetAttribute(small_eval_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<8>()));
   CU(cudaFuncSetAttribute(small_eval_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<16>()));
   CU(cudaFuncSetAttribute(small_eval_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<32>()));
@@ -169,7 +180,8 @@ static void free_handle(gpedm_fit_s* h) {
     cudaStreamSynchronize(h->stream);
     if (h->aux) cudaStreamSynchronize(h->aux);
     void* bufs[] = {h->dX, h->dY, h->drhotab, h->dpop, h->bufA, h->bufB, h->bufC, h->dparams, h->dz, h->da,
-                    h->ddiagS, h->dpart, h->dlogdet, h->dtracepart, h->dscal, h->dinfo, h->dcenter, h->dscale};
+                    h->ddiagS, h->dpart, h->dlogdet, h->dtracepart, h->dscal, h->dinfo, h->dcenter, h->dscale,
+                    h->dtasks, h->dsync};
     for (void* b : bufs)
       if (b) cudaFreeAsync(b, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -203,7 +215,7 @@ static void free_handle(gpedm_fit_s* h) {
 // The training data (dX, dY, dpop, drhotab, hY, hpop, single_pop) are filled by the caller.
 static int alloc_handle(int device, int64_t N, int32_t d, int32_t np, bool has_rhomat, gpedm_handle* out) {
   *out = nullptr;
-  if (N < 1 || N > (1 << 20)) return set_err(GPEDM_ERR_ARG, "N=%lld out of range", (long long)N);
+  if (N < 1 || N > 1023 * TB) return set_err(GPEDM_ERR_ARG, "N=%lld out of range 1..%d", (long long)N, 1023 * TB);
   if (d < 1 || d > GPEDM_MAX_D) return set_err(GPEDM_ERR_ARG, "d=%d out of range 1..%d", d, GPEDM_MAX_D);
   if (np < 1) return set_err(GPEDM_ERR_ARG, "np=%d must be >= 1", np);
   int ndev = gpedm_device_count();
@@ -252,6 +264,61 @@ static int alloc_handle(int device, int64_t N, int32_t d, int32_t np, bool has_r
   ALLOC(h->dtracepart, (size_t)h->ntiles * (MAXD + 3) * 8);
   ALLOC(h->dscal, NSCAL * 8);
   ALLOC(h->dinfo, 4);
+  ALLOC(h->dsync, (size_t)(1 + 4 * h->nb * h->nb) * 4);
+  {
+    // Task list of the persistent factorisation kernel (dag_factor.cuh).  A tile whose k loop is longer
+    // than `ch` tiles is computed in PIECES of ch k tiles (running partial result kept in place / in the
+    // scratch matrix); only the last piece carries the epilogue.  Placement by "column step" s:
+    //   * final piece of POTRF(i, s), i >= s + 2, and of TRTRI row s - lag: at step s;
+    //   * the two chain tasks of block column c - DIAG(c) and POTRF(c+1, c) - `lead` steps early: their
+    //     CTAs are then resident, with everything but the last k tiles accumulated, when the chain arrives;
+    //   * a non-final piece as soon as its operands are final, staggered over the following ch steps so
+    //     that the bulk work never queues up in front of the chain.
+    // Within a step: chain tasks, Cholesky tiles, inverse tiles, then pieces.  Every dependency of a task
+    // precedes it in the list, except that chain tasks may precede theirs (bounded: 2 (lead + 1) tasks).
+    struct Ev {
+      int step, cls, seq;
+      int4 t;
+    };
+    std::vector<Ev> evs;
+    const int nb = h->nb, lag = g_dag_lag, lead = g_dag_lead, ch = g_dag_chunk;
+    evs.reserve((size_t)nb * nb * 2);
+    int seq = 0;
+    auto word = [](int kt0, int kt1, int piece, int last) { return kt0 | (kt1 << 10) | (piece << 20) | (last << 30); };
+    // tile (type, i, j) with nkt k tiles; koff: TRTRI operand rows start at block row j
+    auto add_tile = [&](int type, int i, int j, int nkt, int final_step, int cls, int ready_off, int partial_cap) {
+      const int np = std::max(1, (nkt + ch - 1) / ch);
+      for (int q = 0; q + 1 < np; ++q) {
+        const int e = ready_off + (q + 1) * ch;  // first step at which the operands of piece q are final
+        const int st = std::max(e, std::min(e + (i + j) % ch, partial_cap));
+        evs.push_back({st, 3, seq++, make_int4(type, i, j, word(q * ch, (q + 1) * ch, q, 0))});
+      }
+      evs.push_back({final_step, cls, seq++, make_int4(type, i, j, word((np - 1) * ch, nkt, np - 1, 1))});
+    };
+    for (int c = 0; c < nb; ++c) {
+      const int fs = std::max(0, c - lead);
+      add_tile(DAG_DIAG, c, c, c, fs, 0, 0, std::max(0, fs - 1));
+      if (c + 1 < nb) add_tile(DAG_POTRF, c + 1, c, c, fs, 0, 0, std::max(0, fs - 1));
+      for (int i = c + 2; i < nb; ++i) add_tile(DAG_POTRF, i, c, c, c, 1, 0, c - 1);
+    }
+    for (int r = 1; r < nb; ++r)
+      for (int j = 0; j < r; ++j) add_tile(DAG_TRTRI, r, j, r - j, r + lag, 2, j + lag, r + lag - 1);
+    std::stable_sort(evs.begin(), evs.end(), [](const Ev& x, const Ev& y) {
+      if (x.step != y.step) return x.step < y.step;
+      if (x.cls != y.cls) return x.cls < y.cls;
+      return x.seq < y.seq;
+    });
+    std::vector<int4> tasks(evs.size());
+    for (size_t q = 0; q < evs.size(); ++q) tasks[q] = evs[q].t;
+    h->ntasks = (int)tasks.size();
+    ALLOC(h->dtasks, tasks.size() * sizeof(int4));
+    cudaError_t e_ = cudaMemcpyAsync(h->dtasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream);
+    if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(h->stream);  // `tasks` is pageable and goes out of scope
+    if (e_ != cudaSuccess) {
+      free_handle(h);
+      return set_err(GPEDM_ERR_CUDA, "task list upload failed: %s", cudaGetErrorString(e_));
+    }
+  }
   h->num_sms = (device < 64 && g_num_sms[device] > 0) ? g_num_sms[device] : 148;
 #undef ALLOC
   h->pinned = pinned_acquire();
@@ -346,6 +413,7 @@ extern "C" int gpedm_destroy(gpedm_handle h) {
   return 0;
 }
 extern "C" int64_t gpedm_n(gpedm_handle h) { return h ? h->N : -1; }
+extern "C" int32_t gpedm_d(gpedm_handle h) { return h ? h->d : -1; }
 extern "C" int64_t gpedm_launch_count(gpedm_handle h) { return h ? h->launches : -1; }
 extern "C" int gpedm_last_phase_ms(gpedm_handle h, float* ms) {
   if (!h || !ms) return set_err(GPEDM_ERR_ARG, "NULL argument");

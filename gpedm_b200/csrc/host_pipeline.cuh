@@ -133,6 +133,27 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   }
   CU(record_phase_event(h->ev[1], st));
   NvtxRange::next("gpedm:potrf");
+  if (!g_no_dag) {
+    // --- Cholesky + triangular inverse: ONE persistent, dependency-driven launch (dag_factor.cuh)
+    CU(cudaMemsetAsync(h->dsync, 0, (size_t)(1 + 4 * nb * nb) * 4, st));
+    DagArgs da;
+    da.A = h->bufA;
+    da.X = h->bufB;
+    da.W = h->bufC;
+    da.ld = ld;
+    da.nb = nb;
+    da.n_valid = N;
+    da.tasks = h->dtasks;
+    da.ntasks = h->ntasks;
+    da.sync = h->dsync;
+    da.logdet_part = h->dlogdet;
+    da.info = h->dinfo;
+    dag_factor_kernel<<<std::min(h->num_sms, h->ntasks), DAG_THREADS, DAG_SMEM_BYTES, st>>>(da);
+    h->launches++;
+    CU(record_phase_event(h->ev[2], st));
+    NvtxRange::next("gpedm:trtri");
+    CU(record_phase_event(h->ev[3], st));
+  } else {
   // --- Cholesky, right-looking over 128-wide block columns, with look-ahead and grouped updates.
   // Steps are processed in groups [g0, g1) of G block columns (G = GPEDM_POTRF_GROUP while the
   // trailing matrix is large, 1 near the end); [g1, g2) is the next group.
@@ -238,6 +259,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     if (rc) return rc;
   }
   CU(record_phase_event(h->ev[3], st));
+  }  // !g_no_dag
   NvtxRange::next("gpedm:vec");
   // --- z = X Y
   trmv_n_part_kernel<<<h->ntiles, 256, 0, st>>>(h->bufB, ld, h->dY, h->dpart, ld);

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GPEDM_ABI_VERSION 2
+#define GPEDM_ABI_VERSION 3
 #define GPEDM_MAX_D 32              /* max number of predictors (columns of X) */
 #define GPEDM_MAX_P (GPEDM_MAX_D + 3) /* phi_1..d, ve, sigma2, rho */
 
@@ -93,6 +93,7 @@ int gpedm_create(int device, int64_t N, int32_t d, int32_t np, const double* X, 
 int gpedm_set_data(gpedm_handle h, const double* X, const double* Y, const int32_t* pop);
 int gpedm_destroy(gpedm_handle h);
 int64_t gpedm_n(gpedm_handle h);
+int32_t gpedm_d(gpedm_handle h); /* number of predictors (columns of X); -1 for a NULL handle */
 
 /* ---- getlikegrad (reference R/GPfunctions.R:586-750) --------------------------------- */
 /* parst: d+3 transformed parameters.  fixedpars: d+2 values, NaN = free (may be NULL).

@@ -1,5 +1,7 @@
 /*
- * R .Call glue for libgpedm_b200 (cannot be compiled in the build image: R headers are absent).
+ * R .Call glue for libgpedm_b200.  R is absent from the build image, so the glue is compiled and EXECUTED
+ * there against a small stand-in for R's C API (tests/r_stub/, tests/test_r_glue.py: every entry below is
+ * called through the registered table and compared with the direct C-ABI path).
  * Same registration pattern as the reference's generated glue (src/RcppExports.cpp:49-59):
  * R_registerRoutines + R_useDynamicSymbols(FALSE).  Every entry maps SEXP <-> plain pointers and
  * forwards to the C ABI of include/gpedm.h; the fit handle is an external pointer with finalizer.
@@ -123,7 +125,7 @@ SEXP gpedmb200_predict_leaveout(SEXP h, SEXP method, SEXP exclradius, SEXP time,
   const char* names[] = {"mean", "var", "grad", ""};
   SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
   SEXP mean = PROTECT(Rf_allocVector(REALSXP, nd)), var = PROTECT(Rf_allocVector(REALSXP, nd));
-  if (wg) d = Rf_asInteger(Rf_getAttrib(h, Rf_install("d")));
+  if (wg) d = gpedm_d(hh);
   SEXP grad = PROTECT(wg ? Rf_allocMatrix(REALSXP, nd, d) : R_NilValue);
   const double* t = Rf_isNull(time) ? NULL : REAL(time);
   if (Rf_asInteger(method) == 0)

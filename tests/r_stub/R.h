@@ -1,8 +1,6 @@
-/* Minimal declarations of the R C API used by r/gpedm_b200_glue.c, ONLY so that the glue can be
- * type-checked against include/gpedm.h in an image without R (tests/test_host_logic.py). */
+/* Stand-in for <R.h> (see Rinternals.h in this directory). */
 #ifndef R_STUB_H
 #define R_STUB_H
 #include <stddef.h>
-void Rf_error(const char*, ...);
-char* R_alloc(size_t, int);
+#include "Rinternals.h"
 #endif

@@ -34,7 +34,7 @@ def test_header_symbols_exported(L):
 
 
 def test_abi_version_and_struct_layout(L):
-    assert L.gpedm_abi_version() == 2
+    assert L.gpedm_abi_version() == 3
     # gpedm_result: 8 doubles + 4 int32 + 3 * GPEDM_MAX_P doubles
     assert C.sizeof(_lib.Result) == 8 * 8 + 4 * 4 + 3 * 35 * 8
     opt = _lib.RpropOptions()

@@ -1,0 +1,75 @@
+"""Task timeline of the persistent factorisation kernel (dag_factor.cuh) from a -DGPEDM_TIMELINE build.
+
+  nvcc ... -DGPEDM_TIMELINE -o build/libgpedm_timeline.so gpedm_b200/csrc/gpedm_core.cu -ldl
+  python tools/dag_timeline.py [series_len] [bin_us]
+
+Every task logs (globaltimer start, end, SM id, type | i << 8 | j << 20 | k tiles << 32 | wait ns << 44); wait = time
+warp 0 spent polling ready flags.  Printed: SM busy / waiting fractions per time bin and task type, the chain (when
+each D_c became ready), and totals."""
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from gpedm_b200 import _lib
+_lib.LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'build', 'libgpedm_timeline.so')
+import gpedm_b200 as G
+from gpedm_b200 import synth
+from gpedm_b200.batch import default_initparst
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+bin_us = float(sys.argv[2]) if len(sys.argv) > 2 else 500.0
+E = 10
+Y, X = synth.embed(synth.ricker(n, 1004), E, 1)
+m = G.GPModel(Y, X)
+p0 = default_initparst(E, True)
+L = G.lib()
+L.gpedm_debug_timeline.argtypes = [C.POINTER(C.c_ulonglong), C.c_uint, C.POINTER(C.c_uint)]
+for _ in range(2):
+    m.likegrad(p0, 1.0, None, None, True)
+cnt = C.c_uint(0)
+L.gpedm_debug_timeline(None, 0, C.byref(cnt))
+m.likegrad(p0, 1.0, None, None, True)
+MAXR = 1 << 18
+buf = np.zeros(4 * MAXR, dtype=np.uint64)
+L.gpedm_debug_timeline(buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), MAXR, C.byref(cnt))
+rec = buf[:4 * cnt.value].reshape(cnt.value, 4).astype(np.int64)
+code = rec[:, 3]
+isd = (code & 0xff) >= 200
+final_piece = ((code & 0xff) - 200) < 10
+rec, code, final_piece = rec[isd], code[isd], final_piece[isd]
+t0 = rec[:, 0].min()
+st, en, sm = (rec[:, 0] - t0) * 1e-3, (rec[:, 1] - t0) * 1e-3, rec[:, 2]
+typ, ti, tj, nkt, wait = ((code & 0xff) - 200) % 10, (code >> 8) & 0xfff, (code >> 20) & 0xfff, (code >> 32) & 0xfff, ((code >> 44) & 0xfffff) * 1e-3
+T = en.max()
+nsm = int(sm.max()) + 1
+print("N=%d nb=%d tasks=%d SMs=%d kernel span %.3f ms; phases %s" % (len(Y), (len(Y) + 127) // 128, len(rec), nsm, T * 1e-3,
+      {k: round(v, 3) for k, v in m.phase_ms().items()}))
+names = ["diag", "potrf", "trtri"]
+nbin = int(np.ceil(T / bin_us))
+edges = np.arange(nbin + 1) * bin_us
+print("\nfraction of the %d SMs per %.0f us bin: resident per task type, of which waiting on flags (approx: wait spread uniformly over the task)" % (nsm, bin_us))
+print(" ".join("%9s" % h for h in ["t_ms", "diag", "potrf", "trtri", "waiting", "idle"]))
+for b in range(nbin):
+    row, wsum = [], 0.0
+    for k in range(3):
+        msk = typ == k
+        ov = np.clip(np.minimum(en[msk], edges[b + 1]) - np.maximum(st[msk], edges[b]), 0, None)
+        dur = np.maximum(en[msk] - st[msk], 1e-9)
+        row.append(ov.sum() / (nsm * bin_us))
+        wsum += (ov * wait[msk] / dur).sum() / (nsm * bin_us)
+    print(" ".join(["%9.2f" % (edges[b] * 1e-3)] + ["%9.3f" % v for v in row] + ["%9.3f" % wsum, "%9.3f" % (1 - sum(row))]))
+tot_res = (en - st).sum()
+print("\ntotals (SM-ms): resident %.1f of %.1f available; waiting on flags %.1f; k tiles executed %d (%.1f us per k tile while not waiting)"
+      % (tot_res * 1e-3, T * nsm * 1e-3, wait.sum() * 1e-3, nkt.sum(), (tot_res - wait.sum()) / max(1, nkt.sum() + 0.6 * ((typ > 0) & final_piece).sum())))
+for k in range(3):
+    msk = typ == k
+    print("  %-6s %5d tasks, mean %.1f us, max %.1f us, waiting %.1f%% of residency" % (names[k], msk.sum(), (en - st)[msk].mean(), (en - st)[msk].max(),
+          100 * wait[msk].sum() / max(1e-9, (en - st)[msk].sum())))
+d = np.where((typ == 0) & final_piece)[0]
+order = d[np.argsort(tj[d])]
+ends = en[order]
+print("\nchain: D_c ready at (us) and step from the previous column; diag task start, its wait, its k tiles")
+for q, ix in enumerate(order):
+    if q % max(1, len(order) // 32) == 0 or q == len(order) - 1:
+        print("  c=%3d ready %9.1f  step %7.1f  task start %9.1f wait %7.1f nkt %d" % (tj[ix], en[ix], en[ix] - (ends[q - 1] if q else 0), st[ix], wait[ix], nkt[ix]))
+steps = np.diff(ends)
+print("chain step: median %.1f us, mean %.1f, max %.1f; last D ready at %.1f us of %.1f" % (np.median(steps), steps.mean(), steps.max(), ends[-1], T))
