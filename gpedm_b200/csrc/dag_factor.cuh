@@ -11,6 +11,7 @@
 //   DIAG (j)      T = A_jj - sum_{k<j} L_jk L_jk^T ;  L_jj = chol(T) ;  D_j = L_jj^-1   (in shared memory)
 //   POTRF (i,j)   T = A_ij - sum_{k<j} L_ik L_jk^T ;  L_ij = T D_j^T                    (i > j)
 //   TRTRI (i,j)   T = sum_{k=j}^{i-1} L_ik X_kj ;     X_ij = -D_i T                     (i > j, X_jj = D_j)
+//   LAUUM (i,j)   S_ij = sum_{k>=i} X_ki^T X_kj                                         (i >= j; Sigma^-1 = X^T X)
 //
 // Every tile is written exactly once, by one CTA, after ONE long k loop (the DMMA contraction of
 // dgemm_tile.cuh at its long-k rate) followed by a 128^3 epilogue product against the diagonal-block
@@ -44,14 +45,15 @@ static_assert(DAG_P >= TB * DG_LD, "resident tile must fit the operand ring");
 static_assert(DAG_E >= 64 * DG_WLD + 2 * TB + 64, "diag scratch must fit the epilogue ring");
 constexpr int DAG_SMEM_BYTES = (DAG_P + DAG_E) * (int)sizeof(double);
 
-enum DagTaskType { DAG_DIAG = 0, DAG_POTRF = 1, DAG_TRTRI = 2 };
+enum DagTaskType { DAG_DIAG = 0, DAG_POTRF = 1, DAG_TRTRI = 2, DAG_LAUUM = 3 };
 
 struct DagArgs {
   double* A;      // Sigma (lower tiles) -> L, in place
   double* X;      // L^-1 (lower tiles; diagonal tiles = D_j)
   size_t ld;
   int nb, n_valid;
-  double* W;      // scratch (lower tiles): running partial sums of TRTRI tiles that are computed in pieces
+  double* W;      // Sigma^-1 (lower tiles), written by the LAUUM tasks; before that, scratch for the running
+                  // partial sums of TRTRI tiles that are computed in pieces
   const int4* tasks;  // {type, i, j, kt0 | kt1 << 10 | piece << 20 | last << 30}: k tiles [kt0, kt1) of the tile
   int ntasks;
   // [0]: task counter; then four nb*nb int arrays: L final, X final, pieces done of L tile, pieces done of X tile
@@ -98,10 +100,10 @@ struct DagRing {
 // (inverse).  Operand tile kt is final once fa[kt] / fb[kt * fsb] are set.  Most of them already are when
 // the task starts: every warp scans the flags once (32 per load round, acquire) and only the k tiles past
 // the first unset flag are polled as the loop reaches them - the ones right behind the chain.
-template <bool B_KMAJOR>
+template <bool A_KMAJOR, bool B_KMAJOR>
 __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][2], DagRing& ring, double* sA, double* sB,
                                           const double* __restrict__ Ap, const double* __restrict__ Bp, size_t ld,
-                                          int nkt, const int* fa, const int* fb, int fsb, bool active, unsigned sgn,
+                                          int nkt, const int* fa, int fsa, const int* fb, int fsb, bool active, unsigned sgn,
                                           int tid DAG_TL(, unsigned long long& tl_wait)) {
   using Cfg = DagCfg;
   constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, PREF = NS - 2;
@@ -115,7 +117,7 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
   for (int base = 0; base < nkt; base += 32) {
     const int kt = base + lane;
     int ok = 1;
-    if (kt < nkt) ok = ld_acquire(fa + kt) & ld_acquire(fb + kt * fsb);
+    if (kt < nkt) ok = ld_acquire(fa + kt * fsa) & ld_acquire(fb + kt * fsb);
     const unsigned m = __ballot_sync(0xffffffffu, ok != 0);
     const int fz = __ffs(~m) - 1;  // first lane whose flags are not both set; -1 if none
     if (fz >= 0) {
@@ -132,10 +134,10 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
     if (r > 0) mbar_wait(&ring.empty[s], (unsigned)((r - 1) & 1));
     if ((j & (SPT - 1)) == 0 && j / SPT >= nready) {  // first slab of a k tile not yet known to be final
       const int kt = j / SPT;
-      warp_wait_flag(fa + kt, lane DAG_TL(, tl_wait));
+      warp_wait_flag(fa + kt * fsa, lane DAG_TL(, tl_wait));
       warp_wait_flag(fb + kt * fsb, lane DAG_TL(, tl_wait));
     }
-    load_slab<Cfg, false, Cfg::TM>(sA + s * SLAB_A, Ap, ld, j * BK, tid);
+    load_slab<Cfg, A_KMAJOR, Cfg::TM>(sA + s * SLAB_A, Ap, ld, j * BK, tid);
     load_slab<Cfg, B_KMAJOR, Cfg::TN>(sB + s * SLAB_B, Bp, ld, j * BK, tid);
     mbar_cp_async_arrive(&ring.full[s]);
     ring.gi++;
@@ -154,7 +156,8 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
       for (int k4 = 0; k4 < BK / 4; ++k4) {
         double av[MT], bv[NT];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) av[i] = flip_sign(a_s[(k4 * 4 + t) * LD_A + m0 + 8 * i + g], sgn);
+        for (int i = 0; i < MT; ++i)
+          av[i] = flip_sign(A_KMAJOR ? a_s[(m0 + 8 * i + g) * LD_K + k4 * 4 + t] : a_s[(k4 * 4 + t) * LD_A + m0 + 8 * i + g], sgn);
 #pragma unroll
         for (int j = 0; j < NT; ++j)
           bv[j] = B_KMAJOR ? b_s[(n0 + 8 * j + g) * LD_K + k4 * 4 + t] : b_s[(k4 * 4 + t) * LD_B + n0 + 8 * j + g];
@@ -216,9 +219,35 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
     const double* Ap;
     const double* Bp;
     const int *fa, *fb;
-    int fsb, nkt;  // flag stride of the B operand, number of 128-wide k tiles of this piece
+    int fsa = 1, fsb, nkt;  // flag strides of the operands, number of 128-wide k tiles of this piece
     double* Cg;    // output tile in global memory
     const bool is_trtri = type == DAG_TRTRI;
+    if (type == DAG_LAUUM) {
+      // ---------------- S_ij = sum_{k >= i} X_ki^T X_kj: both operands K-major, rows of X become final in
+      // ascending order, so the k loop follows the inverse as it completes; no epilogue, no flag (nothing in
+      // this kernel reads S)
+      const double* LAp = a.X + (size_t)ti * TB + (size_t)ti * TB * ld;
+      const double* LBp = a.X + (size_t)ti * TB + (size_t)tj * TB * ld;
+      const bool act = !(ti == tj && n0 > m0 + MT * 8 - 1);
+      double acc[MT][NT][2];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      dag_kloop<true, true>(acc, ring, sA, sB, LAp, LBp, ld, nb - ti, flagX + ti * nb + ti, nb, flagX + ti * nb + tj, nb, act,
+                            0u, tid DAG_TL(, tl_wait));
+      double* Sg = a.W + (size_t)ti * TB + (size_t)tj * TB * ld;
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Sg[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ld] = acc[i][j][e];
+      }
+      DAG_TL(tl_log(tl_t0, (200 + type) | ((long long)ti << 8) | ((long long)tj << 20) | ((long long)(nb - ti) << 32) | ((long long)(tl_wait > 0xfffff ? 0xfffff : tl_wait) << 44));)
+      continue;
+    }
     const double* Cin;  // where the accumulator starts from (nullptr = zero)
     double* Cpart;      // where a non-final piece leaves its partial result
     int* prog;
@@ -272,9 +301,9 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     }
     if (!is_trtri)
-      dag_kloop<false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fb, fsb, active, 0x80000000u, tid DAG_TL(, tl_wait));
+      dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, 0x80000000u, tid DAG_TL(, tl_wait));
     else
-      dag_kloop<true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fb, fsb, true, 0u, tid DAG_TL(, tl_wait));
+      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, 0u, tid DAG_TL(, tl_wait));
     if (!last) {
       // ---------------- non-final piece: leave the partial result, publish the piece count
       if (active) {

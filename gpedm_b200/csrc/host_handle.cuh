@@ -22,7 +22,8 @@ struct gpedm_fit_s {
   int* dinfo = nullptr;
   int* hinfo = nullptr;  // pinned
   int4* dtasks = nullptr;  // task list of the persistent factorisation kernel (dag_factor.cuh)
-  int ntasks = 0;
+  int ntasks = 0;          // all tasks: Cholesky, inverse, Sigma^-1 = X^T X
+  int ntasks_factor = 0;   // without the trailing Sigma^-1 tasks (sequential helper: only L and z are needed)
   int* dsync = nullptr;    // its task counter + per-tile ready flags, zeroed at the start of every evaluation
   int num_sms = 148;
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // gradient-only / full / through-z variants
@@ -74,9 +75,9 @@ static const bool g_diag_ref = getenv("GPEDM_DIAG_REF") != nullptr && atoi(geten
 // GPEDM_NO_DAG=1: round-1 stream-ordered Cholesky / recursive inverse instead of the persistent task kernel
 static const bool g_no_dag = getenv("GPEDM_NO_DAG") != nullptr && atoi(getenv("GPEDM_NO_DAG")) != 0;
 // rows of the inverse are queued this many block columns behind the Cholesky
-static const int g_dag_lead = getenv("GPEDM_DAG_LEAD") ? std::max(0, atoi(getenv("GPEDM_DAG_LEAD"))) : 2;
+static const int g_dag_lead = getenv("GPEDM_DAG_LEAD") ? std::max(0, atoi(getenv("GPEDM_DAG_LEAD"))) : 1;
 // k tiles per piece of a long tile (512 = never split)
-static const int g_dag_chunk = getenv("GPEDM_DAG_CHUNK") ? std::min(512, std::max(1, atoi(getenv("GPEDM_DAG_CHUNK")))) : 16;
+static const int g_dag_chunk = getenv("GPEDM_DAG_CHUNK") ? std::min(512, std::max(1, atoi(getenv("GPEDM_DAG_CHUNK")))) : 512;
 static const int g_dag_lag = getenv("GPEDM_DAG_LAG") ? std::max(1, atoi(getenv("GPEDM_DAG_LAG"))) : 2;
 static std::mutex g_attr_mutex;
 static int ensure_kernel_attrs(int device) {
@@ -310,6 +311,12 @@ static int alloc_handle(int device, int64_t N, int32_t d, int32_t np, bool has_r
     });
     std::vector<int4> tasks(evs.size());
     for (size_t q = 0; q < evs.size(); ++q) tasks[q] = evs[q].t;
+    h->ntasks_factor = (int)tasks.size();
+    // Sigma^-1 = X^T X after the inverse, longest k range first.  S_ij sums over block rows k >= i of X in
+    // ascending order - the order in which the inverse completes them - so the CTAs that run out of inverse
+    // tiles at the end of the factorisation accumulate S behind it instead of idling.
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j <= i; ++j) tasks.push_back(make_int4(DAG_LAUUM, i, j, 0));
     h->ntasks = (int)tasks.size();
     ALLOC(h->dtasks, tasks.size() * sizeof(int4));
     cudaError_t e_ = cudaMemcpyAsync(h->dtasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream);

@@ -144,11 +144,11 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     da.nb = nb;
     da.n_valid = N;
     da.tasks = h->dtasks;
-    da.ntasks = h->ntasks;
+    da.ntasks = through_z_only ? h->ntasks_factor : h->ntasks;
     da.sync = h->dsync;
     da.logdet_part = h->dlogdet;
     da.info = h->dinfo;
-    dag_factor_kernel<<<std::min(h->num_sms, h->ntasks), DAG_THREADS, DAG_SMEM_BYTES, st>>>(da);
+    dag_factor_kernel<<<std::min(h->num_sms, da.ntasks), DAG_THREADS, DAG_SMEM_BYTES, st>>>(da);
     h->launches++;
     CU(record_phase_event(h->ev[2], st));
     NvtxRange::next("gpedm:trtri");
@@ -276,8 +276,8 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   h->launches += 2;
   CU(record_phase_event(h->ev[4], st));
   NvtxRange::next("gpedm:lauum");
-  // --- S = Sigma^-1 = X^T X (lower tiles) into bufC
-  {
+  // --- S = Sigma^-1 = X^T X (lower tiles) into bufC (already done by the persistent kernel unless GPEDM_NO_DAG)
+  if (g_no_dag) {
     TileOp lu = make_op(OP_LAUUM, h->ntiles, nb);
     lu.P0 = h->bufB;
     lu.P2 = h->bufC;

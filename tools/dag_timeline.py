@@ -43,14 +43,14 @@ T = en.max()
 nsm = int(sm.max()) + 1
 print("N=%d nb=%d tasks=%d SMs=%d kernel span %.3f ms; phases %s" % (len(Y), (len(Y) + 127) // 128, len(rec), nsm, T * 1e-3,
       {k: round(v, 3) for k, v in m.phase_ms().items()}))
-names = ["diag", "potrf", "trtri"]
+names = ["diag", "potrf", "trtri", "lauum"]
 nbin = int(np.ceil(T / bin_us))
 edges = np.arange(nbin + 1) * bin_us
 print("\nfraction of the %d SMs per %.0f us bin: resident per task type, of which waiting on flags (approx: wait spread uniformly over the task)" % (nsm, bin_us))
-print(" ".join("%9s" % h for h in ["t_ms", "diag", "potrf", "trtri", "waiting", "idle"]))
+print(" ".join("%9s" % h for h in ["t_ms", "diag", "potrf", "trtri", "lauum", "waiting", "idle"]))
 for b in range(nbin):
     row, wsum = [], 0.0
-    for k in range(3):
+    for k in range(4):
         msk = typ == k
         ov = np.clip(np.minimum(en[msk], edges[b + 1]) - np.maximum(st[msk], edges[b]), 0, None)
         dur = np.maximum(en[msk] - st[msk], 1e-9)
@@ -60,7 +60,7 @@ for b in range(nbin):
 tot_res = (en - st).sum()
 print("\ntotals (SM-ms): resident %.1f of %.1f available; waiting on flags %.1f; k tiles executed %d (%.1f us per k tile while not waiting)"
       % (tot_res * 1e-3, T * nsm * 1e-3, wait.sum() * 1e-3, nkt.sum(), (tot_res - wait.sum()) / max(1, nkt.sum() + 0.6 * ((typ > 0) & final_piece).sum())))
-for k in range(3):
+for k in range(4):
     msk = typ == k
     print("  %-6s %5d tasks, mean %.1f us, max %.1f us, waiting %.1f%% of residency" % (names[k], msk.sum(), (en - st)[msk].mean(), (en - st)[msk].max(),
           100 * wait[msk].sum() / max(1e-9, (en - st)[msk].sum())))
