@@ -165,10 +165,10 @@ def run_reference(args):
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the lauum launch from the committed ncu --set full
-    capture (profiles/r01_lauum_tile_kernel_ncu.txt); None when the summary is absent."""
+    capture of the dominant kernel (profiles/r02_dag_factor_kernel_ncu.txt); None when the summary is absent."""
     try:
         tot = 0.0
-        for line in open(os.path.join(ROOT, "profiles", "r01_lauum_tile_kernel_ncu.txt")):
+        for line in open(os.path.join(ROOT, "profiles", "r02_dag_factor_kernel_ncu.txt")):
             if line.startswith("dram__bytes_read.sum =") or line.startswith("dram__bytes_write.sum ="):
                 val, unit = line.split("=")[1].split()[:2]
                 tot += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
@@ -307,19 +307,24 @@ def run_ours(args):
         # divided by the device-timed step is that kernel family's achieved rate INCLUDING the serial
         # Cholesky chain, launch gaps and the HBM-class kernels around it - the honest fraction of peak.
         roof = {"bound": "tensor",
-                "kernel": "tile_once_kernel<*> (FP64 DMMA tile contraction; all potrf/trtri/lauum launches of one "
-                          "evaluation, N^3 flop) - whole-step rate incl. the serial Cholesky chain and HBM-class kernels",
+                "kernel": "dag_factor_kernel (FP64 DMMA tile contraction; the Cholesky, triangular-inverse and X^T X tiles of "
+                          "one evaluation, N^3 flop, one persistent launch) - rate over the WHOLE step, i.e. including "
+                          "assembly, vector and trace kernels",
                 "achieved": eval_tf, "peak": peak_dmma, "unit": "TFLOP/s", "frac": eval_tf / peak_dmma,
                 "traffic": ncu_traffic_bytes(),
-                "traffic_note": "dram bytes of the lauum launch (N^3/3 of the step's flops) from the committed ncu --set full capture",
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the dag_factor_kernel launch from the committed "
+                                "ncu --set full capture; algorithmic minimum 3 x 4N(N+1) B (read Sigma, write L, X, Sigma^-1)",
+                "algorithmic_bytes": 4 * 4.0 * N * (N + 1),
                 "peak_source": "live FP64 DMMA m8n8k4 issue-rate probe (gpedm_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "peak_crosscheck": {"dfma_issue_TFLOPs": peak_dfma, "cublas_dgemm_8192_TFLOPs_r01": 35.9},
                 "flops_per_eval": n3,
                 "phases_ms": phases,
-                "phase_tflops": {"potrf": tf(n3 / 3, phases["potrf"]), "trtri": tf(n3 / 3, phases["trtri"]),
-                                 "lauum": tf(n3 / 3, phases["lauum"])},
-                "phase_frac": {"potrf": tf(n3 / 3, phases["potrf"]) / peak_dmma, "trtri": tf(n3 / 3, phases["trtri"]) / peak_dmma,
-                               "lauum": tf(n3 / 3, phases["lauum"]) / peak_dmma},
+                # potrf + trtri + lauum are ONE persistent launch (dag_factor_kernel: all N^3 flop of the step)
+                "factor_kernel": {"name": "dag_factor_kernel (Cholesky + triangular inverse + Sigma^-1 = X^T X, one persistent "
+                                          "dependency-driven launch)",
+                                  "ms": phases["potrf"] + phases["trtri"] + phases["lauum"],
+                                  "achieved": tf(n3, phases["potrf"] + phases["trtri"] + phases["lauum"]),
+                                  "frac": tf(n3, phases["potrf"] + phases["trtri"] + phases["lauum"]) / peak_dmma},
                 "hbm_kernels": {"assemble_GBs": 4.0 * N * (N + 1) / (phases["assemble"] * 1e-3) * 1e-9,
                                 "trace_GBs": 4.0 * N * (N + 1) / (phases["trace"] * 1e-3) * 1e-9,
                                 "assemble_frac": 4.0 * N * (N + 1) / (phases["assemble"] * 1e-3) * 1e-9 / hbm,

@@ -5,4 +5,4 @@ from ._lib import GPEDMError, build, lib  # noqa: F401
 from .core import (GPModel, fmingrad_Rprop, fp64_peak, getcov, getcovinv, getlikegrad, logit)  # noqa: F401
 from .fitgp import (GP, fitGP, getconditionals, getR2, getR2pop, getrhomatrix, makelags, predict,  # noqa: F401
                     predict_iter, predict_seq, summary, update)
-from .batch import fit_batch, fit_grid  # noqa: F401
+from .batch import b_profile, fit_batch, fit_grid, multistart  # noqa: F401

@@ -133,3 +133,83 @@ def fit_grid_hostprep(y, Es, taus, pop=None, ngpus=1, devices=None):
                         ln_post=-r["nllpost"], R2_insample=getR2(m["yobs"], ins), R2_loo=getR2(m["yobs"], loo),
                         status=r["status"]))
     return out
+
+
+def initpars_to_parst(initpars, d, single_pop):
+    """fitGP's transform of a constrained start (phi_1..d, ve, sigma2, rho) to the optimiser's scale
+    (R/GPfunctions.R:421-429; note rhomin = 0 here, 1e-4 inside getlikegrad)."""
+    ip = np.asarray(initpars, dtype=np.float64)
+    if len(ip) != d + 3:
+        raise ValueError("initpars must have number of predictors + 3 entries")
+    with np.errstate(divide="ignore"):
+        t = np.concatenate([np.log(ip[:d]), [logit(ip[d], VEMIN, VEMAX), logit(ip[d + 1], SIGMA2MIN, SIGMA2MAX),
+                                             logit(ip[d + 2], 0.0, 1.0)]])
+    if single_pop:
+        t[d + 2] = 0.0
+    return t
+
+
+def multistart(Y, X, pop=None, starts=None, nstarts=8, seed=0, ngpus=1, devices=None, **fit_kw):
+    """The same training set fitted from several starting points in ONE batched call - the remedy the
+    reference suggests against local minima ("One could try using different values of initpars",
+    vignettes/hierarchical.Rmd:47), which in R is a loop of fitGP(..., initpars=) calls.
+    starts: list of constrained initpars vectors (phi_1..d, ve, sigma2, rho); default: fitGP's own start
+    (R/GPfunctions.R:409) plus nstarts-1 random ones (phi log-uniform in [0.01, 2], ve in [0.001, 0.5],
+    sigma2 in [0.5, 4], rho in [0.1, 0.9]).  Returns (results sorted by ln_post descending, index of best)."""
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 1:
+        X = X[:, None]
+    d = X.shape[1]
+    single = pop is None or len(set(np.asarray(pop, dtype=object).tolist())) == 1
+    if starts is None:
+        rng = np.random.default_rng(seed)
+        starts = [np.concatenate([np.full(d, 0.1), [0.001, 1 - 0.001, 0.5]])]
+        for _ in range(nstarts - 1):
+            starts.append(np.concatenate([np.exp(rng.uniform(np.log(0.01), np.log(2.0), d)), [rng.uniform(0.001, 0.5)],
+                                          [rng.uniform(0.5, 4.0)], [rng.uniform(0.1, 0.9)]]))
+    probs = [dict(Y=Y, X=X, pop=pop, initparst=initpars_to_parst(s, d, single), **fit_kw) for s in starts]
+    res = fit_batch(probs, ngpus=ngpus, devices=devices)
+    for r, s in zip(res, starts):
+        r["initpars"] = np.asarray(s, dtype=np.float64)
+        r["ln_post"] = -r["nllpost"]
+    order = sorted(range(len(res)), key=lambda i: -res[i]["ln_post"] if res[i]["status"] == 0 else np.inf)
+    return [res[i] for i in order], order[0]
+
+
+def b_profile_problems(y, m, h, bs, z=None, pop=None):
+    """Training sets of the fisheries model's catchability search: for every candidate b the composite
+    predictor is x = m - b h (escapement, R/GPfisheries.R:247-251), then fitGP's global scaling and
+    complete-row selection (R/GPfunctions.R:378-385, :445-451); ytrans = "none".  The reference evaluates
+    these one b at a time inside optimize() (R/GPfisheries.R:114-117, objective GPnlike_fish :232-294)."""
+    y = np.asarray(y, dtype=np.float64)
+    m = np.asarray(m, dtype=np.float64).reshape(len(y), -1)
+    h = np.asarray(h, dtype=np.float64).reshape(len(y), -1)
+    if m.shape != h.shape:
+        raise ValueError("m and h must have the same number of columns")
+    zc = None if z is None else np.asarray(z, dtype=np.float64).reshape(len(y), -1)
+    popv = np.ones(len(y), dtype=np.int64).astype(object) if pop is None else np.asarray(pop, dtype=object)
+    probs = []
+    for b in bs:
+        x = m - float(b) * h
+        if zc is not None:
+            x = np.column_stack([x, zc])
+        yds = (y - _mean(y)) / _sd(y)
+        xds = (x - np.array([_mean(x[:, j]) for j in range(x.shape[1])])[None, :]) / \
+            np.array([_sd(x[:, j]) for j in range(x.shape[1])])[None, :]
+        ok = ~(np.isnan(yds) | np.isnan(xds).any(axis=1))
+        probs.append(dict(Y=yds[ok], X=xds[ok], pop=popv[ok]))
+    return probs
+
+
+def b_profile(y, m, h, bs, z=None, pop=None, ngpus=1, devices=None, **fit_kw):
+    """ln_post of the fisheries model over a grid of catchabilities b, all fits in ONE batched call; the
+    maximiser is what fitGP_fish's optimize() searches for (R/GPfisheries.R:114-117).  Returns a list of
+    dicts (b, ln_post, pars, iter, status) and the index of the best b."""
+    probs = b_profile_problems(y, m, h, bs, z, pop)
+    for p in probs:
+        p.update(fit_kw)
+    res = fit_batch(probs, ngpus=ngpus, devices=devices)
+    out = [dict(b=float(b), ln_post=-r["nllpost"], pars=r["pars"], iter=r["iter"], nevals=r["nevals"], status=r["status"])
+           for b, r in zip(bs, res)]
+    best = max(range(len(out)), key=lambda i: out[i]["ln_post"] if out[i]["status"] == 0 else -np.inf)
+    return out, best

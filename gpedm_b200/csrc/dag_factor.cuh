@@ -47,19 +47,26 @@ constexpr int DAG_SMEM_BYTES = (DAG_P + DAG_E) * (int)sizeof(double);
 
 enum DagTaskType { DAG_DIAG = 0, DAG_POTRF = 1, DAG_TRTRI = 2, DAG_LAUUM = 3 };
 
-struct DagArgs {
+// One factorisation problem.  A launch may carry the task lists of MANY independent fits (the lockstep
+// batch of mid-size fits, host_batch.cuh): their tasks are interleaved in one list, so a CTA that would
+// wait for one fit's chain picks up another fit's tile instead.
+struct DagFit {
   double* A;      // Sigma (lower tiles) -> L, in place
   double* X;      // L^-1 (lower tiles; diagonal tiles = D_j)
-  size_t ld;
-  int nb, n_valid;
   double* W;      // Sigma^-1 (lower tiles), written by the LAUUM tasks; before that, scratch for the running
                   // partial sums of TRTRI tiles that are computed in pieces
-  const int4* tasks;  // {type, i, j, kt0 | kt1 << 10 | piece << 20 | last << 30}: k tiles [kt0, kt1) of the tile
-  int ntasks;
-  // [0]: task counter; then four nb*nb int arrays: L final, X final, pieces done of L tile, pieces done of X tile
-  int* sync;
+  size_t ld;
+  int nb, n_valid;
+  int* flags;     // four nb*nb int arrays: L final, X final, pieces done of L tile, pieces done of X tile (zeroed per evaluation)
   double* logdet_part;
   int* info;
+};
+
+struct DagArgs {
+  const DagFit* fits;
+  const int4* tasks;  // {type | fit << 4, i, j, kt0 | kt1 << 10 | piece << 20 | last << 30}: k tiles [kt0, kt1) of the tile
+  int ntasks;
+  int* counter;       // next task to claim (zeroed per evaluation)
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -196,13 +203,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
   }
   __syncthreads();
   DagRing ring{full_bar, empty_bar, 0u, 0u};
-  const int nb = a.nb;
-  const size_t ld = a.ld;
-  int* counter = a.sync;
-  int* flagL = a.sync + 1;
-  int* flagX = flagL + nb * nb;
-  int* progL = flagX + nb * nb;
-  int* progX = progL + nb * nb;
+  int* counter = a.counter;
 
   for (;;) {
     if (tid == 0) s_task = atomicAdd(counter, 1);
@@ -210,7 +211,14 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
     const int tix = s_task;
     if (tix >= a.ntasks) break;
     const int4 tk = a.tasks[tix];
-    const int type = tk.x, ti = tk.y, tj = tk.z;
+    const int type = tk.x & 15, ti = tk.y, tj = tk.z;
+    const DagFit f = a.fits[tk.x >> 4];
+    const int nb = f.nb;
+    const size_t ld = f.ld;
+    int* flagL = f.flags;
+    int* flagX = flagL + nb * nb;
+    int* progL = flagX + nb * nb;
+    int* progX = progL + nb * nb;
     const int kt0 = tk.w & 1023, kt1 = (tk.w >> 10) & 1023, piece = (tk.w >> 20) & 1023;
     const bool last = (tk.w >> 30) & 1;
     DAG_TL(const unsigned long long tl_t0 = tl_now(); unsigned long long tl_wait = 0;)
@@ -226,8 +234,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       // ---------------- S_ij = sum_{k >= i} X_ki^T X_kj: both operands K-major, rows of X become final in
       // ascending order, so the k loop follows the inverse as it completes; no epilogue, no flag (nothing in
       // this kernel reads S)
-      const double* LAp = a.X + (size_t)ti * TB + (size_t)ti * TB * ld;
-      const double* LBp = a.X + (size_t)ti * TB + (size_t)tj * TB * ld;
+      const double* LAp = f.X + (size_t)ti * TB + (size_t)ti * TB * ld;
+      const double* LBp = f.X + (size_t)ti * TB + (size_t)tj * TB * ld;
       const bool act = !(ti == tj && n0 > m0 + MT * 8 - 1);
       double acc[MT][NT][2];
 #pragma unroll
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
       dag_kloop<true, true>(acc, ring, sA, sB, LAp, LBp, ld, nb - ti, flagX + ti * nb + ti, nb, flagX + ti * nb + tj, nb, act,
                             0u, tid DAG_TL(, tl_wait));
-      double* Sg = a.W + (size_t)ti * TB + (size_t)tj * TB * ld;
+      double* Sg = f.W + (size_t)ti * TB + (size_t)tj * TB * ld;
       if (act) {
 #pragma unroll
         for (int i = 0; i < MT; ++i)
@@ -252,23 +260,23 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
     double* Cpart;      // where a non-final piece leaves its partial result
     int* prog;
     if (!is_trtri) {
-      Ap = a.A + (size_t)ti * TB + (size_t)kt0 * TB * ld;
-      Bp = a.A + (size_t)tj * TB + (size_t)kt0 * TB * ld;
+      Ap = f.A + (size_t)ti * TB + (size_t)kt0 * TB * ld;
+      Bp = f.A + (size_t)tj * TB + (size_t)kt0 * TB * ld;
       fa = flagL + ti * nb + kt0;
       fb = flagL + tj * nb + kt0;
       fsb = 1;
-      Cg = a.A + (size_t)ti * TB + (size_t)tj * TB * ld;
+      Cg = f.A + (size_t)ti * TB + (size_t)tj * TB * ld;
       Cin = Cg;  // in place: Sigma tile, then Sigma - partial sums
       Cpart = Cg;
       prog = progL + ti * nb + tj;
     } else {
-      Ap = a.A + (size_t)ti * TB + (size_t)(tj + kt0) * TB * ld;
-      Bp = a.X + (size_t)(tj + kt0) * TB + (size_t)tj * TB * ld;
+      Ap = f.A + (size_t)ti * TB + (size_t)(tj + kt0) * TB * ld;
+      Bp = f.X + (size_t)(tj + kt0) * TB + (size_t)tj * TB * ld;
       fa = flagL + ti * nb + tj + kt0;
       fb = flagX + (tj + kt0) * nb + tj;
       fsb = nb;
-      Cg = a.X + (size_t)ti * TB + (size_t)tj * TB * ld;
-      Cpart = a.W + (size_t)ti * TB + (size_t)tj * TB * ld;
+      Cg = f.X + (size_t)ti * TB + (size_t)tj * TB * ld;
+      Cpart = f.W + (size_t)ti * TB + (size_t)tj * TB * ld;
       Cin = piece > 0 ? Cpart : nullptr;
       prog = progX + ti * nb + tj;
     }
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       double* rdiag = w + 64 * DG_WLD;
       double* dvec = rdiag + TB;
       double* colbuf = dvec + TB;
-      diag_cholesky_smem<DAG_THREADS>(T, rdiag, dvec, colbuf, tj, a.n_valid, a.info);
+      diag_cholesky_smem<DAG_THREADS>(T, rdiag, dvec, colbuf, tj, f.n_valid, f.info);
       auto lower_block_elem = [](int idx, int& r, int& c, bool& on_diag) {
         const int b = idx >> 9, e = idx & 511;
         const int bi = (b >= 6) ? 3 : ((b >= 3) ? 2 : ((b >= 1) ? 1 : 0)), bj = b - bi * (bi + 1) / 2;
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       }
       {
         double v = 0.0;
-        if (tid < TB && tj * TB + tid < a.n_valid) v = log(dvec[tid]);
+        if (tid < TB && tj * TB + tid < f.n_valid) v = log(dvec[tid]);
         __syncthreads();
         if (tid < TB) {
 #pragma unroll
@@ -367,10 +375,10 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
           if ((tid & 31) == 0) dvec[tid >> 5] = v;
         }
         __syncthreads();
-        if (tid == 0) a.logdet_part[tj] = ((dvec[0] + dvec[1]) + dvec[2]) + dvec[3];
+        if (tid == 0) f.logdet_part[tj] = ((dvec[0] + dvec[1]) + dvec[2]) + dvec[3];
       }
       diag_invert_smem<DAG_THREADS>(T, w, rdiag);
-      double* Dg = a.X + (size_t)tj * TB * (ld + 1);
+      double* Dg = f.X + (size_t)tj * TB * (ld + 1);
 #pragma unroll 4
       for (int idx = tid; idx < 10 * 512; idx += DAG_THREADS) {
         int r, c;
@@ -399,7 +407,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
     //   TRTRI: C = -D_i T    (A operand = D_i streamed,  B operand = T resident)
     // D is lower triangular: DMMAs whose D fragment is identically zero are skipped.
     const int dblk = is_trtri ? ti : tj;
-    const double* Dg = a.X + (size_t)dblk * TB * (ld + 1);
+    const double* Dg = f.X + (size_t)dblk * TB * (ld + 1);
     warp_wait_flag(flagL + dblk * nb + dblk, lane DAG_TL(, tl_wait));
     auto issue_e = [&](int j) {
       const int s = ring.gi % NS, r = ring.gi / NS;

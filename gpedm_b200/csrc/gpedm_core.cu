@@ -25,6 +25,7 @@
 #include "kernels.cuh"
 #include "diag_block.cuh"
 #include "dag_factor.cuh"
+#include "mid_batch.cuh"
 #include "small_fit.cuh"
 #include "lag_prep.cuh"
 

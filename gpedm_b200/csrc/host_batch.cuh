@@ -271,6 +271,388 @@ static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_
   return 0;
 }
 
+// ------------------------------------------------------------------------------- batched mid-size fits
+// All fits of a batch with 128 < N <= GPEDM_MID_MAX_N advance in lockstep (mid_batch.cuh): per Rprop
+// iteration ONE round of launches evaluates every still-active fit - assembly, the persistent
+// factorisation kernel over the interleaved task lists of all fits, the two triangular matrix-vector
+// products, the trace terms, the scalar reductions - and the scalar Rprop logic of fmingrad_Rprop
+// (reference R/GPfunctions.R:522-584) runs on the host per fit exactly as in gpedm_fit_rprop.
+static const int g_mid_max_n = getenv("GPEDM_MID_MAX_N") ? atoi(getenv("GPEDM_MID_MAX_N")) : 1024;
+static const bool g_no_mid_batch = getenv("GPEDM_NO_MID_BATCH") != nullptr && atoi(getenv("GPEDM_NO_MID_BATCH")) != 0;
+
+static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fit_desc* descs,
+                         const gpedm_rprop_options* opts_in, gpedm_result* results) {
+  const int nf = (int)idx.size();
+  if (nf == 0) return 0;
+  NvtxRange nvtx_entry("gpedm:fit_batch_mid");
+  CU(cudaSetDevice(device));
+  int rc = ensure_kernel_attrs(device);
+  if (rc) return rc;
+  gpedm_rprop_options o;
+  if (opts_in)
+    o = *opts_in;
+  else
+    gpedm_default_rprop_options(&o);
+  const double eta_minus = o.eta_minus - 1, eta_plus = o.eta_plus - 1;
+  const int sms = (device < 64 && g_num_sms[device] > 0) ? g_num_sms[device] : 148;
+  // ---- layout of one device arena: per fit the three work matrices, vectors, partials, flags
+  struct Lay {
+    size_t A, X, S, dX, dY, dpop, rhotab, z, a, diagS, part, logdet, tracepart, scal, flags, params;
+    int N, d, np, nb, Np, ntiles, split, nflags;
+  };
+  std::vector<Lay> lay(nf);
+  size_t tot = 0;
+  auto take = [&](size_t bytes) {
+    size_t off = tot;
+    tot += (bytes + 255) & ~(size_t)255;
+    return off;
+  };
+  int dmax = 1;
+  size_t flags_begin = 0, flags_end = 0;
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    if (ds.N < 1 || ds.d < 1 || ds.d > GPEDM_MAX_D || ds.np < 1 || !ds.X || !ds.Y || !ds.pop || !ds.initparst)
+      return set_err(GPEDM_ERR_ARG, "bad descriptor for fit %d", idx[q]);
+    for (int64_t i = 0; i < ds.N; ++i)
+      if (ds.pop[i] < 0 || ds.pop[i] >= ds.np) return set_err(GPEDM_ERR_ARG, "fit %d: pop code outside 0..np-1", idx[q]);
+    Lay& L = lay[q];
+    L.N = (int)ds.N;
+    L.d = ds.d;
+    L.np = ds.np;
+    L.nb = ceil_div(L.N, TB);
+    L.Np = L.nb * TB;
+    L.ntiles = L.nb * (L.nb + 1) / 2;
+    L.split = 4;  // few tiles per fit: four column ranges per tile in the assembly / trace kernels
+    L.nflags = 4 * L.nb * L.nb;
+    dmax = std::max(dmax, L.d);
+  }
+  for (int q = 0; q < nf; ++q) {  // flags of all fits contiguous: one memset per iteration
+    if (q == 0) flags_begin = tot;
+    lay[q].flags = take((size_t)lay[q].nflags * 4);
+    flags_end = tot;
+  }
+  const size_t counter_off = take(4);
+  const size_t info_off = take((size_t)nf * 4);
+  size_t x_begin = tot, x_end = tot;
+  for (int q = 0; q < nf; ++q) {  // X matrices contiguous: zeroed once (upper part of their diagonal tiles is never written)
+    lay[q].X = take((size_t)lay[q].Np * lay[q].Np * 8);
+    x_end = tot;
+  }
+  for (int q = 0; q < nf; ++q) {
+    Lay& L = lay[q];
+    const size_t mat = (size_t)L.Np * L.Np * 8;
+    L.A = take(mat);
+    L.S = take(mat);
+    L.dX = take((size_t)L.N * L.d * 8);
+    L.dY = take((size_t)L.Np * 8);
+    L.dpop = take((size_t)L.N * 4);
+    L.rhotab = descs[idx[q]].rhomat ? take((size_t)L.np * L.np * 8) : 0;
+    L.z = take((size_t)L.Np * 8);
+    L.a = take((size_t)L.Np * 8);
+    L.diagS = take((size_t)L.Np * 8);
+    L.part = take((size_t)L.nb * L.Np * 8);
+    L.logdet = take((size_t)L.nb * 8);
+    L.tracepart = take((size_t)L.ntiles * L.split * (MAXD + 3) * 8);
+    L.scal = take((size_t)NSCAL * 8);
+    L.params = take(sizeof(EvalParams));
+  }
+  DevBuf arena, dFits, dDag, dTasks, dMapTS, dMapT, dMapV, dActive;
+  PinnedBuf pParams, pScal, pInfo;
+  cudaError_t e = arena.alloc(tot);
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "mid-size batch: cudaMalloc of %zu bytes failed: %s", tot, cudaGetErrorString(e));
+  char* base = (char*)arena.p;
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  StreamGuard stg;
+  stg.s = st;
+  // ---- per-fit descriptors, static per-fit task lists, uploads
+  std::vector<MidFit> hfits(nf);
+  std::vector<DagFit> hdag(nf);
+  std::vector<std::vector<int4>> ftasks(nf);
+  std::vector<gpedm_fit_s> meta(nf);
+  e = pParams.alloc(sizeof(EvalParams) * nf);
+  if (e == cudaSuccess) e = pScal.alloc((size_t)NSCAL * 8 * nf);
+  if (e == cudaSuccess) e = pInfo.alloc((size_t)nf * 4);
+  if (e == cudaSuccess) e = cudaMemsetAsync(base + x_begin, 0, x_end - x_begin, st);
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "mid-size batch setup failed: %s", cudaGetErrorString(e));
+  EvalParams* hparams = (EvalParams*)pParams.p;
+  double* hscal = (double*)pScal.p;
+  int* hinfo = (int*)pInfo.p;
+  size_t total_tasks = 0, nTS = 0, nT = 0, nV = 0;
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    const Lay& L = lay[q];
+    MidFit& F = hfits[q];
+    F.A = (double*)(base + L.A);
+    F.X = (double*)(base + L.X);
+    F.S = (double*)(base + L.S);
+    F.ld = L.Np;
+    F.N = L.N;
+    F.nb = L.nb;
+    F.ntiles = L.ntiles;
+    F.split = L.split;
+    F.d = L.d;
+    F.pad = 0;
+    F.dX = (const double*)(base + L.dX);
+    F.dpop = (const int*)(base + L.dpop);
+    F.drhotab = ds.rhomat ? (const double*)(base + L.rhotab) : nullptr;
+    F.P = (const EvalParams*)(base + L.params);
+    F.dY = (const double*)(base + L.dY);
+    F.dz = (double*)(base + L.z);
+    F.da = (double*)(base + L.a);
+    F.ddiagS = (double*)(base + L.diagS);
+    F.dpart = (double*)(base + L.part);
+    F.dlogdet = (double*)(base + L.logdet);
+    F.dtracepart = (double*)(base + L.tracepart);
+    F.dscal = (double*)(base + L.scal);
+    DagFit& G = hdag[q];
+    G.A = F.A;
+    G.X = F.X;
+    G.W = F.S;
+    G.ld = L.Np;
+    G.nb = L.nb;
+    G.n_valid = L.N;
+    G.flags = (int*)(base + L.flags);
+    G.logdet_part = F.dlogdet;
+    G.info = (int*)(base + info_off) + q;
+    int nfac = 0;
+    build_dag_tasks(L.nb, 1, 0, 512, q, ftasks[q], &nfac);  // strict dependency order: any number of CTAs makes progress
+    total_tasks += ftasks[q].size();
+    nTS += (size_t)L.ntiles * L.split;
+    nT += L.ntiles;
+    nV += ceil_div(L.Np, 256);
+    e = cudaMemcpyAsync((void*)F.dX, ds.X, (size_t)L.N * L.d * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync((void*)F.dY, 0, (size_t)L.Np * 8, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((void*)F.dY, ds.Y, (size_t)L.N * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((void*)F.dpop, ds.pop, (size_t)L.N * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && ds.rhomat)
+      e = cudaMemcpyAsync((void*)F.drhotab, ds.rhomat, (size_t)L.np * L.np * 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "mid-size batch upload failed: %s", cudaGetErrorString(e));
+    gpedm_fit_s& m = meta[q];
+    m.N = ds.N;
+    m.d = ds.d;
+    m.np = ds.np;
+    m.p = ds.d + 3;
+    m.has_rhomat = ds.rhomat != nullptr;
+    m.single_pop = true;
+    for (int64_t i = 1; i < ds.N; ++i)
+      if (ds.pop[i] != ds.pop[0]) m.single_pop = false;
+    m.hparams = hparams + q;
+    m.hscal = hscal + (size_t)q * NSCAL;
+  }
+  e = dFits.alloc(sizeof(MidFit) * nf);
+  if (e == cudaSuccess) e = dDag.alloc(sizeof(DagFit) * nf);
+  if (e == cudaSuccess) e = dTasks.alloc(total_tasks * sizeof(int4));
+  if (e == cudaSuccess) e = dMapTS.alloc(nTS * sizeof(int2));
+  if (e == cudaSuccess) e = dMapT.alloc(nT * sizeof(int2));
+  if (e == cudaSuccess) e = dMapV.alloc(nV * sizeof(int2));
+  if (e == cudaSuccess) e = dActive.alloc((size_t)nf * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dFits.p, hfits.data(), sizeof(MidFit) * nf, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dDag.p, hdag.data(), sizeof(DagFit) * nf, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "mid-size batch setup failed: %s", cudaGetErrorString(e));
+  const int DC = dmax <= 8 ? 8 : (dmax <= 12 ? 12 : (dmax <= 16 ? 16 : 32));
+  const int asm_smem = 2 * dmax * TB * 8 + 2 * TB * 4;
+  const int trace_smem = (2 * dmax * TB + 2 * TB + DC + 8 * (DC + 3)) * 8 + 2 * TB * 4;
+  static std::mutex attr_mu;
+  {
+    std::lock_guard<std::mutex> lock(attr_mu);
+    const int big = (2 * MAXD * TB + 2 * TB + MAXD + 8 * (MAXD + 3)) * 8 + 2 * TB * 4;
+    cudaFuncSetAttribute(mid_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(mid_trace_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(mid_trace_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(mid_trace_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(mid_trace_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  }
+  std::vector<int> active;
+  std::vector<int4> tasks;
+  std::vector<int2> mapTS, mapT, mapV;
+  // one round of launches: evaluate every fit in `active` at the parameters in hparams
+  static const bool trace_iters = getenv("GPEDM_MID_TRACE") != nullptr;
+  int round_no = 0;
+  auto launch = [&](int full) -> int {
+    const int na = (int)active.size();
+    if (na == 0) return 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    // interleave the active fits' task lists position by position; per-CTA maps of the tiled kernels
+    tasks.clear();
+    mapTS.clear();
+    mapT.clear();
+    mapV.clear();
+    size_t maxlen = 0;
+    for (int q : active) maxlen = std::max(maxlen, ftasks[q].size());
+    for (size_t pos = 0; pos < maxlen; ++pos)
+      for (int q : active)
+        if (pos < ftasks[q].size()) tasks.push_back(ftasks[q][pos]);
+    for (int q : active) {
+      const Lay& L = lay[q];
+      for (int b = 0; b < L.ntiles * L.split; ++b) mapTS.push_back(make_int2(q, b));
+      for (int b = 0; b < L.ntiles; ++b) mapT.push_back(make_int2(q, b));
+      for (int b = 0; b < ceil_div(L.Np, 256); ++b) mapV.push_back(make_int2(q, b));
+    }
+    cudaError_t e2 = cudaSuccess;
+    for (int q : active)
+      if (e2 == cudaSuccess)
+        e2 = cudaMemcpyAsync(base + lay[q].params, hparams + q, sizeof(EvalParams), cudaMemcpyHostToDevice, st);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(dTasks.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, st);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(dMapTS.p, mapTS.data(), mapTS.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(dMapT.p, mapT.data(), mapT.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(dMapV.p, mapV.data(), mapV.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(dActive.p, active.data(), (size_t)na * 4, cudaMemcpyHostToDevice, st);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(base + flags_begin, 0, flags_end - flags_begin, st);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(base + counter_off, 0, 4, st);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(base + info_off, 0, (size_t)nf * 4, st);
+    if (e2 != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "mid-size batch upload failed: %s", cudaGetErrorString(e2));
+    const MidFit* F = (const MidFit*)dFits.p;
+    mid_assemble_kernel<<<(unsigned)mapTS.size(), 256, asm_smem, st>>>(F, (const int2*)dMapTS.p);
+    DagArgs da;
+    da.fits = (const DagFit*)dDag.p;
+    da.tasks = (const int4*)dTasks.p;
+    da.ntasks = (int)tasks.size();
+    da.counter = (int*)(base + counter_off);
+    dag_factor_kernel<<<std::min(sms, da.ntasks), DAG_THREADS, DAG_SMEM_BYTES, st>>>(da);
+    mid_trmv_n_kernel<<<(unsigned)mapT.size(), 256, 0, st>>>(F, (const int2*)dMapT.p);
+    mid_reduce_kernel<<<(unsigned)mapV.size(), 256, 0, st>>>(F, (const int2*)dMapV.p, 0);
+    mid_trmv_t_kernel<<<(unsigned)mapT.size(), 256, 0, st>>>(F, (const int2*)dMapT.p);
+    mid_reduce_kernel<<<(unsigned)mapV.size(), 256, 0, st>>>(F, (const int2*)dMapV.p, 1);
+    if (DC == 8)
+      mid_trace_kernel<8><<<(unsigned)mapTS.size(), 256, trace_smem, st>>>(F, (const int2*)dMapTS.p);
+    else if (DC == 12)
+      mid_trace_kernel<12><<<(unsigned)mapTS.size(), 256, trace_smem, st>>>(F, (const int2*)dMapTS.p);
+    else if (DC == 16)
+      mid_trace_kernel<16><<<(unsigned)mapTS.size(), 256, trace_smem, st>>>(F, (const int2*)dMapTS.p);
+    else
+      mid_trace_kernel<32><<<(unsigned)mapTS.size(), 256, trace_smem, st>>>(F, (const int2*)dMapTS.p);
+    if (full) mid_extract_diag_kernel<<<(unsigned)mapV.size(), 256, 0, st>>>(F, (const int2*)dMapV.p);
+    mid_final_reduce_kernel<<<na, 256, 0, st>>>(F, (const int*)dActive.p, full);
+    for (int q : active)
+      if (e2 == cudaSuccess)
+        e2 = cudaMemcpyAsync(hscal + (size_t)q * NSCAL, base + lay[q].scal, (size_t)NSCAL * 8, cudaMemcpyDeviceToHost, st);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(hinfo, base + info_off, (size_t)nf * 4, cudaMemcpyDeviceToHost, st);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+    if (e2 == cudaSuccess) e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "mid-size batch evaluation failed: %s", cudaGetErrorString(e2));
+    if (trace_iters)
+      fprintf(stderr, "[gpedm mid] round %d: %d active fits, %zu tasks, %.3f ms\n", round_no,
+              na, tasks.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    ++round_no;
+    return 0;
+  };
+  struct State {
+    double pa[GPEDM_MAX_P], del[GPEDM_MAX_P], grad[GPEDM_MAX_P], panew[GPEDM_MAX_P];
+    double nll = 0, s = 0, df = 10;
+    int iter = 0, nevals = 0, status = 0;
+  };
+  std::vector<State> stt(nf);
+  std::vector<HostPars> hp(nf);
+  // ---- initial evaluation (:545)
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    for (int i = 0; i < ds.d + 3; ++i) {
+      stt[q].pa[i] = stt[q].panew[i] = ds.initparst[i];
+      stt[q].del[i] = o.delta0;
+    }
+    host_transform(&meta[q], stt[q].panew, ds.modeprior, ds.fixedpars, ds.rhofixed, hp[q]);
+    fill_params(&meta[q], hp[q]);
+    active.push_back(q);
+  }
+  rc = launch(0);
+  bool first = true;
+  while (rc == 0) {
+    std::vector<int> next_active;
+    for (int q : active) {
+      State& S = stt[q];
+      const gpedm_fit_desc& ds = descs[idx[q]];
+      gpedm_result r;
+      finish_result(&meta[q], hp[q], false, &r);
+      S.nevals++;
+      if (hinfo[q] > 0) {
+        S.status = hinfo[q];
+        continue;
+      }
+      const int p = ds.d + 3;
+      if (first) {
+        S.nll = r.nllpost;
+        for (int i = 0; i < p; ++i) S.grad[i] = r.grad[i];
+        S.s = r.gradnorm;
+      } else {
+        S.s = r.gradnorm;
+        S.df = fabs(r.nllpost / S.nll - 1);  // :565
+        for (int i = 0; i < p; ++i) {
+          const double gc = S.grad[i] * r.grad[i];
+          const double tdel = S.del[i] * (1 + eta_plus * (gc > 0) + eta_minus * (gc < 0));  // :569
+          S.del[i] = tdel < o.deltamin ? o.deltamin : (tdel > o.deltamax ? o.deltamax : tdel);
+          S.pa[i] = S.panew[i];
+          S.grad[i] = r.grad[i];
+        }
+        S.nll = r.nllpost;
+        S.iter++;
+      }
+      if (S.s > o.tol_grad && S.iter < o.maxiter && S.df > o.tol_df) {  // :556
+        for (int i = 0; i < p; ++i) S.panew[i] = S.pa[i] - sgn(S.grad[i]) * S.del[i];  // :559
+        host_transform(&meta[q], S.panew, ds.modeprior, ds.fixedpars, ds.rhofixed, hp[q]);
+        fill_params(&meta[q], hp[q]);
+        next_active.push_back(q);
+      }
+    }
+    first = false;
+    active.swap(next_active);
+    if (active.empty()) break;
+    rc = launch(0);
+  }
+  // ---- final full evaluation at each fit's last parameters (:580)
+  if (rc == 0) {
+    active.clear();
+    for (int q = 0; q < nf; ++q) {
+      if (stt[q].status != 0) continue;
+      const gpedm_fit_desc& ds = descs[idx[q]];
+      host_transform(&meta[q], stt[q].pa, ds.modeprior, ds.fixedpars, ds.rhofixed, hp[q]);
+      fill_params(&meta[q], hp[q]);
+      active.push_back(q);
+    }
+    rc = launch(1);
+  }
+  if (rc) return rc;
+  int first_bad = 0;
+  std::vector<double> ha, hd;
+  for (int q = 0; q < nf; ++q) {
+    const gpedm_fit_desc& ds = descs[idx[q]];
+    gpedm_result& R = results[idx[q]];
+    State& S = stt[q];
+    if (S.status == 0 && hinfo[q] > 0) S.status = hinfo[q];
+    if (S.status != 0) {
+      memset(&R, 0, sizeof(R));
+      R.status = S.status;
+      R.iter = S.iter;
+      R.nevals = S.nevals;
+      R.p = ds.d + 3;
+      if (!first_bad) first_bad = S.status;
+      continue;
+    }
+    finish_result(&meta[q], hp[q], true, &R);
+    R.iter = S.iter;
+    R.nevals = S.nevals + 1;
+    R.status = 0;
+    if ((ds.want_loo && (ds.loo_mean || ds.loo_var)) || ds.insamp_mean || ds.insamp_var) {
+      ha.resize(ds.N);
+      hd.resize(ds.N);
+      e = cudaMemcpy(ha.data(), base + lay[q].a, (size_t)ds.N * 8, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(hd.data(), base + lay[q].diagS, (size_t)ds.N * 8, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "mid-size batch download failed: %s", cudaGetErrorString(e));
+      const double ve = hp[q].ve;
+      for (int64_t i = 0; i < ds.N; ++i) {
+        const double a = ha[i], sii = hd[i], y = ds.Y[i];
+        if (ds.want_loo && ds.loo_mean) ds.loo_mean[i] = y - a / sii;
+        if (ds.want_loo && ds.loo_var) ds.loo_var[i] = 1.0 / sii - ve;
+        if (ds.insamp_mean) ds.insamp_mean[i] = y - ve * a;
+        if (ds.insamp_var) ds.insamp_var[i] = ve - ve * ve * sii;
+      }
+    }
+  }
+  if (first_bad) return set_err(first_bad, "at least one mid-size fit failed: covariance matrix not positive definite (pivot %d)", first_bad);
+  return 0;
+}
+
 // Concurrent fits per GPU.  Independent fits interleave on one device and fill each other's
 // chain-bound stretches: measured at N ~ 8190 (8 grid cells, one B200) 20.18 ms per evaluation with one
 // worker, 18.73 with two, 18.37 with three; memory is 3 N^2 doubles per resident fit.
@@ -478,12 +860,25 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
   // Fits with N <= 128 (one tile) advance in lockstep through the batched one-CTA-per-fit kernel,
   // one host thread per GPU over a strided share; everything larger goes through the tiled
   // pipeline, pulled from a shared queue by W worker threads per GPU.  Both kinds run concurrently.
-  std::vector<int> small_order, big_order;
-  for (int q = 0; q < nfits; ++q) (descs[order[q]].N <= TB && !g_no_small_batch ? small_order : big_order).push_back(order[q]);
+  std::vector<int> small_order, mid_order, big_order;
+  for (int q = 0; q < nfits; ++q) {
+    const int64_t n = descs[order[q]].N;
+    if (n <= TB && !g_no_small_batch)
+      small_order.push_back(order[q]);
+    else if (n > TB && n <= g_mid_max_n && !g_no_mid_batch)
+      mid_order.push_back(order[q]);
+    else
+      big_order.push_back(order[q]);
+  }
   if (small_order.size() < 2) {  // a single small fit gains nothing from the batched kernel
-    big_order = order;
+    big_order.insert(big_order.end(), small_order.begin(), small_order.end());
     small_order.clear();
   }
+  if (mid_order.size() < 2) {  // likewise for the lockstep mid-size path
+    big_order.insert(big_order.end(), mid_order.begin(), mid_order.end());
+    mid_order.clear();
+  }
+  std::stable_sort(big_order.begin(), big_order.end(), [&](int a, int b) { return cost(a) > cost(b); });
   const int nbig = (int)big_order.size();
   std::atomic<int> next(0);
   std::vector<std::vector<BatchRecord>> per_gpu(ngpus);
@@ -495,14 +890,16 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
   for (int i : big_order) nmax = std::max<int64_t>(nmax, descs[i].N);
   // small problems leave most of the GPU idle -> interleave several fits; large ones already fill it
   const int W = default_workers_per_gpu(nmax, nbig, ngpus);
-  std::vector<std::vector<BatchRecord>> per_worker(ngpus * (W + 1));  // slot W of each GPU: the small-fit thread
-  std::vector<std::string> werrs(ngpus * (W + 1));
+  // slots W, W+1 of each GPU: the lockstep threads of the small (N <= 128) and mid-size fits
+  const int WS = W + 2;
+  std::vector<std::vector<BatchRecord>> per_worker(ngpus * WS);
+  std::vector<std::string> werrs(ngpus * WS);
   // The queue is ordered by descending cost.  The first pick of every worker is static and interleaved
   // across GPUs (worker w of GPU g takes entry w * ngpus + g) so that the heaviest fits start on
   // different devices; everything after that is pulled dynamically.
   next.store(std::min(nbig, ngpus * W));
   auto worker = [&](int g, int w) {
-    const int wi = g * (W + 1) + w;
+    const int wi = g * WS + w;
     cudaSetDevice(devs[g]);
     bool first = true;
     for (;;) {
@@ -519,13 +916,38 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
       per_worker[wi].push_back(rec);
     }
   };
-  auto small_worker = [&](int g) {
-    const int wi = g * (W + 1) + W;
+  auto lockstep_worker = [&](int g, bool mid) {
+    const int wi = g * WS + W + (mid ? 1 : 0);
+    const std::vector<int>& pool = mid ? mid_order : small_order;
     std::vector<int> mine;
-    for (size_t q = g; q < small_order.size(); q += ngpus) mine.push_back(small_order[q]);
+    for (size_t q = g; q < pool.size(); q += ngpus) mine.push_back(pool[q]);  // strided share of the cost-ordered list
     if (mine.empty()) return;
     std::vector<gpedm_result> tmp(nfits);
-    int rc = fit_batch_small(devs[g], mine, descs, opts, tmp.data());
+    int rc = 0;
+    if (!mid) {
+      rc = fit_batch_small(devs[g], mine, descs, opts, tmp.data());
+    } else {
+      // waves of at most ~48 GB of work matrices (3 Np^2 doubles per fit)
+      const double cap = 48e9;
+      size_t b = 0;
+      while (b < mine.size()) {
+        double bytes = 0;
+        size_t e2 = b;
+        while (e2 < mine.size()) {
+          const double np_ = (double)ceil_div((int)descs[mine[e2]].N, TB) * TB;
+          if (e2 > b && bytes + 24.0 * np_ * np_ > cap) break;
+          bytes += 24.0 * np_ * np_;
+          ++e2;
+        }
+        std::vector<int> wave(mine.begin() + b, mine.begin() + e2);
+        int rcw = fit_batch_mid(devs[g], wave, descs, opts, tmp.data());
+        if (rcw != 0 && rc == 0) {
+          rc = rcw;
+          werrs[wi] = gpedm_last_error();
+        }
+        b = e2;
+      }
+    }
     if (rc != 0) werrs[wi] = gpedm_last_error();
     for (int i : mine) {
       BatchRecord rec;
@@ -541,7 +963,9 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
     std::vector<std::thread> th;
     try {
       if (!small_order.empty())
-        for (int g = 0; g < ngpus; ++g) th.emplace_back(small_worker, g);
+        for (int g = 0; g < ngpus; ++g) th.emplace_back(lockstep_worker, g, false);
+      if (!mid_order.empty())
+        for (int g = 0; g < ngpus; ++g) th.emplace_back(lockstep_worker, g, true);
       if (nbig > 0)
         for (int g = 0; g < ngpus; ++g)
           for (int w = 0; w < W; ++w) th.emplace_back(worker, g, w);
@@ -552,8 +976,8 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
     }
     for (auto& t : th) t.join();
   }
-  for (int wi = 0; wi < ngpus * (W + 1); ++wi) {
-    const int g = wi / (W + 1);
+  for (int wi = 0; wi < ngpus * WS; ++wi) {
+    const int g = wi / WS;
     per_gpu[g].insert(per_gpu[g].end(), per_worker[wi].begin(), per_worker[wi].end());
     if (errs[g].empty() && !werrs[wi].empty()) errs[g] = werrs[wi];
   }

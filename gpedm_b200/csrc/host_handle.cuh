@@ -25,7 +25,9 @@ struct gpedm_fit_s {
   int ntasks = 0;          // all tasks: Cholesky, inverse, Sigma^-1 = X^T X
   int ntasks_factor = 0;   // without the trailing Sigma^-1 tasks (sequential helper: only L and z are needed)
   int* dsync = nullptr;    // its task counter + per-tile ready flags, zeroed at the start of every evaluation
+  DagFit* dfit = nullptr;  // its description of this fit's matrices
   int num_sms = 148;
+  int tile_split = 1;  // CTAs per 128 x 128 tile in the assembly / trace kernels (column ranges; > 1 below one wave of tiles)
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // gradient-only / full / through-z variants
   int64_t graph_launches[3] = {0, 0, 0};
   const double* dsigma_in = nullptr;  // gpedm_covinv: factor this N x N matrix instead of assembling Sigma
@@ -113,8 +115,9 @@ static int ensure_kernel_attrs(int device) {
   CU(cudaFuncSetAttribute(small_eval_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<8>()));
   CU(cudaFuncSetAttribute(small_eval_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<16>()));
   CU(cudaFuncSetAttribute(small_eval_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_eval_smem_bytes<32>()));
-  int trace_smem = (4 * MAXD * TB + 2 * TB + 8 * (MAXD + 3)) * 8 + 2 * TB * 4;
+  int trace_smem = (2 * MAXD * TB + 2 * TB + MAXD + 8 * (MAXD + 3)) * 8 + 2 * TB * 4;
   CU(cudaFuncSetAttribute(grad_trace_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
+  CU(cudaFuncSetAttribute(grad_trace_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
   CU(cudaFuncSetAttribute(grad_trace_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
   CU(cudaFuncSetAttribute(grad_trace_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
   int asm_smem = 2 * MAXD * TB * 8 + 2 * TB * 4;
@@ -182,7 +185,7 @@ static void free_handle(gpedm_fit_s* h) {
     if (h->aux) cudaStreamSynchronize(h->aux);
     void* bufs[] = {h->dX, h->dY, h->drhotab, h->dpop, h->bufA, h->bufB, h->bufC, h->dparams, h->dz, h->da,
                     h->ddiagS, h->dpart, h->dlogdet, h->dtracepart, h->dscal, h->dinfo, h->dcenter, h->dscale,
-                    h->dtasks, h->dsync};
+                    h->dtasks, h->dsync, h->dfit};
     for (void* b : bufs)
       if (b) cudaFreeAsync(b, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -210,6 +213,59 @@ static void free_handle(gpedm_fit_s* h) {
     fprintf(stderr, "[gpedm free] device bufs %.2f ms, pinned %.2f, graphs %.2f, events %.2f, streams %.2f\n", t1 - t0,
             t2 - t1, t3 - t2, t4 - t3, t5 - t4);
   delete h;
+}
+
+// ------------------------------------------------------------------------------- factorisation task list
+// Task list of the persistent factorisation kernel (dag_factor.cuh).  A tile whose k loop is longer
+// than `ch` tiles is computed in PIECES of ch k tiles (running partial result kept in place / in the
+// scratch matrix); only the last piece carries the epilogue.  Placement by "column step" s:
+//   * final piece of POTRF(i, s), i >= s + 2, and of TRTRI row s - lag: at step s;
+//   * the two chain tasks of block column c - DIAG(c) and POTRF(c+1, c) - `lead` steps early: their
+//     CTAs are then resident, with everything but the last k tiles accumulated, when the chain arrives;
+//   * a non-final piece as soon as its operands are final, staggered over the following ch steps so
+//     that the bulk work never queues up in front of the chain.
+// Within a step: chain tasks, Cholesky tiles, inverse tiles, then pieces.  Every dependency of a task
+// precedes it in the list, except that chain tasks may precede theirs (bounded: 2 (lead + 1) tasks).
+static void build_dag_tasks(int nb, int lag, int lead, int ch, int fit, std::vector<int4>& tasks, int* nfactor) {
+  struct Ev {
+    int step, cls, seq;
+    int4 t;
+  };
+  std::vector<Ev> evs;
+  evs.reserve((size_t)nb * nb * 2);
+  int seq = 0;
+  auto word = [](int kt0, int kt1, int piece, int last) { return kt0 | (kt1 << 10) | (piece << 20) | (last << 30); };
+  // tile (type, i, j) with nkt k tiles; koff: TRTRI operand rows start at block row j
+  auto add_tile = [&](int type, int i, int j, int nkt, int final_step, int cls, int ready_off, int partial_cap) {
+    const int np = std::max(1, (nkt + ch - 1) / ch);
+    for (int q = 0; q + 1 < np; ++q) {
+      const int e = ready_off + (q + 1) * ch;  // first step at which the operands of piece q are final
+      const int st = std::max(e, std::min(e + (i + j) % ch, partial_cap));
+      evs.push_back({st, 3, seq++, make_int4(type | (fit << 4), i, j, word(q * ch, (q + 1) * ch, q, 0))});
+    }
+    evs.push_back({final_step, cls, seq++, make_int4(type | (fit << 4), i, j, word((np - 1) * ch, nkt, np - 1, 1))});
+  };
+  for (int c = 0; c < nb; ++c) {
+    const int fs = std::max(0, c - lead);
+    add_tile(DAG_DIAG, c, c, c, fs, 0, 0, std::max(0, fs - 1));
+    if (c + 1 < nb) add_tile(DAG_POTRF, c + 1, c, c, fs, 0, 0, std::max(0, fs - 1));
+    for (int i = c + 2; i < nb; ++i) add_tile(DAG_POTRF, i, c, c, c, 1, 0, c - 1);
+  }
+  for (int r = 1; r < nb; ++r)
+    for (int j = 0; j < r; ++j) add_tile(DAG_TRTRI, r, j, r - j, r + lag, 2, j + lag, r + lag - 1);
+  std::stable_sort(evs.begin(), evs.end(), [](const Ev& x, const Ev& y) {
+    if (x.step != y.step) return x.step < y.step;
+    if (x.cls != y.cls) return x.cls < y.cls;
+    return x.seq < y.seq;
+  });
+  tasks.resize(evs.size());
+  for (size_t q = 0; q < evs.size(); ++q) tasks[q] = evs[q].t;
+  *nfactor = (int)tasks.size();
+  // Sigma^-1 = X^T X after the inverse, longest k range first.  S_ij sums over block rows k >= i of X in
+  // ascending order - the order in which the inverse completes them - so the CTAs that run out of inverse
+  // tiles at the end of the factorisation accumulate S behind it instead of idling.
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j <= i; ++j) tasks.push_back(make_int4(DAG_LAUUM | (fit << 4), i, j, 0));
 }
 
 // Allocate a handle for an N x d problem with np populations: device buffers, streams, events.
@@ -262,64 +318,34 @@ static int alloc_handle(int device, int64_t N, int32_t d, int32_t np, bool has_r
   ALLOC(h->ddiagS, Np * 8);
   ALLOC(h->dpart, (size_t)h->nb * Np * 8);
   ALLOC(h->dlogdet, (size_t)h->nb * 8);
-  ALLOC(h->dtracepart, (size_t)h->ntiles * (MAXD + 3) * 8);
+  {
+    const int sms = (device < 64 && g_num_sms[device] > 0) ? g_num_sms[device] : 148;
+    h->tile_split = h->ntiles * 4 <= 2 * sms ? 4 : (h->ntiles * 2 <= 2 * sms ? 2 : 1);
+  }
+  ALLOC(h->dtracepart, (size_t)h->ntiles * h->tile_split * (MAXD + 3) * 8);
   ALLOC(h->dscal, NSCAL * 8);
   ALLOC(h->dinfo, 4);
   ALLOC(h->dsync, (size_t)(1 + 4 * h->nb * h->nb) * 4);
   {
-    // Task list of the persistent factorisation kernel (dag_factor.cuh).  A tile whose k loop is longer
-    // than `ch` tiles is computed in PIECES of ch k tiles (running partial result kept in place / in the
-    // scratch matrix); only the last piece carries the epilogue.  Placement by "column step" s:
-    //   * final piece of POTRF(i, s), i >= s + 2, and of TRTRI row s - lag: at step s;
-    //   * the two chain tasks of block column c - DIAG(c) and POTRF(c+1, c) - `lead` steps early: their
-    //     CTAs are then resident, with everything but the last k tiles accumulated, when the chain arrives;
-    //   * a non-final piece as soon as its operands are final, staggered over the following ch steps so
-    //     that the bulk work never queues up in front of the chain.
-    // Within a step: chain tasks, Cholesky tiles, inverse tiles, then pieces.  Every dependency of a task
-    // precedes it in the list, except that chain tasks may precede theirs (bounded: 2 (lead + 1) tasks).
-    struct Ev {
-      int step, cls, seq;
-      int4 t;
-    };
-    std::vector<Ev> evs;
-    const int nb = h->nb, lag = g_dag_lag, lead = g_dag_lead, ch = g_dag_chunk;
-    evs.reserve((size_t)nb * nb * 2);
-    int seq = 0;
-    auto word = [](int kt0, int kt1, int piece, int last) { return kt0 | (kt1 << 10) | (piece << 20) | (last << 30); };
-    // tile (type, i, j) with nkt k tiles; koff: TRTRI operand rows start at block row j
-    auto add_tile = [&](int type, int i, int j, int nkt, int final_step, int cls, int ready_off, int partial_cap) {
-      const int np = std::max(1, (nkt + ch - 1) / ch);
-      for (int q = 0; q + 1 < np; ++q) {
-        const int e = ready_off + (q + 1) * ch;  // first step at which the operands of piece q are final
-        const int st = std::max(e, std::min(e + (i + j) % ch, partial_cap));
-        evs.push_back({st, 3, seq++, make_int4(type, i, j, word(q * ch, (q + 1) * ch, q, 0))});
-      }
-      evs.push_back({final_step, cls, seq++, make_int4(type, i, j, word((np - 1) * ch, nkt, np - 1, 1))});
-    };
-    for (int c = 0; c < nb; ++c) {
-      const int fs = std::max(0, c - lead);
-      add_tile(DAG_DIAG, c, c, c, fs, 0, 0, std::max(0, fs - 1));
-      if (c + 1 < nb) add_tile(DAG_POTRF, c + 1, c, c, fs, 0, 0, std::max(0, fs - 1));
-      for (int i = c + 2; i < nb; ++i) add_tile(DAG_POTRF, i, c, c, c, 1, 0, c - 1);
-    }
-    for (int r = 1; r < nb; ++r)
-      for (int j = 0; j < r; ++j) add_tile(DAG_TRTRI, r, j, r - j, r + lag, 2, j + lag, r + lag - 1);
-    std::stable_sort(evs.begin(), evs.end(), [](const Ev& x, const Ev& y) {
-      if (x.step != y.step) return x.step < y.step;
-      if (x.cls != y.cls) return x.cls < y.cls;
-      return x.seq < y.seq;
-    });
-    std::vector<int4> tasks(evs.size());
-    for (size_t q = 0; q < evs.size(); ++q) tasks[q] = evs[q].t;
-    h->ntasks_factor = (int)tasks.size();
-    // Sigma^-1 = X^T X after the inverse, longest k range first.  S_ij sums over block rows k >= i of X in
-    // ascending order - the order in which the inverse completes them - so the CTAs that run out of inverse
-    // tiles at the end of the factorisation accumulate S behind it instead of idling.
-    for (int i = 0; i < nb; ++i)
-      for (int j = 0; j <= i; ++j) tasks.push_back(make_int4(DAG_LAUUM, i, j, 0));
+    std::vector<int4> tasks;
+    build_dag_tasks(h->nb, g_dag_lag, g_dag_lead, g_dag_chunk, 0, tasks, &h->ntasks_factor);
+    const int nb = h->nb;
     h->ntasks = (int)tasks.size();
     ALLOC(h->dtasks, tasks.size() * sizeof(int4));
-    cudaError_t e_ = cudaMemcpyAsync(h->dtasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream);
+    ALLOC(h->dfit, sizeof(DagFit));
+    DagFit hf;
+    hf.A = h->bufA;
+    hf.X = h->bufB;
+    hf.W = h->bufC;
+    hf.ld = Np;
+    hf.nb = nb;
+    hf.n_valid = (int)N;
+    hf.flags = h->dsync + 1;
+    hf.logdet_part = h->dlogdet;
+    hf.info = h->dinfo;
+    cudaError_t e_ = cudaMemcpyAsync(h->dfit, &hf, sizeof(hf), cudaMemcpyHostToDevice, h->stream);
+    if (e_ == cudaSuccess)
+      e_ = cudaMemcpyAsync(h->dtasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream);
     if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(h->stream);  // `tasks` is pageable and goes out of scope
     if (e_ != cudaSuccess) {
       free_handle(h);

@@ -128,7 +128,8 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     h->launches++;
   } else {
     int smem = 2 * d * TB * 8 + 2 * TB * 4;
-    assemble_sigma_kernel<<<h->ntiles, 256, smem, st>>>(h->bufA, ld, N, h->dX, h->dpop, h->drhotab, h->dparams);
+    assemble_sigma_kernel<<<h->ntiles * h->tile_split, 256, smem, st>>>(h->bufA, ld, N, h->dX, h->dpop, h->drhotab,
+                                                                          h->dparams, h->tile_split);
     h->launches++;
   }
   CU(record_phase_event(h->ev[1], st));
@@ -137,17 +138,10 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     // --- Cholesky + triangular inverse: ONE persistent, dependency-driven launch (dag_factor.cuh)
     CU(cudaMemsetAsync(h->dsync, 0, (size_t)(1 + 4 * nb * nb) * 4, st));
     DagArgs da;
-    da.A = h->bufA;
-    da.X = h->bufB;
-    da.W = h->bufC;
-    da.ld = ld;
-    da.nb = nb;
-    da.n_valid = N;
+    da.fits = h->dfit;
     da.tasks = h->dtasks;
     da.ntasks = through_z_only ? h->ntasks_factor : h->ntasks;
-    da.sync = h->dsync;
-    da.logdet_part = h->dlogdet;
-    da.info = h->dinfo;
+    da.counter = h->dsync;
     dag_factor_kernel<<<std::min(h->num_sms, da.ntasks), DAG_THREADS, DAG_SMEM_BYTES, st>>>(da);
     h->launches++;
     CU(record_phase_event(h->ev[2], st));
@@ -289,30 +283,27 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   NvtxRange::next("gpedm:trace");
   // --- gradient trace terms + scalar reductions
   {
-    int DC = d <= 8 ? 8 : (d <= 16 ? 16 : 32);
-    int smem = (4 * d * TB + 2 * TB + 8 * (DC + 3)) * 8 + 2 * TB * 4;
-    if (DC <= 16) {
-      // The kernel is compiled for 3 CTAs/SM (latency-bound: more resident warps help), but a CTA then
-      // runs ~1.26x longer than at 2 CTAs/SM (measured), so when the tile count quantises into the same
-      // number of waves either way, cap residency at 2 by padding the dynamic shared memory request.
-      const int w3 = ceil_div(h->ntiles, 3 * h->num_sms), w2 = ceil_div(h->ntiles, 2 * h->num_sms);
-      if (1.26 * w3 > w2) smem = std::max(smem, 80 * 1024);
-    }
+    const int DC = d <= 8 ? 8 : (d <= 12 ? 12 : (d <= 16 ? 16 : 32));
+    const int smem = (2 * d * TB + 2 * TB + DC + 8 * (DC + 3)) * 8 + 2 * TB * 4;
+    const int cs = h->tile_split, grid = h->ntiles * cs;
+#define GPEDM_TRACE(DCV)                                                                                         \
+  grad_trace_kernel<DCV><<<grid, 256, smem, st>>>(h->bufC, ld, N, h->dX, h->dpop, h->drhotab, h->da, h->dparams, \
+                                                  h->dtracepart, cs)
     if (DC == 8)
-      grad_trace_kernel<8><<<h->ntiles, 256, smem, st>>>(h->bufC, ld, N, h->dX, h->dpop, h->drhotab, h->da,
-                                                         h->dparams, h->dtracepart);
+      GPEDM_TRACE(8);
+    else if (DC == 12)
+      GPEDM_TRACE(12);
     else if (DC == 16)
-      grad_trace_kernel<16><<<h->ntiles, 256, smem, st>>>(h->bufC, ld, N, h->dX, h->dpop, h->drhotab, h->da,
-                                                          h->dparams, h->dtracepart);
+      GPEDM_TRACE(16);
     else
-      grad_trace_kernel<32><<<h->ntiles, 256, smem, st>>>(h->bufC, ld, N, h->dX, h->dpop, h->drhotab, h->da,
-                                                          h->dparams, h->dtracepart);
+      GPEDM_TRACE(32);
+#undef GPEDM_TRACE
     h->launches++;
     if (full) {
       extract_diag_kernel<<<ceil_div(N, 256), 256, 0, st>>>(h->bufC, ld, N, h->ddiagS);
       h->launches++;
     }
-    final_reduce_kernel<<<1, 256, 0, st>>>(h->dlogdet, nb, h->dz, h->da, h->ddiagS, N, h->dtracepart, h->ntiles,
+    final_reduce_kernel<<<1, 256, 0, st>>>(h->dlogdet, nb, h->dz, h->da, h->ddiagS, N, h->dtracepart, h->ntiles * h->tile_split,
                                            d + 3, full ? 1 : 0, h->dscal);
     h->launches++;
   }

@@ -46,12 +46,15 @@ __device__ __forceinline__ double cov_entry(const double* xi, const double* xj, 
 }
 
 // Sigma = Cd + ve*I on the lower tiles (reference R/GPfunctions.R:633-641; the symmetrisation
-// at :641 is a no-op because each entry is computed once).  grid = nb*(nb+1)/2 tiles.
-__global__ void __launch_bounds__(256) assemble_sigma_kernel(double* __restrict__ A, size_t ld, int N,
+// at :641 is a no-op because each entry is computed once).  grid = nb*(nb+1)/2 tiles x csplit column
+// ranges (csplit > 1 only when there are fewer tiles than SMs).  A thread owns TWO consecutive rows
+// (16-byte loads of the staged predictors, 16-byte stores: one column of the tile is written as 64 x 16
+// contiguous bytes) and every fourth column of its range; the arithmetic per entry is exactly cov_entry's.
+__device__ __forceinline__ void assemble_sigma_body(double* __restrict__ A, size_t ld, int N,
                                                               const double* __restrict__ X,
                                                               const int* __restrict__ pop,
                                                               const double* __restrict__ rhotab,
-                                                              const EvalParams* __restrict__ P) {
+                                                              const EvalParams* __restrict__ P, int csplit, const int bid) {
   extern __shared__ double sm[];
   const int d = P->d;
   double* xi = sm;             // [d][128]
@@ -59,7 +62,8 @@ __global__ void __launch_bounds__(256) assemble_sigma_kernel(double* __restrict_
   int* pi_s = (int*)(xj + d * TB);
   int* pj_s = pi_s + TB;
   int ti, tj;
-  tri_decode(blockIdx.x, ti, tj);
+  tri_decode(bid / csplit, ti, tj);
+  const int ncols = TB / csplit, cbeg = (bid % csplit) * ncols;
   const int tid = threadIdx.x;
   for (int idx = tid; idx < d * TB; idx += 256) {
     int k = idx >> 7, r = idx & 127;
@@ -77,19 +81,41 @@ __global__ void __launch_bounds__(256) assemble_sigma_kernel(double* __restrict_
   const double sigma2 = P->sigma2, rho = P->rho, ve = P->ve;
   const int np = P->np;
   const double* rt = P->use_rhotab ? rhotab : nullptr;
-  const int r = tid & 127, half = tid >> 7;
-  const int gi = ti * TB + r;
-  for (int c = half * 64; c < half * 64 + 64; ++c) {
-    int gj = tj * TB + c;
-    double v;
-    if (gi < N && gj < N) {
-      v = cov_entry(xi + r, xj + c, TB, d, sigma2, rho, pi_s[r], pj_s[c], rt, np);
-      if (gi == gj) v = __dadd_rn(v, ve);
-    } else {
-      v = (gi == gj) ? 1.0 : 0.0;
+  const int r0 = 2 * (tid & 63), cg = tid >> 6;
+  const int gi0 = ti * TB + r0;
+  const int p0 = max(pi_s[r0], 0), p1 = max(pi_s[r0 + 1], 0);  // (padding rows: value overwritten below)
+  for (int c = cbeg + cg; c < cbeg + ncols; c += 4) {
+    const int gj = tj * TB + c;
+    double dist0 = 0.0, dist1 = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double2 xr = *reinterpret_cast<const double2*>(xi + k * TB + r0);
+      const double xc = xj[k * TB + c];
+      const double f0 = __dsub_rn(xr.x, xc), f1 = __dsub_rn(xr.y, xc);
+      dist0 = __dadd_rn(dist0, __dmul_rn(f0, f0));
+      dist1 = __dadd_rn(dist1, __dmul_rn(f1, f1));
     }
-    A[(size_t)gi + (size_t)gj * ld] = v;
+    const int pj = max(pj_s[c], 0);
+    double v0 = __dmul_rn(sigma2, exp(-dist0)), v1 = __dmul_rn(sigma2, exp(-dist1));
+    if (rt != nullptr) {
+      v0 = __dmul_rn(v0, rt[p0 + pj * np]);  // training codes are always < np
+      v1 = __dmul_rn(v1, rt[p1 + pj * np]);
+    } else {
+      if (p0 != pj) v0 = __dmul_rn(v0, rho);
+      if (p1 != pj) v1 = __dmul_rn(v1, rho);
+    }
+    if (gi0 == gj) v0 = __dadd_rn(v0, ve);
+    if (gi0 + 1 == gj) v1 = __dadd_rn(v1, ve);
+    if (gj >= N || gi0 >= N) v0 = (gi0 == gj) ? 1.0 : 0.0;          // identity in the padding
+    if (gj >= N || gi0 + 1 >= N) v1 = (gi0 + 1 == gj) ? 1.0 : 0.0;
+    *reinterpret_cast<double2*>(A + (size_t)gi0 + (size_t)gj * ld) = make_double2(v0, v1);
   }
+}
+__global__ void __launch_bounds__(256) assemble_sigma_kernel(double* __restrict__ A, size_t ld, int N,
+                                                              const double* __restrict__ X,
+                                                              const int* __restrict__ pop,
+                                                              const double* __restrict__ rhotab,
+                                                              const EvalParams* __restrict__ P, int csplit) {
+  assemble_sigma_body(A, ld, N, X, pop, rhotab, P, csplit, (int)blockIdx.x);
 }
 
 // General rectangular covariance (getcov with X2 != X): out[(row) + (col)*ldo] where
@@ -276,13 +302,13 @@ __global__ void __launch_bounds__(256) diag_potf2_inv_kernel(double* __restrict_
 // keep the result deterministic.
 
 // zpart[tj][row] = sum_{c in tile tj} X[row, c] * y[c]      for lower tiles (ti >= tj)
-__global__ void __launch_bounds__(256) trmv_n_part_kernel(const double* __restrict__ X, size_t ld,
+__device__ __forceinline__ void trmv_n_part_body(const double* __restrict__ X, size_t ld,
                                                            const double* __restrict__ y,
-                                                           double* __restrict__ part, size_t np_ld) {
+                                                           double* __restrict__ part, size_t np_ld, const int bid) {
   __shared__ double ys[TB];
   __shared__ double red[TB];
   int ti, tj;
-  tri_decode(blockIdx.x, ti, tj);
+  tri_decode(bid, ti, tj);
   const int tid = threadIdx.x, r = tid & 127, half = tid >> 7;
   if (tid < TB) ys[tid] = y[(size_t)tj * TB + tid];
   __syncthreads();
@@ -297,14 +323,19 @@ __global__ void __launch_bounds__(256) trmv_n_part_kernel(const double* __restri
   __syncthreads();
   if (half == 0) part[(size_t)tj * np_ld + (size_t)ti * TB + r] = s + red[r];
 }
+__global__ void __launch_bounds__(256) trmv_n_part_kernel(const double* __restrict__ X, size_t ld,
+                                                           const double* __restrict__ y,
+                                                           double* __restrict__ part, size_t np_ld) {
+  trmv_n_part_body(X, ld, y, part, np_ld, (int)blockIdx.x);
+}
 
 // apart[ti][col] = sum_{r in tile ti} X[r, col] * z[r]       for lower tiles (ti >= tj)
-__global__ void __launch_bounds__(256) trmv_t_part_kernel(const double* __restrict__ X, size_t ld,
+__device__ __forceinline__ void trmv_t_part_body(const double* __restrict__ X, size_t ld,
                                                            const double* __restrict__ z,
-                                                           double* __restrict__ part, size_t np_ld) {
+                                                           double* __restrict__ part, size_t np_ld, const int bid) {
   __shared__ double zs[TB];
   int ti, tj;
-  tri_decode(blockIdx.x, ti, tj);
+  tri_decode(bid, ti, tj);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < TB) zs[tid] = z[(size_t)ti * TB + tid];
   __syncthreads();
@@ -319,12 +350,17 @@ __global__ void __launch_bounds__(256) trmv_t_part_kernel(const double* __restri
     if (lane == 0) part[(size_t)ti * np_ld + (size_t)tj * TB + c] = s;
   }
 }
+__global__ void __launch_bounds__(256) trmv_t_part_kernel(const double* __restrict__ X, size_t ld,
+                                                           const double* __restrict__ z,
+                                                           double* __restrict__ part, size_t np_ld) {
+  trmv_t_part_body(X, ld, z, part, np_ld, (int)blockIdx.x);
+}
 
 // out[i] = sum over the tile partials that exist for i, in fixed order.
 // mode 0: partial index tj runs 0..tile(i)   (z);  mode 1: ti runs tile(i)..nb-1   (a)
-__global__ void reduce_parts_kernel(const double* __restrict__ part, size_t np_ld, int nb, int mode,
-                                    double* __restrict__ out, int n_alloc) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void reduce_parts_body(const double* __restrict__ part, size_t np_ld, int nb, int mode,
+                                    double* __restrict__ out, int n_alloc, const int bid) {
+  int i = bid * blockDim.x + threadIdx.x;
   if (i >= n_alloc) return;
   int t = i / TB;
   double s = 0.0;
@@ -334,10 +370,17 @@ __global__ void reduce_parts_kernel(const double* __restrict__ part, size_t np_l
     for (int q = t; q < nb; ++q) s += part[(size_t)q * np_ld + i];
   out[i] = s;
 }
+__global__ void reduce_parts_kernel(const double* __restrict__ part, size_t np_ld, int nb, int mode,
+                                    double* __restrict__ out, int n_alloc) {
+  reduce_parts_body(part, np_ld, nb, mode, out, n_alloc, (int)blockIdx.x);
+}
 
-__global__ void extract_diag_kernel(const double* __restrict__ S, size_t ld, int n, double* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void extract_diag_body(const double* __restrict__ S, size_t ld, int n, double* __restrict__ out, const int bid) {
+  int i = bid * blockDim.x + threadIdx.x;
   if (i < n) out[i] = S[(size_t)i + (size_t)i * ld];
+}
+__global__ void extract_diag_kernel(const double* __restrict__ S, size_t ld, int n, double* __restrict__ out) {
+  extract_diag_body(S, ld, n, out, (int)blockIdx.x);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -347,39 +390,39 @@ __global__ void extract_diag_kernel(const double* __restrict__ S, size_t ld, int
 // Reads Sigma^-1 (lower tiles) once; Cd and the per-coordinate squared distances D_k are
 // recomputed from the staged predictor tiles instead of being stored (the reference keeps d
 // dense N x N matrices, :539-542).  Off-diagonal entries count twice (symmetry).
-// tracepart[tile][q], q = 0..d-1 (phi), d (ve), d+1 (sigma2), d+2 (rho).
+// tracepart[cta][q], q = 0..d-1 (phi), d (ve), d+1 (sigma2), d+2 (rho).
+// A thread owns two consecutive rows (16-byte loads of Sigma^-1 and of the staged predictors) and every
+// fourth column of the CTA's column range.  Here Cd only weights a sum that is compared at 1e-8, so its
+// squared distance is accumulated as sum_k phi_k (x_ik - x_jk)^2 with FMAs, sharing (x_ik - x_jk)^2 with
+// the D_k terms (the assembly kernel keeps getcov's exact operation order; this one does not need to).
+// The 1/sigma2 and 1/rho factors are applied once per CTA, not per entry.
 template <int DC>
-__global__ void __launch_bounds__(256, DC <= 16 ? 3 : 1) grad_trace_kernel(const double* __restrict__ S, size_t ld, int N,
+__device__ __forceinline__ void grad_trace_body(const double* __restrict__ S, size_t ld, int N,
                                                           const double* __restrict__ X,
                                                           const int* __restrict__ pop,
                                                           const double* __restrict__ rhotab,
                                                           const double* __restrict__ avec,
                                                           const EvalParams* __restrict__ P,
-                                                          double* __restrict__ tracepart) {
+                                                          double* __restrict__ tracepart, int csplit, const int bid) {
   extern __shared__ double sm[];
   const int d = P->d;
-  double* xi = sm;                  // scaled  [d][128]
-  double* xj = xi + d * TB;
-  double* ri = xj + d * TB;         // raw     [d][128]
-  double* rj = ri + d * TB;
+  double* ri = sm;                  // raw predictors of the tile's rows  [d][128]
+  double* rj = ri + d * TB;         // ... of its columns
   double* ai = rj + d * TB;         // [128]
   double* aj = ai + TB;
-  double* red = aj + TB;            // [8][DC+3]
+  double* phis = aj + TB;           // [DC]
+  double* red = phis + DC;          // [8][DC+3]
   int* pi_s = (int*)(red + 8 * (DC + 3));
   int* pj_s = pi_s + TB;
   int ti, tj;
-  tri_decode(blockIdx.x, ti, tj);
+  tri_decode(bid / csplit, ti, tj);
+  const int ncols = TB / csplit, cbeg = (bid % csplit) * ncols;
   const int tid = threadIdx.x;
   for (int idx = tid; idx < d * TB; idx += 256) {
     int k = idx >> 7, r = idx & 127;
     int gi = ti * TB + r, gj = tj * TB + r;
-    double s = P->sqphi[k];
-    double vi = gi < N ? X[(size_t)gi + (size_t)k * N] : 0.0;
-    double vj = gj < N ? X[(size_t)gj + (size_t)k * N] : 0.0;
-    ri[idx] = vi;
-    rj[idx] = vj;
-    xi[idx] = __dmul_rn(vi, s);
-    xj[idx] = __dmul_rn(vj, s);
+    ri[idx] = gi < N ? X[(size_t)gi + (size_t)k * N] : 0.0;
+    rj[idx] = gj < N ? X[(size_t)gj + (size_t)k * N] : 0.0;
   }
   if (tid < TB) {
     int gi = ti * TB + tid, gj = tj * TB + tid;
@@ -388,38 +431,63 @@ __global__ void __launch_bounds__(256, DC <= 16 ? 3 : 1) grad_trace_kernel(const
     ai[tid] = gi < N ? avec[gi] : 0.0;
     aj[tid] = gj < N ? avec[gj] : 0.0;
   }
+  if (tid < DC) phis[tid] = tid < d ? P->phi[tid] : 0.0;
   __syncthreads();
   const double sigma2 = P->sigma2, rho = P->rho;
   const int np = P->np;
   const double* rt = P->use_rhotab ? rhotab : nullptr;
-  const int r = tid & 127, half = tid >> 7;
-  const int gi = ti * TB + r;
+  const int r0 = 2 * (tid & 63), cg = tid >> 6;
+  const int gi0 = ti * TB + r0;
   double acc[DC + 3];
 #pragma unroll
   for (int q = 0; q < DC + 3; ++q) acc[q] = 0.0;
-  if (gi < N) {
-    const double a_i = ai[r];
-    const int p_i = pi_s[r];
-    const double* Sp = S + (size_t)gi + (size_t)tj * TB * ld;
-    for (int c = half * 64; c < half * 64 + 64; ++c) {
-      int gj = tj * TB + c;
-      if (gj >= N || gj > gi) continue;
-      double sij = Sp[(size_t)c * ld];
-      double q = 0.5 * (a_i * aj[c] - sij);
-      double cd = cov_entry(xi + r, xj + c, TB, d, sigma2, rho, p_i, pj_s[c], rt, np);
-      double w = (gi == gj) ? 1.0 : 2.0;
-      double qc = w * q * cd;
+  const double a0 = ai[r0], a1 = ai[r0 + 1];
+  const int p0 = pi_s[r0], p1 = pi_s[r0 + 1];
+  const double* Sp = S + (size_t)gi0 + (size_t)tj * TB * ld;
+  // the Sigma^-1 pair of the NEXT column is requested before the current one is processed (the loop is
+  // otherwise bound by the latency of this load: ncu long-scoreboard stalls)
+  double2 s2n = *reinterpret_cast<const double2*>(Sp + (size_t)(cbeg + cg) * ld);
+  for (int c = cbeg + cg; c < cbeg + ncols; c += 4) {
+    const int gj = tj * TB + c;
+    const double2 s2 = s2n;
+    if (c + 4 < cbeg + ncols) s2n = *reinterpret_cast<const double2*>(Sp + (size_t)(c + 4) * ld);
+    if (gj >= N || gj > gi0 + 1 || gi0 >= N) continue;  // nothing of this column pair lies in the lower triangle
+    double d20[DC], d21[DC];
+    double dist0 = 0.0, dist1 = 0.0;
 #pragma unroll
-      for (int k = 0; k < DC; ++k) {
-        if (k < d) {
-          double df = ri[k * TB + r] - rj[k * TB + c];
-          acc[k] -= qc * (df * df);
-        }
+    for (int k = 0; k < DC; ++k) {
+      if (k < d) {
+        const double2 xr = *reinterpret_cast<const double2*>(ri + k * TB + r0);
+        const double xc = rj[k * TB + c];
+        const double f0 = xr.x - xc, f1 = xr.y - xc;
+        d20[k] = f0 * f0;
+        d21[k] = f1 * f1;
+        dist0 = fma(phis[k], d20[k], dist0);
+        dist1 = fma(phis[k], d21[k], dist1);
+      } else {
+        d20[k] = d21[k] = 0.0;
       }
-      if (gi == gj) acc[DC] += q;
-      acc[DC + 1] += qc / sigma2;
-      if (p_i != pj_s[c]) acc[DC + 2] += qc / rho;
     }
+    const int pj = pj_s[c];
+    const double ajc = aj[c];
+    double m0 = 1.0, m1 = 1.0;
+    if (rt != nullptr) {
+      m0 = rt[p0 + pj * np];
+      m1 = rt[(p1 < 0 ? p0 : p1) + pj * np];
+    } else {
+      if (p0 != pj) m0 = rho;
+      if (p1 != pj) m1 = rho;
+    }
+    const bool ok0 = gj <= gi0, ok1 = gi0 + 1 < N;  // (gj <= gi0 + 1 and gi0 < N hold here)
+    const double q0 = 0.5 * (a0 * ajc - s2.x), q1 = 0.5 * (a1 * ajc - s2.y);
+    const double qc0 = ok0 ? ((gi0 == gj) ? 1.0 : 2.0) * q0 * (sigma2 * exp(-dist0) * m0) : 0.0;
+    const double qc1 = ok1 ? ((gi0 + 1 == gj) ? 1.0 : 2.0) * q1 * (sigma2 * exp(-dist1) * m1) : 0.0;
+#pragma unroll
+    for (int k = 0; k < DC; ++k) acc[k] = fma(-qc0, d20[k], fma(-qc1, d21[k], acc[k]));
+    if (gi0 == gj) acc[DC] += q0;
+    if (gi0 + 1 == gj && ok1) acc[DC] += q1;
+    acc[DC + 1] += qc0 + qc1;
+    acc[DC + 2] += (p0 != pj ? qc0 : 0.0) + (p1 != pj ? qc1 : 0.0);
   }
   // block reduction in fixed order: warp shuffle tree, then 8 warp partials summed by warp 0
   const int warp = tid >> 5, lane = tid & 31;
@@ -434,9 +502,21 @@ __global__ void __launch_bounds__(256, DC <= 16 ? 3 : 1) grad_trace_kernel(const
   if (tid < DC + 3) {
     double v = 0.0;
     for (int w = 0; w < 8; ++w) v += red[w * (DC + 3) + tid];
+    if (tid == DC + 1) v /= sigma2;
+    if (tid == DC + 2) v /= rho;
     int qo = tid < DC ? tid : d + (tid - DC);
-    if (tid >= DC || tid < d) tracepart[(size_t)blockIdx.x * (MAXD + 3) + qo] = v;
+    if (tid >= DC || tid < d) tracepart[(size_t)bid * (MAXD + 3) + qo] = v;
   }
+}
+template <int DC>
+__global__ void __launch_bounds__(256, DC <= 16 ? 2 : 1) grad_trace_kernel(const double* __restrict__ S, size_t ld, int N,
+                                                          const double* __restrict__ X,
+                                                          const int* __restrict__ pop,
+                                                          const double* __restrict__ rhotab,
+                                                          const double* __restrict__ avec,
+                                                          const EvalParams* __restrict__ P,
+                                                          double* __restrict__ tracepart, int csplit) {
+  grad_trace_body<DC>(S, ld, N, X, pop, rhotab, avec, P, tracepart, csplit, (int)blockIdx.x);
 }
 
 // Final scalar reductions of one evaluation (single CTA, fixed order => deterministic):
@@ -446,12 +526,12 @@ __global__ void __launch_bounds__(256, DC <= 16 ? 3 : 1) grad_trace_kernel(const
 //  scal[3]        = sum a_i^2 / S_ii     /
 //  scal[4]        = tr(S)                 -> df = N - ve tr(S)  (:743)
 //  scal[8 + q]    = trace terms q = 0..d+2
-__global__ void __launch_bounds__(256) final_reduce_kernel(const double* __restrict__ logdet_part, int nb,
+__device__ __forceinline__ void final_reduce_body(const double* __restrict__ logdet_part, int nb,
                                                             const double* __restrict__ z,
                                                             const double* __restrict__ avec,
                                                             const double* __restrict__ diagS, int N,
                                                             const double* __restrict__ tracepart, int ntiles,
-                                                            int nq, int have_S, double* __restrict__ scal) {
+                                                            int nq, int have_S, double* __restrict__ scal, const int bid) {
   __shared__ double red[256];
   const int tid = threadIdx.x;
   auto block_sum = [&](double v) -> double {
@@ -497,6 +577,14 @@ __global__ void __launch_bounds__(256) final_reduce_kernel(const double* __restr
     double s = block_sum(v);
     if (tid == 0) scal[8 + q] = s;
   }
+}
+__global__ void __launch_bounds__(256) final_reduce_kernel(const double* __restrict__ logdet_part, int nb,
+                                                            const double* __restrict__ z,
+                                                            const double* __restrict__ avec,
+                                                            const double* __restrict__ diagS, int N,
+                                                            const double* __restrict__ tracepart, int ntiles,
+                                                            int nq, int have_S, double* __restrict__ scal) {
+  final_reduce_body(logdet_part, nb, z, avec, diagS, N, tracepart, ntiles, nq, have_S, scal, (int)blockIdx.x);
 }
 
 // -----------------------------------------------------------------------------------------

@@ -1,0 +1,126 @@
+"""Lockstep batch of mid-size fits (129 <= N <= 1024; SURVEY 8f rank 3: per-population models, pairwise fits,
+multistart, b-profiles) against the per-handle tiled path and the CPU oracle."""
+import numpy as np
+import pytest
+
+import gpedm_b200 as G
+from gpedm_b200 import _lib, batch, synth
+from oracle import gpedm_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL_MODE, TOL_NLL = 1e-6, 1e-10
+
+
+def rel(a, b):
+    return abs(a - b) / abs(b)
+
+
+def _problems():
+    """Sizes straddling the 128-tile edges (129, 256, 257, 500, 640), several d, two populations with a
+    free rho, fixed parameters, a pairwise rho matrix."""
+    probs = []
+    for n, E, seed in [(129 + 2, 2, 31), (256 + 3, 3, 32), (257 + 1, 1, 33), (500 + 4, 4, 34), (640 + 2, 2, 35)]:
+        Y, X = synth.embed(synth.ricker(n, seed), E, 1)
+        probs.append(dict(Y=Y, X=X, initparst=batch.default_initparst(E, True)))
+    Y, X, pop = synth.hierarchical_thetalog(npop=2, n=150, E=2, seed0=50)
+    probs.append(dict(Y=Y, X=X, pop=pop, initparst=batch.default_initparst(2, False)))
+    Y, X, pop = synth.hierarchical_thetalog(npop=3, n=70, E=2, seed0=60)
+    probs.append(dict(Y=Y, X=X, pop=pop, initparst=batch.default_initparst(2, False), rhofixed=0.3,
+                      fixedpars=[np.nan, np.nan, 0.01, np.nan]))
+    probs.append(dict(Y=Y, X=X, pop=pop, initparst=batch.default_initparst(2, False),
+                      rhomatrix=np.array([[1, .3, .5], [.3, 1, .2], [.5, .2, 1.]])))
+    return probs
+
+
+def test_mid_batch_matches_tiled_path_and_oracle(gpu_lib):
+    probs = _problems()
+    sizes = [len(p["Y"]) for p in probs]
+    assert sizes[:5] == [129, 256, 257, 500, 640] and all(128 < s <= 1024 for s in sizes)
+    res = G.fit_batch(probs, ngpus=1, want_loo=True)
+    for pr, r in zip(probs, res):
+        m = G.GPModel(pr["Y"], pr["X"], pr.get("pop"), pr.get("rhomatrix"), None if pr.get("rhomatrix") is None else [0, 1, 2])
+        one = m.fit_rprop(pr["initparst"], 1.0, pr.get("fixedpars"), pr.get("rhofixed"))
+        assert r["status"] == 0 and one["iter"] == r["iter"] and one["nevals"] == r["nevals"]
+        # same kernels, same per-tile arithmetic, same reduction order: the two paths agree to the last bit
+        assert r["nllpost"] == one["nllpost"]
+        np.testing.assert_array_equal(r["pars"], one["pars"])
+        np.testing.assert_array_equal(r["grad"], one["grad"])
+        assert r["lnL_LOO"] == one["lnL_LOO"] and r["df"] == one["df"]
+        np.testing.assert_array_equal(r["loo_mean"], m.vector(_lib.VEC_LOO_MEAN))
+        np.testing.assert_array_equal(r["loo_var"], m.vector(_lib.VEC_LOO_VAR))
+        np.testing.assert_array_equal(r["insamp_mean"], m.vector(_lib.VEC_MEAN))
+        m.close()
+    # against the oracle's fmingrad_Rprop (reference R/GPfunctions.R:522-584) for three of them
+    for k in (0, 2, 5):
+        pr = probs[k]
+        d = pr["X"].shape[1]
+        pop = pr.get("pop", np.ones(len(pr["Y"]), dtype=int))
+        o = O.fmingrad_Rprop(pr["initparst"], pr["Y"], pr["X"], pop, 1, np.full(d + 2, np.nan), None, None)
+        assert res[k]["iter"] == o["iter"]
+        assert np.max(np.abs(res[k]["pars"] - o["pars"]) / np.maximum(1, np.abs(o["pars"]))) <= TOL_MODE
+        assert rel(res[k]["nllpost"], o["nllpost"]) <= TOL_NLL
+
+
+def test_mixed_batch_small_mid_and_tiled(gpu_lib):
+    """One batch with one-tile fits (one-CTA kernel), mid-size fits (lockstep tiled batch) and a fit above the
+    mid-size limit (worker-thread path): each returns what an individual fit returns."""
+    probs = []
+    g, _ = batch.grid_problems(synth.ricker(110, 21), [1, 2, 3], [1])
+    probs += g
+    for n, E, seed in [(300, 3, 22), (520, 4, 23), (700, 2, 24), (1300, 3, 25)]:
+        Yb, Xb = synth.embed(synth.ricker(n, seed), E, 1)
+        probs.append(dict(Y=Yb, X=Xb, initparst=batch.default_initparst(E, True)))
+    res = G.fit_batch(probs, ngpus=1, want_loo=True)
+    for pr, r in zip(probs, res):
+        m = G.GPModel(pr["Y"], pr["X"], pr.get("pop"))
+        one = m.fit_rprop(pr.get("initparst", batch.default_initparst(np.atleast_2d(pr["X"].T).T.shape[1])), 1.0, None, None)
+        assert r["status"] == 0 and one["iter"] == r["iter"]
+        assert np.max(np.abs(one["pars"] - r["pars"]) / np.maximum(1, np.abs(one["pars"]))) <= 1e-9
+        assert rel(r["nllpost"], one["nllpost"]) <= 1e-11
+        np.testing.assert_allclose(r["loo_mean"], m.vector(_lib.VEC_LOO_MEAN), atol=1e-9)
+        m.close()
+
+
+def test_mid_batch_reports_non_positive_definite_fit(gpu_lib):
+    """One poisoned fit (NaN predictor) must be reported with its pivot and must not disturb the others."""
+    probs = _problems()[:3]
+    bad = dict(probs[1])
+    Xb = bad["X"].copy()
+    Xb[40, 0] = np.nan
+    bad["X"] = Xb
+    probs.insert(1, bad)
+    with pytest.raises(G.GPEDMError) as e:
+        G.fit_batch(probs, ngpus=1)
+    assert e.value.status >= 1 and "not positive definite" in str(e.value)
+
+
+def test_multistart_and_b_profile_clients(gpu_lib):
+    """Batch clients of SURVEY 8f rank 3: multistart over initpars (vignettes/hierarchical.Rmd:47) and the
+    b-profile of the fisheries model (R/GPfisheries.R:114-134, objective GPnlike_fish :232-294)."""
+    Y, X, pop = synth.hierarchical_thetalog(npop=2, n=100, E=2, seed0=80)
+    starts = [np.array([0.1, 0.1, 0.001, 0.999, 0.5]), np.array([1.0, 0.01, 0.1, 2.0, 0.2]), np.array([0.02, 1.5, 0.3, 1.0, 0.8])]
+    res, best = G.multistart(Y, X, pop, starts=starts)
+    assert [r["ln_post"] for r in res] == sorted([r["ln_post"] for r in res], reverse=True)
+    for r in res:
+        o = O.fmingrad_Rprop(batch.initpars_to_parst(r["initpars"], 2, False), Y, X, pop, 1, np.full(4, np.nan), None, None)
+        assert r["iter"] == o["iter"]
+        assert np.max(np.abs(r["pars"] - o["pars"]) / np.maximum(1, np.abs(o["pars"]))) <= TOL_MODE
+        assert rel(r["nllpost"], o["nllpost"]) <= TOL_NLL
+    # harvested Ricker: escapement = m - b h with a true b of 0.4; the profile's maximum is near it
+    rng = np.random.default_rng(3)
+    T, btrue = 200, 0.4
+    bio, cpue, harv = np.empty(T), np.empty(T), rng.uniform(0.1, 0.6, T)
+    bio[0] = 0.8
+    for t in range(T - 1):
+        esc = bio[t] * (1 - btrue * harv[t])
+        bio[t + 1] = esc * np.exp(1.5 * (1 - esc)) * np.exp(0.03 * rng.standard_normal())
+    m_ = np.concatenate([[np.nan], bio[:-1]])
+    h_ = np.concatenate([[np.nan], bio[:-1] * harv[:-1]])
+    bs = np.linspace(0.0, 0.9, 10)
+    prof, ib = G.b_profile(bio, m_, h_, bs)
+    assert abs(prof[ib]["b"] - btrue) <= 0.11
+    for k in (0, ib, len(bs) - 1):
+        x2 = (m_ - bs[k] * h_)[:, None]
+        o = O.fitGP(y=bio, x=x2, scaling="global")
+        assert prof[k]["iter"] == o["iter"]
+        assert prof[k]["ln_post"] == pytest.approx(o["insampfitstats"]["ln_post"], rel=1e-9)
