@@ -45,7 +45,9 @@ static_assert(DAG_P >= TB * DG_LD, "resident tile must fit the operand ring");
 static_assert(DAG_E >= 64 * DG_WLD + 2 * TB + 64, "diag scratch must fit the epilogue ring");
 constexpr int DAG_SMEM_BYTES = (DAG_P + DAG_E) * (int)sizeof(double);
 
+static_assert(DagCfg::MT == 8 && DagCfg::NT == 4, "the triangular variants below assume 64 x 32 warp tiles");
 enum DagTaskType { DAG_DIAG = 0, DAG_POTRF = 1, DAG_TRTRI = 2, DAG_LAUUM = 3 };
+constexpr int DAG_NFLAG = 5;  // flag arrays per fit (see DagFit::flags)
 
 // One factorisation problem.  A launch may carry the task lists of MANY independent fits (the lockstep
 // batch of mid-size fits, host_batch.cuh): their tasks are interleaved in one list, so a CTA that would
@@ -57,7 +59,7 @@ struct DagFit {
                   // partial sums of TRTRI tiles that are computed in pieces
   size_t ld;
   int nb, n_valid;
-  int* flags;     // four nb*nb int arrays: L final, X final, pieces done of L tile, pieces done of X tile (zeroed per evaluation)
+  int* flags;     // DAG_NFLAG nb*nb int arrays: L final, X final, pieces done of L tile / X tile / S tile (zeroed per evaluation)
   double* logdet_part;
   int* info;
 };
@@ -83,6 +85,21 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 #else
 #define DAG_TL(...)
 #endif
+#ifdef GPEDM_TIMELINE
+// chain marks: extra timeline records {time, time, smid, 150 | mark << 8 | column << 20} logged by thread 0 of the
+// two chain tasks of a block column (DIAG(c), POTRF(c+1, c)); tools/dag_timeline.py prints the per-step breakdown
+__device__ __forceinline__ void tl_mark(unsigned long long t, int mark, int col) {
+  if (threadIdx.x == 0) {
+    const unsigned int i = atomicAdd(&g_tl_count, 1u);
+    if (i < TL_MAX) {
+      g_tl_rec[4 * i] = t;
+      g_tl_rec[4 * i + 1] = t;
+      g_tl_rec[4 * i + 2] = tl_smid();
+      g_tl_rec[4 * i + 3] = 150ull | ((unsigned long long)mark << 8) | ((unsigned long long)col << 20);
+    }
+  }
+}
+#endif
 __device__ __forceinline__ void warp_wait_flag(const int* f, int lane DAG_TL(, unsigned long long& waited)) {
   if (lane == 0) {
     if (ld_acquire(f) == 0) {
@@ -107,19 +124,25 @@ struct DagRing {
 // (inverse).  Operand tile kt is final once fa[kt] / fb[kt * fsb] are set.  Most of them already are when
 // the task starts: every warp scans the flags once (32 per load round, acquire) and only the k tiles past
 // the first unset flag are polled as the loop reaches them - the ones right behind the chain.
-template <bool A_KMAJOR, bool B_KMAJOR>
+// TRI (diagonal tiles of the Cholesky): the warp tile sits at (m0, n0) of a symmetric tile of which only the lower
+// part is used, so the 8 x 8 blocks strictly above the diagonal are skipped.
+template <bool A_KMAJOR, bool B_KMAJOR, bool TRI = false>
 __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][2], DagRing& ring, double* sA, double* sB,
                                           const double* __restrict__ Ap, const double* __restrict__ Bp, size_t ld,
                                           int nkt, const int* fa, int fsa, const int* fb, int fsb, bool active, unsigned sgn,
-                                          int tid DAG_TL(, unsigned long long& tl_wait)) {
+                                          int tid, int m0, int n0 DAG_TL(, unsigned long long& tl_wait, int tl_col = -1)) {
   using Cfg = DagCfg;
   constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, PREF = NS - 2;
   constexpr int SLAB_A = Cfg::SLAB_A, SLAB_B = Cfg::SLAB_B;
   constexpr int LD_A = Cfg::LD_MN_A, LD_B = Cfg::LD_MN_B, LD_K = Cfg::LD_K;
   constexpr int SPT = TB / BK;  // slabs per k tile
-  const int warp = tid >> 5, lane = tid & 31;
+  const int lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int m0 = (warp % Cfg::WM) * (MT * 8), n0 = (warp / Cfg::WM) * (NT * 8);
+  // TRI: a DMMA that is predicated off still occupies the sub-partition's DMMA pipe for its 16 cycles (measured),
+  // so the skipping is done with warp-uniform BRANCHES between three fully unrolled variants.  The warp tiles of a
+  // diagonal task sit at (m0 - n0) / 8 = dl 8 x 8 blocks below the diagonal: dl >= 3 all 32 blocks are needed,
+  // dl == 0 the blocks j <= i (26), dl == -4 the blocks j <= i - 4 (10).
+  const int tri_cls = !TRI ? 0 : ((m0 - n0) >= 24 ? 0 : ((m0 - n0) == 0 ? 1 : 2));
   int nready = 0;
   for (int base = 0; base < nkt; base += 32) {
     const int kt = base + lane;
@@ -139,23 +162,39 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
   auto issue = [&](int j) {  // copy slab j of this task into ring stage gi % NS
     const int s = ring.gi % NS, r = ring.gi / NS;
     if (r > 0) mbar_wait(&ring.empty[s], (unsigned)((r - 1) & 1));
-    if ((j & (SPT - 1)) == 0 && j / SPT >= nready) {  // first slab of a k tile not yet known to be final
-      const int kt = j / SPT;
-      warp_wait_flag(fa + kt * fsa, lane DAG_TL(, tl_wait));
-      warp_wait_flag(fb + kt * fsb, lane DAG_TL(, tl_wait));
-    }
     load_slab<Cfg, A_KMAJOR, Cfg::TM>(sA + s * SLAB_A, Ap, ld, j * BK, tid);
     load_slab<Cfg, B_KMAJOR, Cfg::TN>(sB + s * SLAB_B, Bp, ld, j * BK, tid);
     mbar_cp_async_arrive(&ring.full[s]);
     ring.gi++;
   };
-#pragma unroll
-  for (int j = 0; j < PREF; ++j)
-    if (j < nk) issue(j);
+  // Slabs are issued PREF ahead of the one being consumed.  The first slab of a k tile that is not yet known to be
+  // final needs that tile's flags: while older slabs are still waiting to be consumed the flags are only PEEKED
+  // (no blocking: the contraction of what has landed goes first), and the warp blocks on them only once its
+  // pipeline is empty - so when the chain tile arrives nothing but that tile's own work is left to do.
+  int issued = 0, ready_slabs = nready * SPT;
   for (int kt = 0; kt < nk; ++kt) {
-    if (kt + PREF < nk) issue(kt + PREF);
+    const int want = kt + PREF + 1 < nk ? kt + PREF + 1 : nk;
+    while (issued < want) {
+      if (issued >= ready_slabs) {
+        const int ktile = issued / SPT;
+        if (issued > kt) {
+          int ok = 0;
+          if (lane == 0) ok = ld_acquire(fa + ktile * fsa) & ld_acquire(fb + ktile * fsb);
+          ok = __shfl_sync(0xffffffffu, ok, 0);  // (also orders the other lanes' operand reads after the acquire)
+          if (!ok) break;
+        } else {
+          warp_wait_flag(fa + ktile * fsa, lane DAG_TL(, tl_wait));
+          warp_wait_flag(fb + ktile * fsb, lane DAG_TL(, tl_wait));
+          DAG_TL(if (tl_col >= 0 && ktile == nkt - 1) tl_mark(tl_now(), 20, tl_col);)
+        }
+        ready_slabs = (ktile + 1) * SPT;
+      }
+      issue(issued);
+      ++issued;
+    }
     const int s = ring.gc % NS;
     mbar_wait(&ring.full[s], (unsigned)((ring.gc / NS) & 1));
+    DAG_TL(if (tl_col >= 0 && kt >= nk - SPT) tl_mark(tl_now(), 21 + (kt - (nk - SPT)), tl_col);)
     if (active) {
       const double* a_s = sA + s * SLAB_A;
       const double* b_s = sB + s * SLAB_B;
@@ -168,10 +207,24 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
 #pragma unroll
         for (int j = 0; j < NT; ++j)
           bv[j] = B_KMAJOR ? b_s[(n0 + 8 * j + g) * LD_K + k4 * 4 + t] : b_s[(k4 * 4 + t) * LD_B + n0 + 8 * j + g];
+        if (!TRI || tri_cls == 0) {
 #pragma unroll
-        for (int i = 0; i < MT; ++i)
+          for (int i = 0; i < MT; ++i)
 #pragma unroll
-          for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+            for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+        } else if (tri_cls == 1) {
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+              if (j <= i) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+        } else {
+#pragma unroll
+          for (int i = 4; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+              if (j <= i - 4) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+        }
       }
     }
     __syncwarp();
@@ -189,7 +242,19 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
   __shared__ int s_task;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  // Warp tile (64 x 32) origins inside the 128 x 128 tile.  Every SM sub-partition has its own DMMA pipe (one
+  // m8n8k4 per 16.75 cycles, tools/smsp_probe.cu) shared by warps w and w + 4, so wherever a triangular operand
+  // makes the warp tiles unequal the map pairs heavy with light:
+  //   k loops over full tiles        (m0, n0) = (64 (w & 1), 32 (w >> 1))
+  //   diagonal tiles (lower part)    the six warp tiles that touch the lower triangle: the two full ones alone on a
+  //                                  sub-partition, a 26-block with a 10-block tile on the two others (dm0, dn0)
+  //   epilogue  T D_j^T   (POTRF)    work grows with the column strip: strips {0, 96} and {32, 64} paired (n0p)
+  //   epilogue -D_i T     (TRTRI)    work grows with the row half: one upper and one lower half per sub-partition (m0t)
   const int m0 = (warp % Cfg::WM) * (MT * 8), n0 = (warp / Cfg::WM) * (NT * 8);
+  const int dm0 = (int)((0x8Bu >> warp) & 1u) * 64;                       // w = 0..7 -> 64 64  0 64  0  0  0 64
+  const int dn0 = (int)((0x31322010u >> (4 * warp)) & 0xfu) * 32;         //          ->  0 32  0 64 64 96 32 96
+  const int n0p = (int)((0x2310u >> (4 * (warp >> 1))) & 0xfu) * 32;      // w >> 1 = 0..3 -> 0 32 96 64
+  const int m0t = (int)(((warp & 1) ^ (warp >> 2)) & 1) * 64;
   double* sA = smem;
   double* sB = smem + NS * SLAB_A;
   double* T = smem;               // resident tile, aliases the operand ring
@@ -232,19 +297,42 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
     const bool is_trtri = type == DAG_TRTRI;
     if (type == DAG_LAUUM) {
       // ---------------- S_ij = sum_{k >= i} X_ki^T X_kj: both operands K-major, rows of X become final in
-      // ascending order, so the k loop follows the inverse as it completes; no epilogue, no flag (nothing in
-      // this kernel reads S)
-      const double* LAp = f.X + (size_t)ti * TB + (size_t)ti * TB * ld;
-      const double* LBp = f.X + (size_t)ti * TB + (size_t)tj * TB * ld;
-      const bool act = !(ti == tj && n0 > m0 + MT * 8 - 1);
-      double acc[MT][NT][2];
-#pragma unroll
-      for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-      dag_kloop<true, true>(acc, ring, sA, sB, LAp, LBp, ld, nb - ti, flagX + ti * nb + ti, nb, flagX + ti * nb + tj, nb, act,
-                            0u, tid DAG_TL(, tl_wait));
+      // ascending order, so the k loop follows the inverse as it completes; no epilogue, no ready flag (nothing
+      // in this kernel reads S).  A tile may be summed in PIECES over block rows [ti + kt0, ti + kt1) of X
+      // (partial sums kept in place in S; summation order unchanged), so that the chain-bound stretches of a
+      // mid-size factorisation absorb the X^T X work instead of leaving it all for after the last column.
+      const int r0 = ti + kt0;
+      const double* LAp = f.X + (size_t)r0 * TB + (size_t)ti * TB * ld;
+      const double* LBp = f.X + (size_t)r0 * TB + (size_t)tj * TB * ld;
       double* Sg = f.W + (size_t)ti * TB + (size_t)tj * TB * ld;
+      int* progS = progX + nb * nb + ti * nb + tj;
+      const bool act = !(ti == tj && n0 > m0 + MT * 8 - 1);
+      if (piece > 0) {
+        if (lane == 0) {
+          if (ld_acquire(progS) < piece) {
+            DAG_TL(const unsigned long long w0 = tl_now();)
+            while (ld_acquire(progS) < piece) __nanosleep(32);
+            DAG_TL(tl_wait += tl_now() - w0;)
+          }
+        }
+        __syncwarp();
+      }
+      double acc[MT][NT][2];
+      if (piece > 0 && act) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) acc[i][j][e] = __ldcg(Sg + (size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ld);
+      } else {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      }
+      dag_kloop<true, true>(acc, ring, sA, sB, LAp, LBp, ld, kt1 - kt0, flagX + r0 * nb + ti, nb, flagX + r0 * nb + tj, nb, act,
+                            0u, tid, m0, n0 DAG_TL(, tl_wait));
       if (act) {
 #pragma unroll
         for (int i = 0; i < MT; ++i)
@@ -253,7 +341,14 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
 #pragma unroll
             for (int e = 0; e < 2; ++e) Sg[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ld] = acc[i][j][e];
       }
-      DAG_TL(tl_log(tl_t0, (200 + type) | ((long long)ti << 8) | ((long long)tj << 20) | ((long long)(nb - ti) << 32) | ((long long)(tl_wait > 0xfffff ? 0xfffff : tl_wait) << 44));)
+      if (!last) {
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence();
+          st_release(progS, piece + 1);
+        }
+      }
+      DAG_TL(tl_log(tl_t0, (200 + type) | ((long long)ti << 8) | ((long long)tj << 20) | ((long long)(kt1 - kt0) << 32) | ((long long)(tl_wait > 0xfffff ? 0xfffff : tl_wait) << 44));)
       continue;
     }
     const double* Cin;  // where the accumulator starts from (nullptr = zero)
@@ -291,8 +386,9 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       }
       __syncwarp();
     }
-    // the strictly upper 64 x 32 warp tiles of a diagonal task are never read: skip their DMMAs
-    const bool active = !(type == DAG_DIAG && n0 > m0 + MT * 8 - 1);
+    // diagonal task: balanced warp tile map (see the kernel head); warps 4 and 5 hold the two tiles above the diagonal
+    const bool active = type != DAG_DIAG || (warp != 4 && warp != 5);
+    const int km0 = type == DAG_DIAG ? dm0 : m0, kn0 = type == DAG_DIAG ? dn0 : n0;
 
     double acc[MT][NT][2];
     if (Cin != nullptr) {  // __ldcg: a partial result may have been written by another SM
@@ -301,17 +397,19 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
 #pragma unroll
         for (int j = 0; j < NT; ++j)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) acc[i][j][e] = __ldcg(Cin + (size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ld);
+          for (int e = 0; e < 2; ++e) acc[i][j][e] = __ldcg(Cin + (size_t)(km0 + 8 * i + g) + (size_t)(kn0 + 8 * j + 2 * t + e) * ld);
     } else {
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     }
-    if (!is_trtri)
-      dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, 0x80000000u, tid DAG_TL(, tl_wait));
+    if (type == DAG_DIAG)
+      dag_kloop<false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, 0x80000000u, tid, km0, kn0 DAG_TL(, tl_wait, last ? tj : -1));
+    else if (!is_trtri)
+      dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, 0x80000000u, tid, km0, kn0 DAG_TL(, tl_wait));
     else
-      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, 0u, tid DAG_TL(, tl_wait));
+      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, 0u, tid, km0, kn0 DAG_TL(, tl_wait));
     if (!last) {
       // ---------------- non-final piece: leave the partial result, publish the piece count
       if (active) {
@@ -320,7 +418,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
 #pragma unroll
           for (int j = 0; j < NT; ++j)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) Cpart[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ld] = acc[i][j][e];
+            for (int e = 0; e < 2; ++e) Cpart[(size_t)(km0 + 8 * i + g) + (size_t)(kn0 + 8 * j + 2 * t + e) * ld] = acc[i][j][e];
       }
       __syncthreads();
       if (tid == 0) {
@@ -330,13 +428,14 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       DAG_TL(tl_log(tl_t0, (210 + type) | ((long long)ti << 8) | ((long long)tj << 20) | ((long long)nkt << 32) | ((long long)(tl_wait > 0xfffff ? 0xfffff : tl_wait) << 44));)
       continue;
     }
+    DAG_TL(if (type == DAG_DIAG || ti == tj + 1) tl_mark(tl_now(), type == DAG_DIAG ? 0 : 10, tj);)
     __syncthreads();  // every warp is done with the operand ring: T may overwrite it
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll
       for (int j = 0; j < NT; ++j)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) T[(m0 + 8 * i + g) + (n0 + 8 * j + 2 * t + e) * DG_LD] = acc[i][j][e];
+        for (int e = 0; e < 2; ++e) T[(km0 + 8 * i + g) + (kn0 + 8 * j + 2 * t + e) * DG_LD] = acc[i][j][e];
     __syncthreads();
 
     if (type == DAG_DIAG) {
@@ -345,7 +444,9 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       double* rdiag = w + 64 * DG_WLD;
       double* dvec = rdiag + TB;
       double* colbuf = dvec + TB;
+      DAG_TL(tl_mark(tl_now(), 1, tj);)
       diag_cholesky_smem<DAG_THREADS>(T, rdiag, dvec, colbuf, tj, f.n_valid, f.info);
+      DAG_TL(tl_mark(tl_now(), 2, tj);)
       auto lower_block_elem = [](int idx, int& r, int& c, bool& on_diag) {
         const int b = idx >> 9, e = idx & 511;
         const int bi = (b >= 6) ? 3 : ((b >= 3) ? 2 : ((b >= 1) ? 1 : 0)), bj = b - bi * (bi + 1) / 2;
@@ -353,31 +454,29 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
         c = 32 * bj + (e >> 4);
         on_diag = bi == bj;
       };
-#pragma unroll 4
-      for (int idx = tid; idx < 10 * 512; idx += DAG_THREADS) {
+      // The chain waits for D_j = L_jj^-1 only (the next column's panel is T D_j^T; nothing in this kernel reads the
+      // diagonal tile of L): L_jj is parked in registers, the in-place inverse and the store of D_j go first and
+      // the flag is released; L_jj and the log-determinant part follow off the critical path.
+      constexpr int LPT = 10 * 512 / DAG_THREADS;  // double2 per thread: the 10 lower 32 x 32 blocks
+      double2 lreg[LPT];
+#pragma unroll
+      for (int q = 0; q < LPT; ++q) {
         int r, c;
         bool dg;
-        lower_block_elem(idx, r, c, dg);
+        lower_block_elem(tid + q * DAG_THREADS, r, c, dg);
         double2 v = *reinterpret_cast<const double2*>(&T[r + c * DG_LD]);
         if (dg) {
           if (r < c) v.x = 0.0;
           if (r + 1 < c) v.y = 0.0;
         }
-        *reinterpret_cast<double2*>(&Cg[(size_t)r + (size_t)c * ld]) = v;
+        lreg[q] = v;
       }
-      {
-        double v = 0.0;
-        if (tid < TB && tj * TB + tid < f.n_valid) v = log(dvec[tid]);
-        __syncthreads();
-        if (tid < TB) {
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-          if ((tid & 31) == 0) dvec[tid >> 5] = v;
-        }
-        __syncthreads();
-        if (tid == 0) f.logdet_part[tj] = ((dvec[0] + dvec[1]) + dvec[2]) + dvec[3];
-      }
+      double lv = 0.0;
+      if (tid < TB && tj * TB + tid < f.n_valid) lv = log(dvec[tid]);
+      __syncthreads();
+      DAG_TL(tl_mark(tl_now(), 3, tj);)
       diag_invert_smem<DAG_THREADS>(T, w, rdiag);
+      DAG_TL(tl_mark(tl_now(), 4, tj);)
       double* Dg = f.X + (size_t)tj * TB * (ld + 1);
 #pragma unroll 4
       for (int idx = tid; idx < 10 * 512; idx += DAG_THREADS) {
@@ -394,8 +493,26 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       __syncthreads();
       if (tid == 0) {
         __threadfence();
-        st_release(flagL + tj * nb + tj, 1);
         st_release(flagX + tj * nb + tj, 1);
+      }
+      DAG_TL(tl_mark(tl_now(), 5, tj);)
+#pragma unroll
+      for (int q = 0; q < LPT; ++q) {
+        int r, c;
+        bool dg;
+        lower_block_elem(tid + q * DAG_THREADS, r, c, dg);
+        *reinterpret_cast<double2*>(&Cg[(size_t)r + (size_t)c * ld]) = lreg[q];
+      }
+      if (tid < TB) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, off);
+        if ((tid & 31) == 0) dvec[tid >> 5] = lv;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        f.logdet_part[tj] = ((dvec[0] + dvec[1]) + dvec[2]) + dvec[3];
+        __threadfence();
+        st_release(flagL + tj * nb + tj, 1);
       }
       // timeline code: 200 + type | i << 8 | j << 20 | k tiles << 32 | ns spent waiting for flags (warp 0) << 44
       DAG_TL(tl_log(tl_t0, (200 + type) | ((long long)ti << 8) | ((long long)tj << 20) | ((long long)nkt << 32) | ((long long)(tl_wait > 0xfffff ? 0xfffff : tl_wait) << 44));)
@@ -406,9 +523,11 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
     //   POTRF: C = T D_j^T   (A operand = T resident, B operand = D_j streamed, B[k][n] = D_j[n][k])
     //   TRTRI: C = -D_i T    (A operand = D_i streamed,  B operand = T resident)
     // D is lower triangular: DMMAs whose D fragment is identically zero are skipped.
+    const int em0 = is_trtri ? m0t : m0, en0 = is_trtri ? n0 : n0p;  // balanced warp tile maps of the epilogue
     const int dblk = is_trtri ? ti : tj;
     const double* Dg = f.X + (size_t)dblk * TB * (ld + 1);
-    warp_wait_flag(flagL + dblk * nb + dblk, lane DAG_TL(, tl_wait));
+    warp_wait_flag(flagX + dblk * nb + dblk, lane DAG_TL(, tl_wait));
+    DAG_TL(if (!is_trtri && ti == tj + 1) tl_mark(tl_now(), 11, tj);)
     auto issue_e = [&](int j) {
       const int s = ring.gi % NS, r = ring.gi / NS;
       if (r > 0) mbar_wait(&ring.empty[s], (unsigned)((r - 1) & 1));
@@ -428,49 +547,67 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       const int s = ring.gc % NS;
       mbar_wait(&ring.full[s], (unsigned)((ring.gc / NS) & 1));
       const double* e_s = sE + s * DAG_ESLAB;
-#pragma unroll
+      // D is lower triangular: D[r][k] = 0 for k > r.  The DMMAs whose D fragment is identically zero are skipped
+      // with warp-uniform jumps into a fall-through switch (a predicated-off DMMA would still cost its pipe slot).
+#define DAG_ROW(i_)                                                                              \
+  _Pragma("unroll") for (int j = 0; j < NT; ++j) dmma884(acc[i_][j][0], acc[i_][j][1], av[i_], bv[j]);
+#define DAG_COL(j_)                                                                              \
+  _Pragma("unroll") for (int i = 0; i < MT; ++i) dmma884(acc[i][j_][0], acc[i][j_][1], av[i], bv[j_]);
+#pragma unroll 1
       for (int k4 = 0; k4 < BK / 4; ++k4) {
         const int kk = kt * BK + k4 * 4;  // first k of this DMMA step
         double av[MT], bv[NT];
         if (is_trtri) {
+          const int imin = kk - em0 > 0 ? (kk - em0) >> 3 : 0;  // row blocks i < imin: 8 i + 7 + em0 < kk
+          if (imin >= MT) continue;
 #pragma unroll
-          for (int i = 0; i < MT; ++i) av[i] = flip_sign(e_s[(k4 * 4 + t) * DG_LD + m0 + 8 * i + g], 0x80000000u);
+          for (int i = 0; i < MT; ++i) av[i] = flip_sign(e_s[(k4 * 4 + t) * DG_LD + em0 + 8 * i + g], 0x80000000u);
 #pragma unroll
-          for (int j = 0; j < NT; ++j) bv[j] = T[(n0 + 8 * j + g) * DG_LD + kk + t];
-#pragma unroll
-          for (int i = 0; i < MT; ++i)
-            if (m0 + 8 * i + 7 >= kk) {  // D_i[m][k] = 0 for k > m
-#pragma unroll
-              for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
-            }
+          for (int j = 0; j < NT; ++j) bv[j] = T[(en0 + 8 * j + g) * DG_LD + kk + t];
+          switch (imin) {
+            case 0: DAG_ROW(0)  // fall through
+            case 1: DAG_ROW(1)
+            case 2: DAG_ROW(2)
+            case 3: DAG_ROW(3)
+            case 4: DAG_ROW(4)
+            case 5: DAG_ROW(5)
+            case 6: DAG_ROW(6)
+            default: DAG_ROW(7)
+          }
         } else {
+          const int jmin = kk - en0 > 0 ? (kk - en0) >> 3 : 0;  // column blocks j < jmin: 8 j + 7 + en0 < kk
+          if (jmin >= NT) continue;
 #pragma unroll
-          for (int i = 0; i < MT; ++i) av[i] = T[(kk + t) * DG_LD + m0 + 8 * i + g];
+          for (int i = 0; i < MT; ++i) av[i] = T[(kk + t) * DG_LD + em0 + 8 * i + g];
 #pragma unroll
-          for (int j = 0; j < NT; ++j) bv[j] = e_s[(k4 * 4 + t) * DG_LD + n0 + 8 * j + g];
-#pragma unroll
-          for (int j = 0; j < NT; ++j)
-            if (n0 + 8 * j + 7 >= kk) {  // D_j[n][k] = 0 for k > n
-#pragma unroll
-              for (int i = 0; i < MT; ++i) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
-            }
+          for (int j = 0; j < NT; ++j) bv[j] = e_s[(k4 * 4 + t) * DG_LD + en0 + 8 * j + g];
+          switch (jmin) {
+            case 0: DAG_COL(0)  // fall through
+            case 1: DAG_COL(1)
+            case 2: DAG_COL(2)
+            default: DAG_COL(3)
+          }
         }
       }
+#undef DAG_ROW
+#undef DAG_COL
       __syncwarp();
       if (lane == 0) mbar_arrive(&ring.empty[s]);
       ring.gc++;
     }
+    DAG_TL(if (!is_trtri && ti == tj + 1) tl_mark(tl_now(), 12, tj);)
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll
       for (int j = 0; j < NT; ++j)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) Cg[(size_t)(m0 + 8 * i + g) + (size_t)(n0 + 8 * j + 2 * t + e) * ld] = acc[i][j][e];
+        for (int e = 0; e < 2; ++e) Cg[(size_t)(em0 + 8 * i + g) + (size_t)(en0 + 8 * j + 2 * t + e) * ld] = acc[i][j][e];
     __syncthreads();  // all stores of the tile issued; T is free again for the next task's ring
     if (tid == 0) {
       __threadfence();
       st_release((is_trtri ? flagX : flagL) + ti * nb + tj, 1);
     }
+    DAG_TL(if (!is_trtri && ti == tj + 1) tl_mark(tl_now(), 13, tj);)
     DAG_TL(tl_log(tl_t0, (200 + type) | ((long long)ti << 8) | ((long long)tj << 20) | ((long long)nkt << 32) | ((long long)(tl_wait > 0xfffff ? 0xfffff : tl_wait) << 44));)
   }
 }

@@ -183,6 +183,27 @@ extern "C" int gpedm_fit_grid(int64_t T, const double* y, const int32_t* pop, in
                                     stats));
 }
 
+// Debug export (host only, no device needed): the task list the persistent factorisation kernel would run for nb
+// block columns, with the library's scheduling defaults.  out[4 q .. 4 q + 3] = {type, i, j, kt0 | kt1 << 10 |
+// piece << 20 | last << 30}.  tests/test_host_logic.py replays it against the kernel's dependency rules.
+extern "C" int gpedm_debug_dag_tasks(int nb, int lauum_chunk, int* out, int max_tasks, int* ntasks, int* nfactor) {
+  if (nb < 1 || nb > 1023) return GPEDM_ERR_ARG;
+  std::vector<int4> tasks;
+  int nf = 0;
+  build_dag_tasks(nb, g_dag_lag, g_dag_lead, g_dag_chunk, lauum_chunk < 0 ? dag_lauum_chunk(nb) : lauum_chunk, g_dag_ltail, 0,
+                  tasks, &nf);
+  if (ntasks) *ntasks = (int)tasks.size();
+  if (nfactor) *nfactor = nf;
+  if (out)
+    for (size_t q = 0; q < tasks.size() && (int)q < max_tasks; ++q) {
+      out[4 * q] = tasks[q].x;
+      out[4 * q + 1] = tasks[q].y;
+      out[4 * q + 2] = tasks[q].z;
+      out[4 * q + 3] = tasks[q].w;
+    }
+  return 0;
+}
+
 #ifdef GPEDM_TIMELINE
 // Debug export: copy the CTA timeline records logged so far (4 x uint64 each) and reset the log.
 extern "C" int gpedm_debug_timeline(unsigned long long* out, unsigned int max_records, unsigned int* n_out) {

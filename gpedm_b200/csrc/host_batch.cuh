@@ -323,7 +323,7 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
     L.Np = L.nb * TB;
     L.ntiles = L.nb * (L.nb + 1) / 2;
     L.split = 4;  // few tiles per fit: four column ranges per tile in the assembly / trace kernels
-    L.nflags = 4 * L.nb * L.nb;
+    L.nflags = DAG_NFLAG * L.nb * L.nb;
     dmax = std::max(dmax, L.d);
   }
   for (int q = 0; q < nf; ++q) {  // flags of all fits contiguous: one memset per iteration
@@ -416,7 +416,7 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
     G.logdet_part = F.dlogdet;
     G.info = (int*)(base + info_off) + q;
     int nfac = 0;
-    build_dag_tasks(L.nb, 1, 0, 512, q, ftasks[q], &nfac);  // strict dependency order: any number of CTAs makes progress
+    build_dag_tasks(L.nb, 1, 0, 512, 0, 1, q, ftasks[q], &nfac);  // strict dependency order: any number of CTAs makes progress
     total_tasks += ftasks[q].size();
     nTS += (size_t)L.ntiles * L.split;
     nT += L.ntiles;

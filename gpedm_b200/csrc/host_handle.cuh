@@ -23,7 +23,8 @@ struct gpedm_fit_s {
   int* hinfo = nullptr;  // pinned
   int4* dtasks = nullptr;  // task list of the persistent factorisation kernel (dag_factor.cuh)
   int ntasks = 0;          // all tasks: Cholesky, inverse, Sigma^-1 = X^T X
-  int ntasks_factor = 0;   // without the trailing Sigma^-1 tasks (sequential helper: only L and z are needed)
+  int ntasks_factor = 0;   // without the Sigma^-1 tasks (sequential helper: only L and z are needed); that list starts at
+  int factor_off = 0;      // dtasks + factor_off
   int* dsync = nullptr;    // its task counter + per-tile ready flags, zeroed at the start of every evaluation
   DagFit* dfit = nullptr;  // its description of this fit's matrices
   int num_sms = 148;
@@ -81,6 +82,13 @@ static const int g_dag_lead = getenv("GPEDM_DAG_LEAD") ? std::max(0, atoi(getenv
 // k tiles per piece of a long tile (512 = never split)
 static const int g_dag_chunk = getenv("GPEDM_DAG_CHUNK") ? std::min(512, std::max(1, atoi(getenv("GPEDM_DAG_CHUNK")))) : 512;
 static const int g_dag_lag = getenv("GPEDM_DAG_LAG") ? std::max(1, atoi(getenv("GPEDM_DAG_LAG"))) : 2;
+// Sigma^-1 = X^T X tiles summed in pieces of this many block rows, interleaved with the factorisation (0 = whole
+// tiles after it, the default: interleaved pieces were measured SLOWER at every size - 4086 rows 3.38 -> 3.66 ms
+// with pieces of 8, 4.07 with 4 - because the busier CTAs claim the chain tasks later, profiles/r02_lauum_pieces.txt).
+static const int g_dag_lchunk = getenv("GPEDM_DAG_LAUUM_CHUNK") ? std::max(0, atoi(getenv("GPEDM_DAG_LAUUM_CHUNK"))) : 0;
+static const int g_dag_lmaxnb = getenv("GPEDM_DAG_LAUUM_MAX_NB") ? atoi(getenv("GPEDM_DAG_LAUUM_MAX_NB")) : 40;
+static const int g_dag_ltail = getenv("GPEDM_DAG_LAUUM_TAIL") ? std::max(1, atoi(getenv("GPEDM_DAG_LAUUM_TAIL"))) : 1;
+static inline int dag_lauum_chunk(int nb) { return (nb >= 3 && nb <= g_dag_lmaxnb) ? g_dag_lchunk : 0; }
 static std::mutex g_attr_mutex;
 static int ensure_kernel_attrs(int device) {
   std::lock_guard<std::mutex> lock(g_attr_mutex);  // batch workers create handles concurrently
@@ -226,7 +234,7 @@ static void free_handle(gpedm_fit_s* h) {
 //     that the bulk work never queues up in front of the chain.
 // Within a step: chain tasks, Cholesky tiles, inverse tiles, then pieces.  Every dependency of a task
 // precedes it in the list, except that chain tasks may precede theirs (bounded: 2 (lead + 1) tasks).
-static void build_dag_tasks(int nb, int lag, int lead, int ch, int fit, std::vector<int4>& tasks, int* nfactor) {
+static void build_dag_tasks(int nb, int lag, int lead, int ch, int lch, int ltail, int fit, std::vector<int4>& tasks, int* nfactor) {
   struct Ev {
     int step, cls, seq;
     int4 t;
@@ -253,19 +261,47 @@ static void build_dag_tasks(int nb, int lag, int lead, int ch, int fit, std::vec
   }
   for (int r = 1; r < nb; ++r)
     for (int j = 0; j < r; ++j) add_tile(DAG_TRTRI, r, j, r - j, r + lag, 2, j + lag, r + lag - 1);
+  // Sigma^-1 = X^T X.  S_ij sums over block rows k >= i of X in ascending order - the order in which the inverse
+  // completes them.  With lch == 0 every tile is one task after the factorisation (longest k range first): the
+  // CTAs that run out of inverse tiles accumulate S behind the inverse instead of idling.  With lch > 0 a tile is
+  // summed in pieces - block rows up to the next multiple of lch, ..., and a final piece of the last `ltail`
+  // rows - each placed right after the inverse row it ends with: a chain-bound factorisation (nb <~ 40, where
+  // most CTAs wait for the Cholesky chain most of the time) then absorbs the X^T X work while it waits, and only
+  // the short final pieces remain after the last column.
+  int nfac = 0;
+  if (lch > 0) {
+    const int tail0 = std::max(0, nb - std::max(1, ltail));  // first block row of the final piece
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j <= i; ++j) {
+        int k0 = i, piece = 0;
+        while (k0 < nb) {
+          int k1;
+          if (k0 >= tail0)
+            k1 = nb;
+          else
+            k1 = std::min(tail0, (k0 / lch + 1) * lch);
+          const int last = k1 == nb;
+          evs.push_back({last ? nb + lag + 1 : k1 - 1 + lag + 1, 4, seq++,
+                         make_int4(DAG_LAUUM | (fit << 4), i, j, word(k0 - i, k1 - i, piece, last))});
+          ++piece;
+          k0 = k1;
+        }
+      }
+  }
   std::stable_sort(evs.begin(), evs.end(), [](const Ev& x, const Ev& y) {
     if (x.step != y.step) return x.step < y.step;
     if (x.cls != y.cls) return x.cls < y.cls;
     return x.seq < y.seq;
   });
   tasks.resize(evs.size());
-  for (size_t q = 0; q < evs.size(); ++q) tasks[q] = evs[q].t;
-  *nfactor = (int)tasks.size();
-  // Sigma^-1 = X^T X after the inverse, longest k range first.  S_ij sums over block rows k >= i of X in
-  // ascending order - the order in which the inverse completes them - so the CTAs that run out of inverse
-  // tiles at the end of the factorisation accumulate S behind it instead of idling.
-  for (int i = 0; i < nb; ++i)
-    for (int j = 0; j <= i; ++j) tasks.push_back(make_int4(DAG_LAUUM | (fit << 4), i, j, 0));
+  for (size_t q = 0; q < evs.size(); ++q) {
+    tasks[q] = evs[q].t;
+    if ((evs[q].t.x & 15) != DAG_LAUUM) nfac = (int)q + 1;
+  }
+  *nfactor = nfac;
+  if (lch <= 0)
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j <= i; ++j) tasks.push_back(make_int4(DAG_LAUUM | (fit << 4), i, j, word(0, nb - i, 0, 1)));
 }
 
 // Allocate a handle for an N x d problem with np populations: device buffers, streams, events.
@@ -325,12 +361,22 @@ static int alloc_handle(int device, int64_t N, int32_t d, int32_t np, bool has_r
   ALLOC(h->dtracepart, (size_t)h->ntiles * h->tile_split * (MAXD + 3) * 8);
   ALLOC(h->dscal, NSCAL * 8);
   ALLOC(h->dinfo, 4);
-  ALLOC(h->dsync, (size_t)(1 + 4 * h->nb * h->nb) * 4);
+  ALLOC(h->dsync, (size_t)(1 + DAG_NFLAG * h->nb * h->nb) * 4);
   {
     std::vector<int4> tasks;
-    build_dag_tasks(h->nb, g_dag_lag, g_dag_lead, g_dag_chunk, 0, tasks, &h->ntasks_factor);
+    const int lch = dag_lauum_chunk(h->nb);
+    build_dag_tasks(h->nb, g_dag_lag, g_dag_lead, g_dag_chunk, lch, g_dag_ltail, 0, tasks, &h->ntasks_factor);
     const int nb = h->nb;
     h->ntasks = (int)tasks.size();
+    h->factor_off = 0;
+    if (lch > 0) {  // Sigma^-1 pieces are interleaved: the factor-only list (sequential helper) is a separate copy
+      std::vector<int4> ftasks;
+      int nf = 0;
+      build_dag_tasks(h->nb, g_dag_lag, g_dag_lead, g_dag_chunk, 0, g_dag_ltail, 0, ftasks, &nf);
+      h->factor_off = h->ntasks;
+      h->ntasks_factor = nf;
+      tasks.insert(tasks.end(), ftasks.begin(), ftasks.begin() + nf);
+    }
     ALLOC(h->dtasks, tasks.size() * sizeof(int4));
     ALLOC(h->dfit, sizeof(DagFit));
     DagFit hf;

@@ -136,10 +136,10 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   NvtxRange::next("gpedm:potrf");
   if (!g_no_dag) {
     // --- Cholesky + triangular inverse: ONE persistent, dependency-driven launch (dag_factor.cuh)
-    CU(cudaMemsetAsync(h->dsync, 0, (size_t)(1 + 4 * nb * nb) * 4, st));
+    CU(cudaMemsetAsync(h->dsync, 0, (size_t)(1 + DAG_NFLAG * nb * nb) * 4, st));
     DagArgs da;
     da.fits = h->dfit;
-    da.tasks = h->dtasks;
+    da.tasks = through_z_only ? h->dtasks + h->factor_off : h->dtasks;
     da.ntasks = through_z_only ? h->ntasks_factor : h->ntasks;
     da.counter = h->dsync;
     dag_factor_kernel<<<std::min(h->num_sms, da.ntasks), DAG_THREADS, DAG_SMEM_BYTES, st>>>(da);

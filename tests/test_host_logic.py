@@ -116,3 +116,82 @@ def test_record_roundtrip():
     i, back = dist.unpack_record(dist.pack_record(7, res))
     assert i == 7 and back["iter"] == 12 and back["nllpost"] == -3.5
     np.testing.assert_array_equal(back["grad"], res["grad"])
+
+
+def _dag_tasks(nb, lauum_chunk=-1):
+    import ctypes as C
+    L = G.lib()
+    n, nf = C.c_int(0), C.c_int(0)
+    L.gpedm_debug_dag_tasks.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    assert L.gpedm_debug_dag_tasks(nb, lauum_chunk, None, 0, C.byref(n), C.byref(nf)) == 0
+    buf = (C.c_int * (4 * n.value))()
+    assert L.gpedm_debug_dag_tasks(nb, lauum_chunk, buf, n.value, C.byref(n), C.byref(nf)) == 0
+    t = np.frombuffer(buf, dtype=np.int32).reshape(-1, 4)
+    return [(int(a) & 15, int(i), int(j), int(w) & 1023, (int(w) >> 10) & 1023, (int(w) >> 20) & 1023, (int(w) >> 30) & 1)
+            for a, i, j, w in t], nf.value
+
+
+@pytest.mark.parametrize("nb,lch", [(1, -1), (2, -1), (3, -1), (4, -1), (5, 2), (8, -1), (8, 0), (13, 3), (32, -1), (32, 8), (64, -1)])
+def test_dag_task_list_covers_every_tile_and_never_deadlocks(nb, lch):
+    """The task list of the persistent factorisation kernel (csrc/host_handle.cuh build_dag_tasks), replayed on the
+    CPU under the kernel's own rules (csrc/dag_factor.cuh): CTAs claim tasks in list order and wait inside a task
+    for the ready flags of its operands.  Every tile's k range must be covered exactly once by consecutive pieces,
+    and in-order claiming by a handful of CTAs (or by 148) must always make progress."""
+    DIAG, POTRF, TRTRI, LAUUM = 0, 1, 2, 3
+    tasks, nfactor = _dag_tasks(nb, lch)
+    # ---- coverage
+    cover = {}
+    for ty, i, j, k0, k1, piece, last in tasks:
+        c = cover.setdefault((ty, i, j), [0, 0, False])  # next k, next piece, closed
+        assert not c[2] and k0 == c[0] and piece == c[1] and k1 >= k0
+        c[0], c[1], c[2] = k1, piece + 1, bool(last)
+    want = {}
+    for c in range(nb):
+        want[(DIAG, c, c)] = c
+        for i in range(c + 1, nb):
+            want[(POTRF, i, c)] = c
+            want[(TRTRI, i, c)] = i - c
+        for j in range(c + 1):
+            want[(LAUUM, c, j)] = nb - c
+    assert set(cover) == set(want)
+    for key, nkt in want.items():
+        assert cover[key][0] == nkt and cover[key][2], key
+    assert sum(1 for t in tasks if t[0] != LAUUM) <= nfactor <= len(tasks)
+
+    # ---- replay
+    def ready(t, Lf, Xf, prog):
+        ty, i, j, k0, k1, piece, last = t
+        if piece > 0 and prog.get((ty, i, j), 0) < piece:
+            return False
+        if ty in (DIAG, POTRF):
+            if not all(Lf[i][k] and Lf[j][k] for k in range(k0, k1)):
+                return False
+            return not (ty == POTRF and last) or Lf[j][j]
+        if ty == TRTRI:
+            if not all(Lf[i][j + k] and Xf[j + k][j] for k in range(k0, k1)):
+                return False
+            return not last or Lf[i][i]
+        return all(Xf[i + k][i] and Xf[i + k][j] for k in range(k0, k1))
+
+    for P in (3, 148):
+        Lf = [[False] * nb for _ in range(nb)]
+        Xf = [[False] * nb for _ in range(nb)]
+        prog, nxt, held, done = {}, 0, [], 0
+        while done < len(tasks):
+            while len(held) < P and nxt < len(tasks):
+                held.append(tasks[nxt])
+                nxt += 1
+            run = [t for t in held if ready(t, Lf, Xf, prog)]
+            assert run, "deadlock with %d CTAs at task %d of %d (nb=%d)" % (P, nxt, len(tasks), nb)
+            for t in run:
+                ty, i, j, k0, k1, piece, last = t
+                held.remove(t)
+                done += 1
+                if not last:
+                    prog[(ty, i, j)] = piece + 1
+                elif ty == DIAG:
+                    Lf[i][i] = Xf[i][i] = True
+                elif ty == POTRF:
+                    Lf[i][j] = True
+                elif ty == TRTRI:
+                    Xf[i][j] = True

@@ -12,6 +12,8 @@ for n in [int(a) for a in sys.argv[1:]] or [4096, 8192]:
     m.bench_evals(p0, 1.0, 2)
     ms = m.bench_evals(p0, 1.0, 5)
     ph = m.phase_ms()
-    print(json.dumps(dict(env=tag, N=len(Y), ms=round(ms, 3), factor_ms=round(ph["potrf"] + ph["trtri"], 3), lauum=round(ph["lauum"], 3),
-                          tflops=round(len(Y) ** 3 / ms * 1e-9, 2))), flush=True)
+    r = m.likegrad(p0, 1.0, None, None, True)
+    print(json.dumps(dict(env=tag, N=len(Y), ms=round(ms, 3), factor_ms=round(ph["potrf"] + ph["trtri"] + ph["lauum"], 3),
+                          tflops=round(len(Y) ** 3 / ms * 1e-9, 2), nll=r["nllpost"].hex() if hasattr(r["nllpost"], "hex") else float(r["nllpost"]).hex(),
+                          g0=float(r["grad"][0]).hex())), flush=True)
     m.close()

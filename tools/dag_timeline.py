@@ -33,6 +33,7 @@ buf = np.zeros(4 * MAXR, dtype=np.uint64)
 L.gpedm_debug_timeline(buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), MAXR, C.byref(cnt))
 rec = buf[:4 * cnt.value].reshape(cnt.value, 4).astype(np.int64)
 code = rec[:, 3]
+marks = rec[(code & 0xff) == 150]
 isd = (code & 0xff) >= 200
 final_piece = ((code & 0xff) - 200) < 10
 rec, code, final_piece = rec[isd], code[isd], final_piece[isd]
@@ -73,3 +74,26 @@ for q, ix in enumerate(order):
         print("  c=%3d ready %9.1f  step %7.1f  task start %9.1f wait %7.1f nkt %d" % (tj[ix], en[ix], en[ix] - (ends[q - 1] if q else 0), st[ix], wait[ix], nkt[ix]))
 steps = np.diff(ends)
 print("chain step: median %.1f us, mean %.1f, max %.1f; last D ready at %.1f us of %.1f" % (np.median(steps), steps.mean(), steps.max(), ends[-1], T))
+
+# ---- chain marks (thread 0 of the two chain tasks of each block column)
+if len(marks):
+    mk = {}
+    for tm, _, _, cd in marks:
+        mk[(int((cd >> 20) & 0xfff), int((cd >> 8) & 0xff))] = (tm - t0) * 1e-3
+    names_m = [("hop: D_c flag -> seen by POTRF(c+1,c)", (5, 0), (11, 0)), ("POTRF epilogue T D^T", (11, 0), (12, 0)),
+               ("POTRF store + fence + flag", (12, 0), (13, 0)), ("  flag of L(c+1,c) seen by DIAG(c+1) warp 0", (13, 0), (20, 1)), ("  first slab of the last k tile landed", (20, 1), (21, 1)),
+               ("  slab 2", (21, 1), (22, 1)), ("  slab 3", (22, 1), (23, 1)), ("  slab 4", (23, 1), (24, 1)), ("  slab 5", (24, 1), (25, 1)),
+               ("  slab 6", (25, 1), (26, 1)), ("  slab 7", (26, 1), (27, 1)), ("  slab 8", (27, 1), (28, 1)), ("  last slab -> k loop exit", (28, 1), (0, 1)),
+               ("hop + last k tile of DIAG(c+1)", (13, 0), (0, 1)),
+               ("acc -> smem", (0, 1), (1, 1)), ("Cholesky 128", (1, 1), (2, 1)), ("L -> registers, log", (2, 1), (3, 1)),
+               ("inverse 128", (3, 1), (4, 1)), ("store D + fence + flag (L store follows)", (4, 1), (5, 1))]
+    nbk = (len(Y) + 127) // 128
+    print("\nchain step breakdown (us), median / mean over columns:")
+    tot = 0.0
+    for label, (ma, da), (mb, db) in names_m:
+        v = [mk[(c + db, mb)] - mk[(c + da, ma)] for c in range(nbk - 1) if (c + da, ma) in mk and (c + db, mb) in mk]
+        if v:
+            print("  %-42s %7.2f %7.2f" % (label, float(np.median(v)), float(np.mean(v))))
+            if not label.startswith("  "):
+                tot += float(np.median(v))
+    print("  %-42s %7.2f" % ("sum of medians", tot))
