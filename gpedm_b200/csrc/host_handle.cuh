@@ -86,6 +86,7 @@ static const int g_dag_lag = getenv("GPEDM_DAG_LAG") ? std::max(1, atoi(getenv("
 // tiles after it, the default: interleaved pieces were measured SLOWER at every size - 4086 rows 3.38 -> 3.66 ms
 // with pieces of 8, 4.07 with 4 - because the busier CTAs claim the chain tasks later, profiles/r02_lauum_pieces.txt).
 static const int g_dag_lchunk = getenv("GPEDM_DAG_LAUUM_CHUNK") ? std::max(0, atoi(getenv("GPEDM_DAG_LAUUM_CHUNK"))) : 0;
+static const int g_dag_lgroup = getenv("GPEDM_DAG_LAUUM_GROUP") ? std::max(1, atoi(getenv("GPEDM_DAG_LAUUM_GROUP"))) : 12;
 static const int g_dag_lmaxnb = getenv("GPEDM_DAG_LAUUM_MAX_NB") ? atoi(getenv("GPEDM_DAG_LAUUM_MAX_NB")) : 40;
 static const int g_dag_ltail = getenv("GPEDM_DAG_LAUUM_TAIL") ? std::max(1, atoi(getenv("GPEDM_DAG_LAUUM_TAIL"))) : 1;
 static inline int dag_lauum_chunk(int nb) { return (nb >= 3 && nb <= g_dag_lmaxnb) ? g_dag_lchunk : 0; }
@@ -299,9 +300,17 @@ static void build_dag_tasks(int nb, int lag, int lead, int ch, int lch, int ltai
     if ((evs[q].t.x & 15) != DAG_LAUUM) nfac = (int)q + 1;
   }
   *nfactor = nfac;
-  if (lch <= 0)
-    for (int i = 0; i < nb; ++i)
-      for (int j = 0; j <= i; ++j) tasks.push_back(make_int4(DAG_LAUUM | (fit << 4), i, j, word(0, nb - i, 0, 1)));
+  if (lch <= 0) {
+    // Order: square groups of G x G tiles (G^2 ~ the number of resident CTAs), longest k ranges first.  The tiles of
+    // a group read only 2 G distinct column panels of X and their k loops advance together, so all but the first
+    // touch of a panel comes from the L2 instead of HBM (row-by-row order re-read a panel per tile).
+    const int G = g_dag_lgroup;
+    for (int i0 = 0; i0 < nb; i0 += G)
+      for (int j0 = 0; j0 <= i0; j0 += G)
+        for (int i = i0; i < std::min(nb, i0 + G); ++i)
+          for (int j = j0; j <= std::min(i, j0 + G - 1); ++j)
+            tasks.push_back(make_int4(DAG_LAUUM | (fit << 4), i, j, word(0, nb - i, 0, 1)));
+  }
 }
 
 // Allocate a handle for an N x d problem with np populations: device buffers, streams, events.
