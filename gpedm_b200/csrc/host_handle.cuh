@@ -86,7 +86,7 @@ static const int g_dag_lag = getenv("GPEDM_DAG_LAG") ? std::max(1, atoi(getenv("
 // tiles after it, the default: interleaved pieces were measured SLOWER at every size - 4086 rows 3.38 -> 3.66 ms
 // with pieces of 8, 4.07 with 4 - because the busier CTAs claim the chain tasks later, profiles/r02_lauum_pieces.txt).
 static const int g_dag_lchunk = getenv("GPEDM_DAG_LAUUM_CHUNK") ? std::max(0, atoi(getenv("GPEDM_DAG_LAUUM_CHUNK"))) : 0;
-static const int g_dag_lgroup = getenv("GPEDM_DAG_LAUUM_GROUP") ? std::max(1, atoi(getenv("GPEDM_DAG_LAUUM_GROUP"))) : 12;
+static const int g_dag_lgroup = getenv("GPEDM_DAG_LAUUM_GROUP") ? std::max(1, atoi(getenv("GPEDM_DAG_LAUUM_GROUP"))) : 1024;
 static const int g_dag_lmaxnb = getenv("GPEDM_DAG_LAUUM_MAX_NB") ? atoi(getenv("GPEDM_DAG_LAUUM_MAX_NB")) : 40;
 static const int g_dag_ltail = getenv("GPEDM_DAG_LAUUM_TAIL") ? std::max(1, atoi(getenv("GPEDM_DAG_LAUUM_TAIL"))) : 1;
 static inline int dag_lauum_chunk(int nb) { return (nb >= 3 && nb <= g_dag_lmaxnb) ? g_dag_lchunk : 0; }
@@ -301,9 +301,10 @@ static void build_dag_tasks(int nb, int lag, int lead, int ch, int lch, int ltai
   }
   *nfactor = nfac;
   if (lch <= 0) {
-    // Order: square groups of G x G tiles (G^2 ~ the number of resident CTAs), longest k ranges first.  The tiles of
-    // a group read only 2 G distinct column panels of X and their k loops advance together, so all but the first
-    // touch of a panel comes from the L2 instead of HBM (row-by-row order re-read a panel per tile).
+    // Order: longest k ranges first, row by row (GPEDM_DAG_LAUUM_GROUP = G >= nb, the default).  Square groups of
+    // G x G tiles share 2 G column panels of X through the L2; measured at N = 8182 with G = 12: HBM reads of the
+    // launch 13.3 -> 12.6 GB but 0.2 % SLOWER (the launch is DMMA-bound at 0.8 TB/s of HBM traffic), 2 % slower at
+    // N = 4086 - kept as a knob only (profiles/r02_lauum_group.txt).
     const int G = g_dag_lgroup;
     for (int i0 = 0; i0 < nb; i0 += G)
       for (int j0 = 0; j0 <= i0; j0 += G)
