@@ -288,6 +288,30 @@ def run_ours(args):
     grid = None
     if args.grid:
         grid = run_grid(G, gd, world, rank, local, barrier)
+        if grid is not None:
+            # the same job with perfect balance and no set-up cost: every evaluation at the headline rate
+            grid["ideal_s"] = grid["total_evals"] * step_ms * 1e-3 / world
+            grid["efficiency_vs_ideal"] = grid["ideal_s"] / grid["wall_s"]
+        if use_dist and args.inproc:
+            # The north-star design of the sharded grid: ONE process drives all the GPUs (gpedm_fit_grid: a worker
+            # thread per GPU on a shared cost-ordered queue, the series uploaded once per GPU, result records
+            # cross-checked by the library's own ncclAllGather).  Rank 0 runs it over all `world` devices while the
+            # other ranks wait at the barrier with their GPUs idle.
+            barrier()
+            if rank == 0:
+                from gpedm_b200 import batch, synth
+                ti0 = time.perf_counter()
+                cells = batch.fit_grid(synth.ricker(SERIES_LEN, SEED), range(1, 11), (1, 2, 3, 4), ngpus=world)
+                ti = time.perf_counter() - ti0
+                grid["inproc"] = {"api": "gpedm_fit_grid(ngpus=%d) in one process" % world, "wall_s": ti,
+                                  "evals_per_sec": sum(c["nevals"] for c in cells) / ti,
+                                  "status_ok": all(c["status"] == 0 for c in cells),
+                                  "iters_equal_torchrun_grid": [int(c["iter"]) for c in cells] == grid["iters"],
+                                  "nccl_gather_status": int(_lib.lib().gpedm_last_gather_status()),
+                                  "nccl_gather_status_note": "0 = the library's ncclAllGather of the records ran and matched "
+                                                             "the host-delivered records; <0 = NCCL unavailable (records "
+                                                             "delivered from host memory)"}
+            barrier()
 
     if rank == 0:
         peak_dmma = G.fp64_peak(0, local)
@@ -340,6 +364,11 @@ def run_ours(args):
                    "nll_rel_diff_vs_gpu": abs(out["nllpost"] - res["nllpost"]) / abs(out["nllpost"]),
                    "grad_err_vs_gpu": float(np.max(np.abs(np.asarray(out["grad"]) - np.asarray(res["grad"])))
                                             / max(1.0, float(np.max(np.abs(out["grad"])))))}
+        if grid is not None and cpu is not None:
+            # the CPU never runs the grid: its time is EXTRAPOLATED from the one timed evaluation
+            grid["cpu_extrapolated_s"] = grid["total_evals"] / cpu["value"]
+            grid["cpu_extrapolated_note"] = ("total_evals x the timed CPU evaluation (cpu_baseline); the CPU restatement did "
+                                             "not run the 40 fits")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(N),
@@ -359,14 +388,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-GRID_WORKERS = 3
+GRID_WORKERS = 3  # resident fits in the `concurrent_fits` measurement
 
 
 def grid_workers(ncells, world):
-    """Concurrent fits per GPU: three give the best aggregate rate (-9 % per evaluation) but stretch
-    every single fit ~2.7x, so with few cells per GPU the longest fit would bound the wall time."""
+    """Concurrent fits per GPU in the grid.  The persistent factorisation kernel occupies every SM, so resident fits
+    alternate instead of filling each other's gaps (56.4 vs 56.8 evaluations/s with 1 vs 3 resident at N=8182) and
+    every extra resident fit stretches each fit: two workers when a GPU has a queue of cells (hides handle set-up /
+    teardown and the host side of the Rprop loop), one when it has only a few, so that the longest fit of the grid
+    (105 iterations, 1.9 s alone) bounds the wall time as little as possible."""
     per_gpu = ncells / max(1, world)
-    return 3 if per_gpu >= 8 else (2 if per_gpu >= 4 else 1)
+    return 2 if per_gpu >= 8 else 1
 
 
 def run_grid(G, gd, world, rank, local, barrier):
@@ -421,8 +453,7 @@ def run_grid(G, gd, world, rank, local, barrier):
                 mine.append(i)
                 r2[i] = st["R2_loo"]
 
-    # GRID_WORKERS concurrent fits per GPU (the ctypes calls release the GIL): independent fits
-    # interleave on the device and fill each other's chain-bound stretches (measured -9 % per evaluation)
+    # W concurrent fits per GPU (the ctypes calls release the GIL), see grid_workers
     threads = [threading.Thread(target=worker, args=(w,)) for w in range(W)]
     for th in threads:
         th.start()
@@ -458,6 +489,8 @@ def main():
                     help="also time the 40-fit E x tau grid sharded over the ranks (default)")
     ap.add_argument("--no-grid", dest="grid", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inproc", dest="inproc", action="store_false", default=True,
+                    help="skip the single-process multi-GPU grid (gpedm_fit_grid over all devices) at N > 1")
     args = ap.parse_args()
     try:
         if args.impl == "reference":

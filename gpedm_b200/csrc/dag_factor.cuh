@@ -43,7 +43,8 @@ constexpr int DAG_ESLAB = 16 * DG_LD;
 constexpr int DAG_E = DAG_NS * DAG_ESLAB;
 static_assert(DAG_P >= TB * DG_LD, "resident tile must fit the operand ring");
 static_assert(DAG_E >= 64 * DG_WLD + 2 * TB + 64, "diag scratch must fit the epilogue ring");
-constexpr int DAG_SMEM_BYTES = (DAG_P + DAG_E) * (int)sizeof(double);
+constexpr int DAG_BAR_OFF = (DAG_P + DAG_E) * (int)sizeof(double);  // 2 x NS mbarriers behind the data
+constexpr int DAG_SMEM_BYTES = DAG_BAR_OFF + 2 * DAG_NS * 8;
 
 static_assert(DagCfg::MT == 8 && DagCfg::NT == 4, "the triangular variants below assume 64 x 32 warp tiles");
 enum DagTaskType { DAG_DIAG = 0, DAG_POTRF = 1, DAG_TRTRI = 2, DAG_LAUUM = 3 };
@@ -69,6 +70,7 @@ struct DagArgs {
   const int4* tasks;  // {type | fit << 4, i, j, kt0 | kt1 << 10 | piece << 20 | last << 30}: k tiles [kt0, kt1) of the tile
   int ntasks;
   int* counter;       // next task to claim (zeroed per evaluation)
+  int skew;           // cycles by which warps 4..7 enter a k loop after warps 0..3 (see dag_kloop)
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -113,11 +115,63 @@ __device__ __forceinline__ void warp_wait_flag(const int* f, int lane DAG_TL(, u
 
 // Ring state shared by the k loop and the epilogue: slabs issued / consumed since the kernel started
 // (identical in every thread), so stage and mbarrier parity carry over from task to task.
+// The barriers and the stages are addressed by their 32-bit shared-window addresses, formed once per kernel: going
+// through generic pointers costs an S2R (CTA rank in the cluster) + address arithmetic + cvta on every barrier wait,
+// arrive and copy of every slab hand-off (5.7 % of the warp-stall samples of the round-2 v3 capture).
 struct DagRing {
-  uint64_t* full;
-  uint64_t* empty;
+  uint32_t base;  // shared address of the dynamic shared memory; everything else is a constant offset from it
   unsigned gi, gc;
+  __device__ __forceinline__ uint32_t full(unsigned s) const { return base + (uint32_t)DAG_BAR_OFF + 8u * s; }
+  __device__ __forceinline__ uint32_t empty(unsigned s) const { return base + (uint32_t)DAG_BAR_OFF + 8u * (DAG_NS + s); }
+  __device__ __forceinline__ uint32_t sA(unsigned s) const { return base + s * (uint32_t)(DagCfg::SLAB_A * 8); }
+  __device__ __forceinline__ uint32_t sB(unsigned s) const { return base + (uint32_t)(DAG_NS * DagCfg::SLAB_A * 8) + s * (uint32_t)(DagCfg::SLAB_B * 8); }
+  __device__ __forceinline__ uint32_t sE(unsigned s) const { return base + (uint32_t)(DAG_P * 8) + s * (uint32_t)(DAG_ESLAB * 8); }
 };
+__device__ __forceinline__ void mbar_init_s(uint32_t a, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t a, unsigned parity) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @!p bra WAIT_%=;\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t a) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_cp_async_arrive_s(uint32_t a) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(a) : "memory");
+}
+// load_slab (dgemm_tile.cuh) with the destination given as a shared address
+template <class Cfg, bool KMAJOR, int ROWS>
+__device__ __forceinline__ void load_slab_s(uint32_t s, const double* __restrict__ g, size_t ld, int k0, int tid) {
+  constexpr int CHUNKS = ROWS * Cfg::BK / 2;  // 16-byte chunks per slab
+  static_assert(CHUNKS % Cfg::THREADS == 0, "whole rounds of copies");
+  constexpr int ITERS = CHUNKS / Cfg::THREADS;
+#pragma unroll
+  for (int r = 0; r < ITERS; ++r) {
+    const int chunk = tid + r * Cfg::THREADS;
+    uint32_t dst;
+    const double* src;
+    if (!KMAJOR) {  // global: BK columns (k) of ROWS contiguous doubles
+      constexpr int CPR = ROWS / 2;
+      const int row = chunk / CPR, c2 = (chunk % CPR) << 1;
+      dst = s + (uint32_t)(row * (ROWS + 4) + c2) * 8u;
+      src = g + (size_t)(k0 + row) * ld + c2;
+    } else {  // global: ROWS columns (m) of BK contiguous doubles (k)
+      constexpr int CPR = Cfg::BK / 2;
+      const int row = chunk / CPR, c2 = (chunk % CPR) << 1;
+      dst = s + (uint32_t)(row * Cfg::LD_K + c2) * 8u;
+      src = g + (size_t)row * ld + k0 + c2;
+    }
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+  }
+}
 
 // The k loop of one task: acc (+)= (+/-) sum over `nkt` 128-wide k tiles of A B, operands streamed through the
 // mbarrier ring (see gemm_tile_mb in dgemm_tile.cuh).  A is MN-major; B is MN-major (Cholesky) or K-major
@@ -129,8 +183,8 @@ struct DagRing {
 template <bool A_KMAJOR, bool B_KMAJOR, bool TRI = false>
 __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][2], DagRing& ring, double* sA, double* sB,
                                           const double* __restrict__ Ap, const double* __restrict__ Bp, size_t ld,
-                                          int nkt, const int* fa, int fsa, const int* fb, int fsb, bool active, unsigned sgn,
-                                          int tid, int m0, int n0 DAG_TL(, unsigned long long& tl_wait, int tl_col = -1)) {
+                                          int nkt, const int* fa, int fsa, const int* fb, int fsb, bool active,
+                                          int tid, int m0, int n0, int skew DAG_TL(, unsigned long long& tl_wait, int tl_col = -1)) {
   using Cfg = DagCfg;
   constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, PREF = NS - 2;
   constexpr int SLAB_A = Cfg::SLAB_A, SLAB_B = Cfg::SLAB_B;
@@ -158,13 +212,19 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
   }
   nready = nready < nkt ? nready : nkt;
   __syncwarp();  // the other lanes' acquires order every lane's later operand reads
+  // Warps w and w + 4 share a sub-partition's DMMA pipe and consume the same slabs at the same rate: entering the
+  // loop together, they would also leave every slab together and the pipe would idle while BOTH run the slab
+  // hand-off (barrier waits, address arithmetic, the copies of the next slab).  Half a slab of offset lets one warp
+  // keep the pipe busy through the other's hand-off.
+  // (the offset is taken after the first slabs have been issued: a slab lands only when ALL threads have issued
+  // their share of it)
   const int nk = nkt * SPT;
   auto issue = [&](int j) {  // copy slab j of this task into ring stage gi % NS
-    const int s = ring.gi % NS, r = ring.gi / NS;
-    if (r > 0) mbar_wait(&ring.empty[s], (unsigned)((r - 1) & 1));
-    load_slab<Cfg, A_KMAJOR, Cfg::TM>(sA + s * SLAB_A, Ap, ld, j * BK, tid);
-    load_slab<Cfg, B_KMAJOR, Cfg::TN>(sB + s * SLAB_B, Bp, ld, j * BK, tid);
-    mbar_cp_async_arrive(&ring.full[s]);
+    const unsigned s = ring.gi % NS, r = ring.gi / NS;
+    if (r > 0) mbar_wait_s(ring.empty(s), (r - 1) & 1u);
+    load_slab_s<Cfg, A_KMAJOR, Cfg::TM>(ring.sA(s), Ap, ld, j * BK, tid);
+    load_slab_s<Cfg, B_KMAJOR, Cfg::TN>(ring.sB(s), Bp, ld, j * BK, tid);
+    mbar_cp_async_arrive_s(ring.full(s));
     ring.gi++;
   };
   // Slabs are issued PREF ahead of the one being consumed.  The first slab of a k tile that is not yet known to be
@@ -174,6 +234,12 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
   int issued = 0, ready_slabs = nready * SPT;
   for (int kt = 0; kt < nk; ++kt) {
     const int want = kt + PREF + 1 < nk ? kt + PREF + 1 : nk;
+    if (want <= ready_slabs) {  // steady state: every slab up to `want` is known to be final, no flag traffic
+      while (issued < want) {
+        issue(issued);
+        ++issued;
+      }
+    }
     while (issued < want) {
       if (issued >= ready_slabs) {
         const int ktile = issued / SPT;
@@ -192,8 +258,13 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
       issue(issued);
       ++issued;
     }
-    const int s = ring.gc % NS;
-    mbar_wait(&ring.full[s], (unsigned)((ring.gc / NS) & 1));
+    if (kt == 0 && skew > 0 && (tid & 128)) {
+      const long long c0 = clock64();
+      while (clock64() - c0 < skew) {
+      }
+    }
+    const unsigned s = ring.gc % NS;
+    mbar_wait_s(ring.full(s), (ring.gc / NS) & 1u);
     DAG_TL(if (tl_col >= 0 && kt >= nk - SPT) tl_mark(tl_now(), 21 + (kt - (nk - SPT)), tl_col);)
     if (active) {
       const double* a_s = sA + s * SLAB_A;
@@ -203,7 +274,7 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
         double av[MT], bv[NT];
 #pragma unroll
         for (int i = 0; i < MT; ++i)
-          av[i] = flip_sign(A_KMAJOR ? a_s[(m0 + 8 * i + g) * LD_K + k4 * 4 + t] : a_s[(k4 * 4 + t) * LD_A + m0 + 8 * i + g], sgn);
+          av[i] = A_KMAJOR ? a_s[(m0 + 8 * i + g) * LD_K + k4 * 4 + t] : a_s[(k4 * 4 + t) * LD_A + m0 + 8 * i + g];
 #pragma unroll
         for (int j = 0; j < NT; ++j)
           bv[j] = B_KMAJOR ? b_s[(n0 + 8 * j + g) * LD_K + k4 * 4 + t] : b_s[(k4 * 4 + t) * LD_B + n0 + 8 * j + g];
@@ -228,17 +299,22 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.empty[s]);
+    if (lane == 0) mbar_arrive_s(ring.empty(s));
     ring.gc++;
   }
 }
 
 __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArgs a) {
-  extern __shared__ double smem[];
+  extern __shared__ double smem_raw[];
+  // The shared-window address of a CTA carries its rank in the cluster; left to itself the compiler re-derives it
+  // (S2R SR_CgaCtaId + arithmetic) at every use under this kernel's register pressure.  One opaque register
+  // instead; the generic pointer for ordinary loads / stores is formed from it (and inferred back to shared).
+  uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  asm volatile("" : "+r"(smem_base));
+  double* const smem = (double*)__cvta_shared_to_generic(smem_base);
   using Cfg = DagCfg;
   constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, PREF = NS - 2;
   constexpr int SLAB_A = Cfg::SLAB_A;
-  __shared__ uint64_t full_bar[NS], empty_bar[NS];
   __shared__ int s_task;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -262,12 +338,12 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full_bar[s], DAG_THREADS);
-      mbar_init(&empty_bar[s], DAG_THREADS / 32);
+      mbar_init_s(smem_base + (uint32_t)DAG_BAR_OFF + 8u * s, DAG_THREADS);
+      mbar_init_s(smem_base + (uint32_t)DAG_BAR_OFF + 8u * (NS + s), DAG_THREADS / 32);
     }
   }
   __syncthreads();
-  DagRing ring{full_bar, empty_bar, 0u, 0u};
+  DagRing ring{smem_base, 0u, 0u};
   int* counter = a.counter;
 
   for (;;) {
@@ -332,7 +408,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
           for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
       }
       dag_kloop<true, true>(acc, ring, sA, sB, LAp, LBp, ld, kt1 - kt0, flagX + r0 * nb + ti, nb, flagX + r0 * nb + tj, nb, act,
-                            0u, tid, m0, n0 DAG_TL(, tl_wait));
+                            tid, m0, n0, a.skew DAG_TL(, tl_wait));
       if (act) {
 #pragma unroll
         for (int i = 0; i < MT; ++i)
@@ -397,7 +473,12 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
 #pragma unroll
         for (int j = 0; j < NT; ++j)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) acc[i][j][e] = __ldcg(Cin + (size_t)(km0 + 8 * i + g) + (size_t)(kn0 + 8 * j + 2 * t + e) * ld);
+          for (int e = 0; e < 2; ++e) {
+            // Cholesky tasks accumulate the NEGATED tile, -(A - sum L L^T) = -A + sum L L^T, so that the k loop needs
+            // no sign flips on its fragments; negation commutes with rounding, so the bits are those of A - sum L L^T
+            const double v = __ldcg(Cin + (size_t)(km0 + 8 * i + g) + (size_t)(kn0 + 8 * j + 2 * t + e) * ld);
+            acc[i][j][e] = is_trtri ? v : -v;
+          }
     } else {
 #pragma unroll
       for (int i = 0; i < MT; ++i)
@@ -405,11 +486,20 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     }
     if (type == DAG_DIAG)
-      dag_kloop<false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, 0x80000000u, tid, km0, kn0 DAG_TL(, tl_wait, last ? tj : -1));
+      dag_kloop<false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, tid, km0, kn0, a.skew DAG_TL(, tl_wait, last ? tj : -1));
     else if (!is_trtri)
-      dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, 0x80000000u, tid, km0, kn0 DAG_TL(, tl_wait));
+      dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, a.skew DAG_TL(, tl_wait));
     else
-      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, 0u, tid, km0, kn0 DAG_TL(, tl_wait));
+      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, a.skew DAG_TL(, tl_wait));
+    if (!is_trtri) {
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          acc[i][j][0] = -acc[i][j][0];
+          acc[i][j][1] = -acc[i][j][1];
+        }
+    }
     if (!last) {
       // ---------------- non-final piece: leave the partial result, publish the piece count
       if (active) {
@@ -529,10 +619,10 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
     warp_wait_flag(flagX + dblk * nb + dblk, lane DAG_TL(, tl_wait));
     DAG_TL(if (!is_trtri && ti == tj + 1) tl_mark(tl_now(), 11, tj);)
     auto issue_e = [&](int j) {
-      const int s = ring.gi % NS, r = ring.gi / NS;
-      if (r > 0) mbar_wait(&ring.empty[s], (unsigned)((r - 1) & 1));
-      load_slab<Cfg, false, TB>(sE + s * DAG_ESLAB, Dg, ld, j * BK, tid);
-      mbar_cp_async_arrive(&ring.full[s]);
+      const unsigned s = ring.gi % NS, r = ring.gi / NS;
+      if (r > 0) mbar_wait_s(ring.empty(s), (r - 1) & 1u);
+      load_slab_s<Cfg, false, TB>(ring.sE(s), Dg, ld, j * BK, tid);
+      mbar_cp_async_arrive_s(ring.full(s));
       ring.gi++;
     };
     constexpr int NKE = TB / BK;
@@ -544,8 +634,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     for (int kt = 0; kt < NKE; ++kt) {
       if (kt + PREF < NKE) issue_e(kt + PREF);
-      const int s = ring.gc % NS;
-      mbar_wait(&ring.full[s], (unsigned)((ring.gc / NS) & 1));
+      const unsigned s = ring.gc % NS;
+      mbar_wait_s(ring.full(s), (ring.gc / NS) & 1u);
       const double* e_s = sE + s * DAG_ESLAB;
       // D is lower triangular: D[r][k] = 0 for k > r.  The DMMAs whose D fragment is identically zero are skipped
       // with warp-uniform jumps into a fall-through switch (a predicated-off DMMA would still cost its pipe slot).
@@ -561,7 +651,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
           const int imin = kk - em0 > 0 ? (kk - em0) >> 3 : 0;  // row blocks i < imin: 8 i + 7 + em0 < kk
           if (imin >= MT) continue;
 #pragma unroll
-          for (int i = 0; i < MT; ++i) av[i] = flip_sign(e_s[(k4 * 4 + t) * DG_LD + em0 + 8 * i + g], 0x80000000u);
+          for (int i = 0; i < MT; ++i) av[i] = e_s[(k4 * 4 + t) * DG_LD + em0 + 8 * i + g];
 #pragma unroll
           for (int j = 0; j < NT; ++j) bv[j] = T[(en0 + 8 * j + g) * DG_LD + kk + t];
           switch (imin) {
@@ -592,7 +682,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
 #undef DAG_ROW
 #undef DAG_COL
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ring.empty[s]);
+      if (lane == 0) mbar_arrive_s(ring.empty(s));
       ring.gc++;
     }
     DAG_TL(if (!is_trtri && ti == tj + 1) tl_mark(tl_now(), 12, tj);)
@@ -601,7 +691,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
 #pragma unroll
       for (int j = 0; j < NT; ++j)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) Cg[(size_t)(em0 + 8 * i + g) + (size_t)(en0 + 8 * j + 2 * t + e) * ld] = acc[i][j][e];
+        for (int e = 0; e < 2; ++e)  // TRTRI: X_ij = -(D_i T), the sign applied here instead of on every D fragment
+          Cg[(size_t)(em0 + 8 * i + g) + (size_t)(en0 + 8 * j + 2 * t + e) * ld] = is_trtri ? -acc[i][j][e] : acc[i][j][e];
     __syncthreads();  // all stores of the tile issued; T is free again for the next task's ring
     if (tid == 0) {
       __threadfence();

@@ -277,7 +277,12 @@ static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_
 // factorisation kernel over the interleaved task lists of all fits, the two triangular matrix-vector
 // products, the trace terms, the scalar reductions - and the scalar Rprop logic of fmingrad_Rprop
 // (reference R/GPfunctions.R:522-584) runs on the host per fit exactly as in gpedm_fit_rprop.
-static const int g_mid_max_n = getenv("GPEDM_MID_MAX_N") ? atoi(getenv("GPEDM_MID_MAX_N")) : 1024;
+// Upper size of the lockstep path.  Measured aggregate evaluations/s of a batch, lockstep vs one fit per worker thread
+// (12..48 fits, tools/mid_batch_bench.py): N ~ 1500 3852 vs 1837, 2050 2042 vs 917, 3000 903 vs 560, 4100 403 vs 265,
+// 5000 223 vs 173, 6150 127 vs 123, 8190 58 vs 58 - above ~6000 rows one fit fills the GPU and lockstep only costs memory.
+static const int g_mid_max_n = getenv("GPEDM_MID_MAX_N") ? atoi(getenv("GPEDM_MID_MAX_N")) : 6144;
+// fits per interleaved group of the lockstep task list (0: all active fits, see fit_batch_mid)
+static const int g_mid_group = getenv("GPEDM_MID_GROUP") ? atoi(getenv("GPEDM_MID_GROUP")) : 0;
 static const bool g_no_mid_batch = getenv("GPEDM_NO_MID_BATCH") != nullptr && atoi(getenv("GPEDM_NO_MID_BATCH")) != 0;
 
 static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fit_desc* descs,
@@ -479,11 +484,19 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
     mapTS.clear();
     mapT.clear();
     mapV.clear();
-    size_t maxlen = 0;
-    for (int q : active) maxlen = std::max(maxlen, ftasks[q].size());
-    for (size_t pos = 0; pos < maxlen; ++pos)
-      for (int q : active)
-        if (pos < ftasks[q].size()) tasks.push_back(ftasks[q][pos]);
+    // Task lists are interleaved position by position, so that a CTA which would wait for one fit's Cholesky chain
+    // holds another fit's tile instead.  (GPEDM_MID_GROUP = G interleaves only G fits at a time, group after group;
+    // measured on 12..24 fits of 3000..6150 rows, G = 1 / 2 / 3 / all: 493 / 714 / 862 / 903 evaluations/s at N ~ 3000,
+    // 115 / 125 / 126 / 127 at N ~ 6150 - more fits per group never hurt, so the default is all of them.)
+    for (size_t b = 0; b < active.size();) {
+      const size_t e3 = g_mid_group > 0 ? std::min(active.size(), b + (size_t)g_mid_group) : active.size();
+      size_t maxlen = 0;
+      for (size_t a2 = b; a2 < e3; ++a2) maxlen = std::max(maxlen, ftasks[active[a2]].size());
+      for (size_t pos = 0; pos < maxlen; ++pos)
+        for (size_t a2 = b; a2 < e3; ++a2)
+          if (pos < ftasks[active[a2]].size()) tasks.push_back(ftasks[active[a2]][pos]);
+      b = e3;
+    }
     for (int q : active) {
       const Lay& L = lay[q];
       for (int b = 0; b < L.ntiles * L.split; ++b) mapTS.push_back(make_int2(q, b));
@@ -510,6 +523,7 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
     da.tasks = (const int4*)dTasks.p;
     da.ntasks = (int)tasks.size();
     da.counter = (int*)(base + counter_off);
+    da.skew = g_dag_skew;
     dag_factor_kernel<<<std::min(sms, da.ntasks), DAG_THREADS, DAG_SMEM_BYTES, st>>>(da);
     mid_trmv_n_kernel<<<(unsigned)mapT.size(), 256, 0, st>>>(F, (const int2*)dMapT.p);
     mid_reduce_kernel<<<(unsigned)mapV.size(), 256, 0, st>>>(F, (const int2*)dMapV.p, 0);
@@ -653,21 +667,24 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
   return 0;
 }
 
-// Concurrent fits per GPU.  Independent fits interleave on one device and fill each other's
-// chain-bound stretches: measured at N ~ 8190 (8 grid cells, one B200) 20.18 ms per evaluation with one
-// worker, 18.73 with two, 18.37 with three; memory is 3 N^2 doubles per resident fit.
-// Three concurrent fits stretch every single fit ~2.7x, so with few fits per GPU (the 40-cell grid on 8
-// GPUs) the longest fit would bound the wall time: fewer workers then.
+// Concurrent fits per GPU for the fits that go through one handle each (everything above the lockstep sizes, and
+// single fits).  The persistent factorisation kernel occupies every SM, so two resident fits no longer fill each
+// other's chain-bound stretches - their factorisations simply alternate (N ~ 8190: 56.4 evaluations/s one at a time,
+// 56.8 with three resident) - and every extra resident fit stretches each fit's own duration, which is what bounds
+// a grid spread over several GPUs.  Two workers hide handle creation / teardown and the host side of the Rprop
+// loop when a GPU has a queue of fits; one when it has only a few.
 static int default_workers_per_gpu(int64_t nmax, int nfits, int ngpus) {
   if (g_batch_workers > 0) return g_batch_workers;
-  // The smaller the fits, the less of the GPU one evaluation fills and the more of them interleave
-  // (measured aggregate evaluations/s on one B200, `tools/mid_batch_bench.py`: N~325: 2.3 k with one
-  // worker, 6.4 k with 3, 10.8 k with 12; N~1025: 2.9 k with 3, 4.2 k with 8; N~2040: 1.76 k with 6;
-  // N~4090: 279 with 3, 338 with 5; N~8190: 49.6 / 53.4 / 54.4 with 1 / 2 / 3).
-  int w = nmax <= 640 ? 12 : nmax <= 1536 ? 8 : nmax <= 3072 ? 6 : nmax <= 6144 ? 5 : nmax <= 12288 ? 3 : nmax <= 24576 ? 2 : 1;
-  if (nmax > 6144) {  // large fits: also bound the stretch of the longest fit (see above)
+  int w;
+  if (nmax > 6144) {
     const double per_gpu = (double)nfits / std::max(1, ngpus);
-    w = std::min(w, per_gpu >= 8 ? 3 : (per_gpu >= 4 ? 2 : 1));
+    w = per_gpu >= 8 ? 2 : 1;
+  } else {
+    // Smaller fits that still come through one handle each (gpedm_fit_grid cells, a single mid-size fit next to larger
+    // ones): the evaluation is a dozen launches around a chain-bound factorisation and several of them interleave
+    // (measured aggregate evaluations/s on one B200, tools/mid_batch_bench.py with GPEDM_NO_MID_BATCH=1: N ~ 325 2.3 k
+    // with one worker, 16.5 k with 12; N ~ 1000 4.5 k with 8; N ~ 2050 0.9 k with 6; N ~ 4100 265 with 5).
+    w = nmax <= 640 ? 12 : nmax <= 1536 ? 8 : nmax <= 3072 ? 6 : 5;
   }
   return std::max(1, std::min(w, nfits));
 }

@@ -65,6 +65,18 @@ for k in range(4):
     msk = typ == k
     print("  %-6s %5d tasks, mean %.1f us, max %.1f us, waiting %.1f%% of residency" % (names[k], msk.sum(), (en - st)[msk].mean(), (en - st)[msk].max(),
           100 * wait[msk].sum() / max(1e-9, (en - st)[msk].sum())))
+# per-task cost model: duration = a + b * (k tiles) over the tasks that never waited for a flag; b is the k loop's
+# time per 128^3 k tile (17.5 us = the DMMA pipe's 2048 m8n8k4 per sub-partition at 16.05 cycles, 1.965 GHz),
+# a what a task costs around its k loop (claim, flag scan, accumulator load, pipeline fill, epilogue, store, flag)
+print("\ntask cost model over tasks that did not wait (least squares): us per task + us per k tile")
+for k in range(4):
+    msk = (typ == k) & (wait < 0.5) & final_piece & (nkt > 0)
+    if msk.sum() > 8:
+        A = np.stack([np.ones(msk.sum()), nkt[msk].astype(float)], axis=1)
+        coef, *_ = np.linalg.lstsq(A, (en - st)[msk], rcond=None)
+        resid = (en - st)[msk] - A @ coef
+        print("  %-6s %5d tasks: %6.2f us + %6.3f us x k tiles (rms residual %.1f us); sum a = %.1f SM-ms, sum b k = %.1f SM-ms"
+              % (names[k], msk.sum(), coef[0], coef[1], np.sqrt((resid ** 2).mean()), coef[0] * (typ == k).sum() * 1e-3, coef[1] * nkt[typ == k].sum() * 1e-3))
 d = np.where((typ == 0) & final_piece)[0]
 order = d[np.argsort(tj[d])]
 ends = en[order]
