@@ -300,10 +300,13 @@ def run_ours(args):
             barrier()
             if rank == 0:
                 from gpedm_b200 import batch, synth
-                ti0 = time.perf_counter()
-                cells = batch.fit_grid(synth.ricker(SERIES_LEN, SEED), range(1, 11), (1, 2, 3, 4), ngpus=world)
-                ti = time.perf_counter() - ti0
-                grid["inproc"] = {"api": "gpedm_fit_grid(ngpus=%d) in one process" % world, "wall_s": ti,
+                tis = []
+                for _ in range(2):  # the first call pays context creation, NCCL init and memory-pool growth on the other devices
+                    ti0 = time.perf_counter()
+                    cells = batch.fit_grid(synth.ricker(SERIES_LEN, SEED), range(1, 11), (1, 2, 3, 4), ngpus=world)
+                    tis.append(time.perf_counter() - ti0)
+                ti = tis[1]
+                grid["inproc"] = {"api": "gpedm_fit_grid(ngpus=%d) in one process" % world, "wall_s": ti, "first_call_s": tis[0],
                                   "evals_per_sec": sum(c["nevals"] for c in cells) / ti,
                                   "status_ok": all(c["status"] == 0 for c in cells),
                                   "iters_equal_torchrun_grid": [int(c["iter"]) for c in cells] == grid["iters"],

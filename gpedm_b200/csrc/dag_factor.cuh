@@ -70,7 +70,6 @@ struct DagArgs {
   const int4* tasks;  // {type | fit << 4, i, j, kt0 | kt1 << 10 | piece << 20 | last << 30}: k tiles [kt0, kt1) of the tile
   int ntasks;
   int* counter;       // next task to claim (zeroed per evaluation)
-  int skew;           // cycles by which warps 4..7 enter a k loop after warps 0..3 (see dag_kloop)
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -184,7 +183,7 @@ template <bool A_KMAJOR, bool B_KMAJOR, bool TRI = false>
 __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][2], DagRing& ring, double* sA, double* sB,
                                           const double* __restrict__ Ap, const double* __restrict__ Bp, size_t ld,
                                           int nkt, const int* fa, int fsa, const int* fb, int fsb, bool active,
-                                          int tid, int m0, int n0, int skew DAG_TL(, unsigned long long& tl_wait, int tl_col = -1)) {
+                                          int tid, int m0, int n0 DAG_TL(, unsigned long long& tl_wait, int tl_col = -1)) {
   using Cfg = DagCfg;
   constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, PREF = NS - 2;
   constexpr int SLAB_A = Cfg::SLAB_A, SLAB_B = Cfg::SLAB_B;
@@ -212,12 +211,6 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
   }
   nready = nready < nkt ? nready : nkt;
   __syncwarp();  // the other lanes' acquires order every lane's later operand reads
-  // Warps w and w + 4 share a sub-partition's DMMA pipe and consume the same slabs at the same rate: entering the
-  // loop together, they would also leave every slab together and the pipe would idle while BOTH run the slab
-  // hand-off (barrier waits, address arithmetic, the copies of the next slab).  Half a slab of offset lets one warp
-  // keep the pipe busy through the other's hand-off.
-  // (the offset is taken after the first slabs have been issued: a slab lands only when ALL threads have issued
-  // their share of it)
   const int nk = nkt * SPT;
   auto issue = [&](int j) {  // copy slab j of this task into ring stage gi % NS
     const unsigned s = ring.gi % NS, r = ring.gi / NS;
@@ -257,11 +250,6 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
       }
       issue(issued);
       ++issued;
-    }
-    if (kt == 0 && skew > 0 && (tid & 128)) {
-      const long long c0 = clock64();
-      while (clock64() - c0 < skew) {
-      }
     }
     const unsigned s = ring.gc % NS;
     mbar_wait_s(ring.full(s), (ring.gc / NS) & 1u);
@@ -363,6 +351,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
     const int kt0 = tk.w & 1023, kt1 = (tk.w >> 10) & 1023, piece = (tk.w >> 20) & 1023;
     const bool last = (tk.w >> 30) & 1;
     DAG_TL(const unsigned long long tl_t0 = tl_now(); unsigned long long tl_wait = 0;)
+    // phase marks of every 4th task (30 k loop entered, 31 k loop left, 32 resident tile in smem, 33 epilogue product done)
+    DAG_TL(const bool tl_ph = (tix & 3) == 0;)
 
     // ---------------- operands of the k loop
     const double* Ap;
@@ -407,8 +397,10 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
 #pragma unroll
           for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
       }
+      DAG_TL(if (tl_ph) tl_mark(tl_now(), 30, type);)
       dag_kloop<true, true>(acc, ring, sA, sB, LAp, LBp, ld, kt1 - kt0, flagX + r0 * nb + ti, nb, flagX + r0 * nb + tj, nb, act,
-                            tid, m0, n0, a.skew DAG_TL(, tl_wait));
+                            tid, m0, n0 DAG_TL(, tl_wait));
+      DAG_TL(if (tl_ph) tl_mark(tl_now(), 31, type);)
       if (act) {
 #pragma unroll
         for (int i = 0; i < MT; ++i)
@@ -485,13 +477,15 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
 #pragma unroll
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     }
+    DAG_TL(if (tl_ph) tl_mark(tl_now(), 30, type);)
     if (type == DAG_DIAG)
-      dag_kloop<false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, tid, km0, kn0, a.skew DAG_TL(, tl_wait, last ? tj : -1));
+      dag_kloop<false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, tid, km0, kn0 DAG_TL(, tl_wait, last ? tj : -1));
     else if (!is_trtri)
-      dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, a.skew DAG_TL(, tl_wait));
+      dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0 DAG_TL(, tl_wait));
     else
-      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, a.skew DAG_TL(, tl_wait));
-    if (!is_trtri) {
+      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0 DAG_TL(, tl_wait));
+    DAG_TL(if (tl_ph) tl_mark(tl_now(), 31, type);)
+    if (!is_trtri) {  // back from the negated accumulation
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -527,6 +521,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
 #pragma unroll
         for (int e = 0; e < 2; ++e) T[(km0 + 8 * i + g) + (kn0 + 8 * j + 2 * t + e) * DG_LD] = acc[i][j][e];
     __syncthreads();
+    DAG_TL(if (tl_ph) tl_mark(tl_now(), 32, type);)
 
     if (type == DAG_DIAG) {
       // ---------------- in-CTA Cholesky + inverse of the diagonal block (diag_block.cuh)
@@ -686,6 +681,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       ring.gc++;
     }
     DAG_TL(if (!is_trtri && ti == tj + 1) tl_mark(tl_now(), 12, tj);)
+    DAG_TL(if (tl_ph) tl_mark(tl_now(), 33, type);)
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll

@@ -81,8 +81,6 @@ static const bool g_no_dag = getenv("GPEDM_NO_DAG") != nullptr && atoi(getenv("G
 static const int g_dag_lead = getenv("GPEDM_DAG_LEAD") ? std::max(0, atoi(getenv("GPEDM_DAG_LEAD"))) : 1;
 // k tiles per piece of a long tile (512 = never split)
 static const int g_dag_chunk = getenv("GPEDM_DAG_CHUNK") ? std::min(512, std::max(1, atoi(getenv("GPEDM_DAG_CHUNK")))) : 512;
-// cycles by which warps 4..7 enter a k loop of the persistent kernel after warps 0..3 (dag_kloop)
-static const int g_dag_skew = getenv("GPEDM_DAG_SKEW") ? std::max(0, atoi(getenv("GPEDM_DAG_SKEW"))) : 0;
 static const int g_dag_lag = getenv("GPEDM_DAG_LAG") ? std::max(1, atoi(getenv("GPEDM_DAG_LAG"))) : 2;
 // Sigma^-1 = X^T X tiles summed in pieces of this many block rows, interleaved with the factorisation (0 = whole
 // tiles after it, the default: interleaved pieces were measured SLOWER at every size - 4086 rows 3.38 -> 3.66 ms

@@ -77,6 +77,41 @@ for k in range(4):
         resid = (en - st)[msk] - A @ coef
         print("  %-6s %5d tasks: %6.2f us + %6.3f us x k tiles (rms residual %.1f us); sum a = %.1f SM-ms, sum b k = %.1f SM-ms"
               % (names[k], msk.sum(), coef[0], coef[1], np.sqrt((resid ** 2).mean()), coef[0] * (typ == k).sum() * 1e-3, coef[1] * nkt[typ == k].sum() * 1e-3))
+# phase marks (every 4th task, thread 0): 30 k loop entered, 31 k loop left, 32 resident tile in smem, 33 epilogue
+# product done; matched to the task record of the same SM that encloses them
+pm = marks[((marks[:, 3] >> 8) & 0xff) >= 30]
+if len(pm):
+    ph = {}
+    by_sm = {}
+    for q in range(len(rec)):
+        by_sm.setdefault(int(sm[q]), []).append(q)
+    for sid in by_sm:
+        by_sm[sid].sort(key=lambda q: st[q])
+    starts = {sid: np.array([st[q] for q in qs]) for sid, qs in by_sm.items()}
+    for tm, _, sid, cd in pm:
+        sid = int(sid)
+        tt = (tm - t0) * 1e-3
+        pos = int(np.searchsorted(starts[sid], tt, side="right")) - 1
+        if pos >= 0:
+            q = by_sm[sid][pos]
+            if tt <= en[q] + 1e-6:
+                ph.setdefault(q, {})[int((cd >> 8) & 0xff)] = tt
+    print("\ntask phases (us, median over the sampled tasks that did not wait for flags; k loop per k tile):")
+    print("  %-6s %6s %9s %12s %10s %10s %12s" % ("type", "tasks", "prologue", "k loop/tile", "T -> smem", "epilogue", "store+flag"))
+    for k in range(4):
+        rows = [(q, v) for q, v in ph.items() if typ[q] == k and wait[q] < 0.5 and final_piece[q] and nkt[q] > 0 and 30 in v and 31 in v]
+        if not rows:
+            continue
+        pro = np.median([v[30] - st[q] for q, v in rows])
+        kl = np.median([(v[31] - v[30]) / nkt[q] for q, v in rows])
+        if k == 3:
+            print("  %-6s %6d %9.2f %12.3f %10s %10s %12.2f" % (names[k], len(rows), pro, kl, "-", "-", np.median([en[q] - v[31] for q, v in rows])))
+        elif k == 0:
+            print("  %-6s %6d %9.2f %12.3f %10.2f %10s %12s" % (names[k], len(rows), pro, kl, np.median([v[32] - v[31] for q, v in rows if 32 in v]), "(chain)", "(chain)"))
+        else:
+            r2 = [(q, v) for q, v in rows if 32 in v and 33 in v]
+            print("  %-6s %6d %9.2f %12.3f %10.2f %10.2f %12.2f" % (names[k], len(rows), pro, kl, np.median([v[32] - v[31] for q, v in r2]),
+                  np.median([v[33] - v[32] for q, v in r2]), np.median([en[q] - v[33] for q, v in r2])))
 d = np.where((typ == 0) & final_piece)[0]
 order = d[np.argsort(tj[d])]
 ends = en[order]
@@ -90,7 +125,7 @@ print("chain step: median %.1f us, mean %.1f, max %.1f; last D ready at %.1f us 
 # ---- chain marks (thread 0 of the two chain tasks of each block column)
 if len(marks):
     mk = {}
-    for tm, _, _, cd in marks:
+    for tm, _, _, cd in marks[((marks[:, 3] >> 8) & 0xff) < 30]:
         mk[(int((cd >> 20) & 0xfff), int((cd >> 8) & 0xff))] = (tm - t0) * 1e-3
     names_m = [("hop: D_c flag -> seen by POTRF(c+1,c)", (5, 0), (11, 0)), ("POTRF epilogue T D^T", (11, 0), (12, 0)),
                ("POTRF store + fence + flag", (12, 0), (13, 0)), ("  flag of L(c+1,c) seen by DIAG(c+1) warp 0", (13, 0), (20, 1)), ("  first slab of the last k tile landed", (20, 1), (21, 1)),
