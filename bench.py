@@ -297,23 +297,31 @@ def run_ours(args):
             # thread per GPU on a shared cost-ordered queue, the series uploaded once per GPU, result records
             # cross-checked by the library's own ncclAllGather).  Rank 0 runs it over all `world` devices while the
             # other ranks wait at the barrier with their GPUs idle.
+            # (the other ranks wait on a key of the process-group store, i.e. on the CPU: a NCCL barrier would keep a
+            # spinning kernel resident on their GPUs, and kernels of two processes time-slice on a device)
             barrier()
+            store = dist.distributed_c10d._get_default_store()
             if rank == 0:
-                from gpedm_b200 import batch, synth
-                tis = []
-                for _ in range(2):  # the first call pays context creation, NCCL init and memory-pool growth on the other devices
-                    ti0 = time.perf_counter()
-                    cells = batch.fit_grid(synth.ricker(SERIES_LEN, SEED), range(1, 11), (1, 2, 3, 4), ngpus=world)
-                    tis.append(time.perf_counter() - ti0)
-                ti = tis[1]
-                grid["inproc"] = {"api": "gpedm_fit_grid(ngpus=%d) in one process" % world, "wall_s": ti, "first_call_s": tis[0],
-                                  "evals_per_sec": sum(c["nevals"] for c in cells) / ti,
-                                  "status_ok": all(c["status"] == 0 for c in cells),
-                                  "iters_equal_torchrun_grid": [int(c["iter"]) for c in cells] == grid["iters"],
-                                  "nccl_gather_status": int(_lib.lib().gpedm_last_gather_status()),
-                                  "nccl_gather_status_note": "0 = the library's ncclAllGather of the records ran and matched "
-                                                             "the host-delivered records; <0 = NCCL unavailable (records "
-                                                             "delivered from host memory)"}
+                try:
+                    from gpedm_b200 import batch, synth
+                    tis = []
+                    for _ in range(2):  # the first call pays context creation, NCCL init and memory-pool growth on the other devices
+                        ti0 = time.perf_counter()
+                        cells = batch.fit_grid(synth.ricker(SERIES_LEN, SEED), range(1, 11), (1, 2, 3, 4), ngpus=world)
+                        tis.append(time.perf_counter() - ti0)
+                    ti = tis[1]
+                    grid["inproc"] = {"api": "gpedm_fit_grid(ngpus=%d) in one process" % world, "wall_s": ti, "first_call_s": tis[0],
+                                      "evals_per_sec": sum(c["nevals"] for c in cells) / ti,
+                                      "status_ok": all(c["status"] == 0 for c in cells),
+                                      "iters_equal_torchrun_grid": [int(c["iter"]) for c in cells] == grid["iters"],
+                                      "nccl_gather_status": int(_lib.lib().gpedm_last_gather_status()),
+                                      "nccl_gather_status_note": "0 = the library's ncclAllGather of the records ran and matched "
+                                                                 "the host-delivered records; <0 = NCCL unavailable (records "
+                                                                 "delivered from host memory)"}
+                finally:  # never leave the other ranks waiting
+                    store.set("gpedm_inproc_done", "1")
+            else:
+                store.wait(["gpedm_inproc_done"])
             barrier()
 
     if rank == 0:

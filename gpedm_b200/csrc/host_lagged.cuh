@@ -194,6 +194,113 @@ static void default_initparst(int d, double* t) {
   t[d + 2] = logit3(0.5, 0.0, 1.0);
 }
 
+// Grid on a series short enough for the lockstep batch (every cell has at most GPEDM_MID_MAX_N rows): the cells are
+// prepared on the device as always (lags, scaling, complete rows - create_from_series on the first GPU), their training
+// sets (a few hundred KB each) are handed to the batch scheduler - which advances all cells of a GPU in lockstep through
+// ONE persistent factorisation launch per Rprop round (fit_batch_mid / fit_batch_small) - and the fit statistics of
+// gpedm_get_fit_stats are reduced from the returned in-sample / leave-one-out means.
+static int fit_grid_lockstep(int64_t T, const double* y, const int32_t* pop, int32_t np, int32_t ncells, const int32_t* E,
+                             const int32_t* tau, int32_t scaling, double modeprior, int32_t ngpus, const std::vector<int>& devs,
+                             const gpedm_rprop_options* opts, gpedm_result* results, gpedm_fit_stats* stats) {
+  struct Cell {
+    std::vector<double> X, Y, center, scale, loo, ins;
+    std::vector<int32_t> pop;
+    double ip[GPEDM_MAX_P];
+    int groups = 1;
+  };
+  std::vector<Cell> cells(ncells);
+  std::vector<gpedm_fit_desc> descs(ncells);
+  {
+    LagSeries S;
+    int rc = upload_series(devs[0], T, y, pop, np, S);
+    if (rc) return rc;
+    for (int c = 0; c < ncells; ++c) {
+      gpedm_handle h = nullptr;
+      rc = create_from_series(S, E[c], tau[c], scaling, nullptr, &h);
+      if (rc) return rc;
+      Cell& C = cells[c];
+      const int64_t N = h->N;
+      const size_t nstat = (size_t)(h->d + 1) * h->sc_groups;
+      C.groups = h->sc_groups;
+      C.Y = h->hY;
+      C.pop.assign(h->hpop.begin(), h->hpop.end());
+      C.X.resize((size_t)N * h->d);
+      C.center.resize(nstat);
+      C.scale.resize(nstat);
+      C.loo.resize(N);
+      C.ins.resize(N);
+      cudaError_t e = cudaMemcpy(C.X.data(), h->dX, (size_t)N * h->d * 8, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(C.center.data(), h->dcenter, nstat * 8, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(C.scale.data(), h->dscale, nstat * 8, cudaMemcpyDeviceToHost);
+      gpedm_destroy(h);
+      if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "grid preparation failed: %s", cudaGetErrorString(e));
+      default_initparst(E[c], C.ip);
+      gpedm_fit_desc& D = descs[c];
+      memset(&D, 0, sizeof(D));
+      D.N = N;
+      D.d = E[c];
+      D.np = np;
+      D.X = C.X.data();
+      D.Y = C.Y.data();
+      D.pop = C.pop.data();
+      D.initparst = C.ip;
+      D.modeprior = modeprior;
+      D.rhofixed = NAN;
+      D.want_loo = 1;
+      D.loo_mean = C.loo.data();
+      D.insamp_mean = C.ins.data();
+    }
+  }
+  const int rc = gpedm_fit_batch_impl(ncells, descs.data(), ngpus, devs.data(), opts, results);
+  if (stats) {
+    for (int c = 0; c < ncells; ++c) {
+      gpedm_fit_stats& st = stats[c];
+      memset(&st, 0, sizeof(st));
+      if (results[c].status != 0) continue;
+      const Cell& C = cells[c];
+      const size_t N = C.Y.size();
+      const int stride = E[c] + 1;
+      auto sc = [&](size_t i, double& ctr, double& s) {  // unscaling of y (first statistic of each group), as fit_stats_kernel
+        if (scaling == GPEDM_SCALE_NONE) {
+          ctr = 0.0;
+          s = 1.0;
+        } else {
+          const int g = scaling == GPEDM_SCALE_LOCAL ? C.pop[i] : 0;
+          ctr = C.center[(size_t)stride * g];
+          s = C.scale[(size_t)stride * g];
+        }
+      };
+      double sum = 0.0;
+      for (size_t i = 0; i < N; ++i) {
+        double ctr, s;
+        sc(i, ctr, s);
+        sum += C.Y[i] * s + ctr;
+      }
+      const double mean = sum / (double)N;
+      double sst = 0.0, sin = 0.0, sloo = 0.0;
+      for (size_t i = 0; i < N; ++i) {
+        double ctr, s;
+        sc(i, ctr, s);
+        const double o = C.Y[i] * s + ctr - mean;
+        const double ri = (C.Y[i] - C.ins[i]) * s, rl = (C.Y[i] - C.loo[i]) * s;
+        sst += o * o;
+        sin += ri * ri;
+        sloo += rl * rl;
+      }
+      st.n = (double)N;
+      st.obs_mean = mean;
+      st.ss_total = sst;
+      st.ss_insample = sin;
+      st.ss_loo = sloo;
+      st.R2_insample = 1.0 - sin / sst;
+      st.R2_loo = 1.0 - sloo / sst;
+      st.rmse_insample = sqrt(sin / (double)N);
+      st.rmse_loo = sqrt(sloo / (double)N);
+    }
+  }
+  return rc;
+}
+
 static int gpedm_fit_grid_impl(int64_t T, const double* y, const int32_t* pop, int32_t np, int32_t ncells,
                                const int32_t* E, const int32_t* tau, int32_t scaling, double modeprior, int32_t ngpus,
                                const int32_t* devices, const gpedm_rprop_options* opts, gpedm_result* results,
@@ -210,6 +317,8 @@ static int gpedm_fit_grid_impl(int64_t T, const double* y, const int32_t* pop, i
   }
   for (int c = 0; c < ncells; ++c)
     if (E[c] < 1 || E[c] > GPEDM_MAX_D || tau[c] < 1) return set_err(GPEDM_ERR_ARG, "cell %d: bad E / tau", c);
+  if (T <= g_mid_max_n && ncells >= 2 && !g_no_mid_batch)
+    return fit_grid_lockstep(T, y, pop, np, ncells, E, tau, scaling, modeprior, ngpus, devs, opts, results, stats);
   // queue by descending estimated cost: N ~ T - E tau rows, d = E predictors
   std::vector<int> order(ncells);
   for (int i = 0; i < ncells; ++i) order[i] = i;

@@ -1,5 +1,5 @@
-"""Lockstep batch of mid-size fits (129 <= N <= 1024; SURVEY 8f rank 3: per-population models, pairwise fits,
-multistart, b-profiles) against the per-handle tiled path and the CPU oracle."""
+"""Lockstep batch of mid-size fits (129 <= N <= 6144; SURVEY 8f rank 3: per-population models, pairwise fits,
+multistart, b-profiles, grids on series of a few thousand points) against the per-handle tiled path and the CPU oracle."""
 import numpy as np
 import pytest
 
@@ -63,11 +63,11 @@ def test_mid_batch_matches_tiled_path_and_oracle(gpu_lib):
 
 def test_mixed_batch_small_mid_and_tiled(gpu_lib):
     """One batch with one-tile fits (one-CTA kernel), mid-size fits (lockstep tiled batch) and a fit above the
-    mid-size limit (worker-thread path): each returns what an individual fit returns."""
+    lockstep limit of 6144 rows (worker-thread path): each returns what an individual fit returns."""
     probs = []
     g, _ = batch.grid_problems(synth.ricker(110, 21), [1, 2, 3], [1])
     probs += g
-    for n, E, seed in [(300, 3, 22), (520, 4, 23), (700, 2, 24), (1300, 3, 25)]:
+    for n, E, seed in [(300, 3, 22), (520, 4, 23), (700, 2, 24), (1300, 3, 25), (6300, 2, 26)]:
         Yb, Xb = synth.embed(synth.ricker(n, seed), E, 1)
         probs.append(dict(Y=Yb, X=Xb, initparst=batch.default_initparst(E, True)))
     res = G.fit_batch(probs, ngpus=1, want_loo=True)
@@ -78,6 +78,27 @@ def test_mixed_batch_small_mid_and_tiled(gpu_lib):
         assert np.max(np.abs(one["pars"] - r["pars"]) / np.maximum(1, np.abs(one["pars"]))) <= 1e-9
         assert rel(r["nllpost"], one["nllpost"]) <= 1e-11
         np.testing.assert_allclose(r["loo_mean"], m.vector(_lib.VEC_LOO_MEAN), atol=1e-9)
+        m.close()
+
+
+def test_lockstep_batch_of_larger_fits_matches_single_fits(gpu_lib):
+    """11, 17 and 24 block columns in one lockstep batch (interleaved task lists, strict dependency order) against the
+    per-handle path (its own task order, k-chunked tiles).  Scheduling decides when a tile of the factorisation is
+    computed, never how, so the log posterior is the same to the last bit; the trace terms of the gradient are reduced
+    over a different number of column ranges per tile in the two paths, so the gradient agrees to rounding only."""
+    probs = []
+    for n, E, seed in [(1300, 3, 41), (2100, 2, 42), (3000, 4, 43)]:
+        Y, X = synth.embed(synth.ricker(n, seed), E, 1)
+        probs.append(dict(Y=Y, X=X, initparst=batch.default_initparst(E, True)))
+    res = G.fit_batch(probs, ngpus=1, want_loo=True)
+    for pr, r in zip(probs, res):
+        m = G.GPModel(pr["Y"], pr["X"])
+        one = m.fit_rprop(pr["initparst"], 1.0, None, None)
+        assert r["status"] == 0 and one["iter"] == r["iter"] and one["nevals"] == r["nevals"]
+        assert rel(r["nllpost"], one["nllpost"]) <= 1e-13 and rel(r["lnL_LOO"], one["lnL_LOO"]) <= 1e-12
+        np.testing.assert_allclose(r["pars"], one["pars"], rtol=1e-11, atol=0)
+        assert np.max(np.abs(r["grad"] - one["grad"])) <= 1e-10 * max(1.0, np.max(np.abs(one["grad"])))
+        np.testing.assert_allclose(r["loo_mean"], m.vector(_lib.VEC_LOO_MEAN), rtol=0, atol=1e-11)
         m.close()
 
 
