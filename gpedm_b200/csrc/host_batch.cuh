@@ -75,7 +75,11 @@ static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_
     memcpy(&hP[offN[q]], ds.pop, (size_t)ds.N * 4);
     if (ds.rhomat) memcpy(&hR[offR[q]], ds.rhomat, (size_t)ds.np * ds.np * 8);
   }
-  DevBuf dX, dY, dP, dR, dFits, dParams, dScal, dA, dDiag, dInfo, dActive;
+  // stream-ordered pool allocations (cudaMalloc / cudaFree synchronise the device; see fit_batch_mid)
+  StreamGuard stg;  // declared before the buffers: destroyed after them
+  CU(stg.create());
+  cudaStream_t st = stg.s;
+  PoolBuf dX(st), dY(st), dP(st), dR(st), dFits(st), dParams(st), dScal(st), dA(st), dDiag(st), dInfo(st), dActive(st);
   PinnedBuf pParams, pScal, pInfo;
   cudaError_t e = dX.alloc(totX * 8);
   if (e == cudaSuccess) e = dY.alloc(totN * 8);
@@ -91,10 +95,11 @@ static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_
   if (e == cudaSuccess) e = pParams.alloc(sizeof(EvalParams) * nf);
   if (e == cudaSuccess) e = pScal.alloc((size_t)NSCAL * 8 * nf);
   if (e == cudaSuccess) e = pInfo.alloc((size_t)nf * 4);
-  if (e == cudaSuccess) e = cudaMemcpy(dX.p, hX.data(), totX * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(dY.p, hY.data(), totN * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(dP.p, hP.data(), totN * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && totR) e = cudaMemcpy(dR.p, hR.data(), totR * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dX.p, hX.data(), totX * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dY.p, hY.data(), totN * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dP.p, hP.data(), totN * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && totR) e = cudaMemcpyAsync(dR.p, hR.data(), totR * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "small-fit batch setup failed: %s", cudaGetErrorString(e));
   EvalParams* hparams = (EvalParams*)pParams.p;
   double* hscal = (double*)pScal.p;
@@ -129,9 +134,8 @@ static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_
     m.hparams = hparams + q;
     m.hscal = hscal + (size_t)q * NSCAL;
   }
-  CU(cudaMemcpy(dFits.p, hfits.data(), sizeof(SmallFit) * nf, cudaMemcpyHostToDevice));
-  cudaStream_t st;
-  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CU(cudaMemcpyAsync(dFits.p, hfits.data(), sizeof(SmallFit) * nf, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
   const int DC = dmax <= 8 ? 8 : (dmax <= 16 ? 16 : 32);
   std::vector<int> active;
   auto launch = [&](int full) -> int {
@@ -237,7 +241,6 @@ static int fit_batch_small(int device, const std::vector<int>& idx, const gpedm_
       if (e != cudaSuccess) rc = set_err(GPEDM_ERR_CUDA, "small-fit download failed: %s", cudaGetErrorString(e));
     }
   }
-  cudaStreamDestroy(st);
   if (rc) return rc;
   int first_bad = 0;
   for (int q = 0; q < nf; ++q) {
@@ -361,15 +364,17 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
     L.scal = take((size_t)NSCAL * 8);
     L.params = take(sizeof(EvalParams));
   }
-  DevBuf arena, dFits, dDag, dTasks, dMapTS, dMapT, dMapV, dActive;
+  // device memory from the stream-ordered pool, like the handles: cudaMalloc / cudaFree synchronise the device and were
+  // measured at up to hundreds of milliseconds when they follow other work (a 40-cell grid on a 1024-point series took
+  // 0.44 .. 0.94 s from call to call with them)
+  StreamGuard stg;  // declared before the buffers: destroyed after them
+  CU(stg.create());
+  cudaStream_t st = stg.s;
+  PoolBuf arena(st), dFits(st), dDag(st), dTasks(st), dMapTS(st), dMapT(st), dMapV(st), dActive(st);
   PinnedBuf pParams, pScal, pInfo;
   cudaError_t e = arena.alloc(tot);
-  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "mid-size batch: cudaMalloc of %zu bytes failed: %s", tot, cudaGetErrorString(e));
+  if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "mid-size batch: allocation of %zu bytes failed: %s", tot, cudaGetErrorString(e));
   char* base = (char*)arena.p;
-  cudaStream_t st;
-  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  StreamGuard stg;
-  stg.s = st;
   // ---- per-fit descriptors, static per-fit task lists, uploads
   std::vector<MidFit> hfits(nf);
   std::vector<DagFit> hdag(nf);
@@ -957,6 +962,12 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
         }
         std::vector<int> wave(mine.begin() + b, mine.begin() + e2);
         int rcw = fit_batch_mid(devs[g], wave, descs, opts, tmp.data());
+        if (bytes > 8e9) {  // a large arena is not left cached in the pool (other allocations may want the memory)
+          cudaMemPool_t pool;
+          if (cudaSetDevice(devs[g]) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, devs[g]) == cudaSuccess)
+            cudaMemPoolTrimTo(pool, (size_t)8 << 30);
+          cudaGetLastError();
+        }
         if (rcw != 0 && rc == 0) {
           rc = rcw;
           werrs[wi] = gpedm_last_error();
