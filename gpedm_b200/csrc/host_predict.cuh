@@ -18,15 +18,19 @@ static int gpedm_predict_new_impl(gpedm_handle h, int64_t M, const double* Xnew,
   const int64_t chunk_max = std::min<int64_t>(M, CH);
   const int Mp_max = ceil_div((int)chunk_max, TB) * TB;
   const size_t ldv = h->Np;
-  double *dV = nullptr, *dU = nullptr, *dXn = nullptr, *dmean = nullptr, *dvar = nullptr, *dgrad = nullptr;
-  int* dpn = nullptr;
-  cudaError_t e = cudaMalloc((void**)&dV, ldv * Mp_max * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dU, ldv * Mp_max * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dXn, (size_t)chunk_max * d * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dpn, (size_t)chunk_max * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dmean, (size_t)chunk_max * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dvar, (size_t)chunk_max * 8);
-  if (e == cudaSuccess && gpgrad) e = cudaMalloc((void**)&dgrad, (size_t)chunk_max * d * 8);
+  // scratch from the stream-ordered pool (predict_iter / getconditionals call this once per step with a handful of
+  // points: cudaMalloc + cudaFree of seven buffers synchronise the device on every call)
+  PoolBuf bV(h->stream), bU(h->stream), bXn(h->stream), bpn(h->stream), bmean(h->stream), bvar(h->stream), bgrad(h->stream);
+  cudaError_t e = bV.alloc(ldv * Mp_max * 8);
+  if (e == cudaSuccess) e = bU.alloc(ldv * Mp_max * 8);
+  if (e == cudaSuccess) e = bXn.alloc((size_t)chunk_max * d * 8);
+  if (e == cudaSuccess) e = bpn.alloc((size_t)chunk_max * 4);
+  if (e == cudaSuccess) e = bmean.alloc((size_t)chunk_max * 8);
+  if (e == cudaSuccess) e = bvar.alloc((size_t)chunk_max * 8);
+  if (e == cudaSuccess && gpgrad) e = bgrad.alloc((size_t)chunk_max * d * 8);
+  double *dV = (double*)bV.p, *dU = (double*)bU.p, *dXn = (double*)bXn.p, *dmean = (double*)bmean.p, *dvar = (double*)bvar.p,
+         *dgrad = (double*)bgrad.p;
+  int* dpn = (int*)bpn.p;
   int rc = 0;
   std::vector<double> xn, gtmp;
   for (int64_t m0 = 0; m0 < M && e == cudaSuccess && rc == 0; m0 += CH) {
@@ -66,13 +70,6 @@ static int gpedm_predict_new_impl(gpedm_handle h, int64_t M, const double* Xnew,
         for (int64_t i = 0; i < mc; ++i) gpgrad[m0 + i + (size_t)k * M] = gtmp[i + (size_t)k * mc];
   }
   if (e == cudaSuccess) e = cudaGetLastError();
-  cudaFree(dV);
-  cudaFree(dU);
-  cudaFree(dXn);
-  cudaFree(dpn);
-  cudaFree(dmean);
-  cudaFree(dvar);
-  cudaFree(dgrad);
   if (rc) return rc;
   if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "gpedm_predict_new failed: %s", cudaGetErrorString(e));
   return 0;

@@ -3,6 +3,9 @@ closed-form LOO, block leave-out (lto) and sequential, at N = series-E rows.   p
 import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+from gpedm_b200 import _lib
+if os.environ.get('GPEDM_LIB'):  # A/B against another build of the library
+    _lib.LIB_PATH = os.environ['GPEDM_LIB']
 import gpedm_b200 as G
 from gpedm_b200 import synth
 from gpedm_b200.batch import default_initparst
