@@ -57,7 +57,7 @@ def config(N):
                         "default initpars (R/GPfunctions.R:409); inputs %.0f MB per matrix > L2"
                         % (SERIES_LEN, E, TAU, N, E, N * N * 8 / 1e6),
             "N": int(N), "d": E, "series_len": SERIES_LEN, "tau": TAU, "seed": SEED,
-            "l2": "inputs larger than L2 (3 N x N FP64 work matrices of %.0f MB each)" % (N * N * 8 / 1e6),
+            "l2": "inputs larger than L2 (4 N x N FP64 work matrices of %.0f MB each)" % (N * N * 8 / 1e6),
             "parallelism": "independent fits sharded across GPUs; no data-path collective"}
 
 
@@ -364,6 +364,11 @@ def run_ours(args):
                                 "trace_GBs": 4.0 * N * (N + 1) / (phases["trace"] * 1e-3) * 1e-9,
                                 "assemble_frac": 4.0 * N * (N + 1) / (phases["assemble"] * 1e-3) * 1e-9 / hbm,
                                 "trace_frac": 4.0 * N * (N + 1) / (phases["trace"] * 1e-3) * 1e-9 / hbm,
+                                "trace_traffic_GBs": 8.0 * N * (N + 1) / (phases["trace"] * 1e-3) * 1e-9,
+                                "note": "rates on the algorithmic bytes of SURVEY 8(d), 4N(N+1) per kernel; the trace kernel "
+                                        "actually reads 8N(N+1) B (Sigma^-1 and the kept copy of Sigma, instead of recomputing "
+                                        "every exp): trace_traffic_GBs.  Both kernels are bound by FP64 issue, not by HBM "
+                                        "(DESIGN section 4)",
                                 "hbm_peak_GBs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         cpu = None
         if not args.no_cpu_baseline and world == 1:

@@ -305,7 +305,7 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
   const int sms = (device < 64 && g_num_sms[device] > 0) ? g_num_sms[device] : 148;
   // ---- layout of one device arena: per fit the three work matrices, vectors, partials, flags
   struct Lay {
-    size_t A, X, S, dX, dY, dpop, rhotab, z, a, diagS, part, logdet, tracepart, scal, flags, params;
+    size_t A, X, S, D, dX, dY, dpop, rhotab, z, a, diagS, part, logdet, tracepart, scal, flags, params;
     int N, d, np, nb, Np, ntiles, split, nflags;
   };
   std::vector<Lay> lay(nf);
@@ -351,6 +351,7 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
     const size_t mat = (size_t)L.Np * L.Np * 8;
     L.A = take(mat);
     L.S = take(mat);
+    L.D = take(mat);
     L.dX = take((size_t)L.N * L.d * 8);
     L.dY = take((size_t)L.Np * 8);
     L.dpop = take((size_t)L.N * 4);
@@ -396,6 +397,7 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
     F.A = (double*)(base + L.A);
     F.X = (double*)(base + L.X);
     F.S = (double*)(base + L.S);
+    F.D = (double*)(base + L.D);
     F.ld = L.Np;
     F.N = L.N;
     F.nb = L.nb;
@@ -948,7 +950,7 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
     if (!mid) {
       rc = fit_batch_small(devs[g], mine, descs, opts, tmp.data());
     } else {
-      // waves of at most ~48 GB of work matrices (3 Np^2 doubles per fit)
+      // waves of at most ~48 GB of work matrices (4 Np^2 doubles per fit)
       const double cap = 48e9;
       size_t b = 0;
       while (b < mine.size()) {
@@ -956,8 +958,8 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
         size_t e2 = b;
         while (e2 < mine.size()) {
           const double np_ = (double)ceil_div((int)descs[mine[e2]].N, TB) * TB;
-          if (e2 > b && bytes + 24.0 * np_ * np_ > cap) break;
-          bytes += 24.0 * np_ * np_;
+          if (e2 > b && bytes + 32.0 * np_ * np_ > cap) break;
+          bytes += 32.0 * np_ * np_;
           ++e2;
         }
         std::vector<int> wave(mine.begin() + b, mine.begin() + e2);

@@ -12,7 +12,7 @@ struct gpedm_fit_s {
   bool single_pop = true;
   double *dX = nullptr, *dY = nullptr, *drhotab = nullptr;
   int* dpop = nullptr;
-  double *bufA = nullptr, *bufB = nullptr, *bufC = nullptr;
+  double *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *bufD = nullptr;  // bufD: kept copy of Sigma (lower tiles)
   EvalParams* dparams = nullptr;
   void* pinned = nullptr;         // one recycled pinned block holding hparams | hscal | hinfo
   EvalParams* hparams = nullptr;  // pinned
@@ -192,7 +192,7 @@ static void free_handle(gpedm_fit_s* h) {
   if (h->stream) {
     cudaStreamSynchronize(h->stream);
     if (h->aux) cudaStreamSynchronize(h->aux);
-    void* bufs[] = {h->dX, h->dY, h->drhotab, h->dpop, h->bufA, h->bufB, h->bufC, h->dparams, h->dz, h->da,
+    void* bufs[] = {h->dX, h->dY, h->drhotab, h->dpop, h->bufA, h->bufB, h->bufC, h->bufD, h->dparams, h->dz, h->da,
                     h->ddiagS, h->dpart, h->dlogdet, h->dtracepart, h->dscal, h->dinfo, h->dcenter, h->dscale,
                     h->dtasks, h->dsync, h->dfit};
     for (void* b : bufs)
@@ -358,6 +358,7 @@ static int alloc_handle(int device, int64_t N, int32_t d, int32_t np, bool has_r
   ALLOC(h->bufA, mat);
   ALLOC(h->bufB, mat);
   ALLOC(h->bufC, mat);
+  ALLOC(h->bufD, mat);
   ALLOC(h->dparams, sizeof(EvalParams));
   ALLOC(h->dz, Np * 8);
   ALLOC(h->da, Np * 8);

@@ -124,11 +124,11 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   CU(record_phase_event(h->ev[0], st));
   // --- assemble Sigma (lower tiles) into bufA (or take the caller's matrix: gpedm_covinv)
   if (h->dsigma_in) {
-    load_sigma_kernel<<<h->ntiles, 256, 0, st>>>(h->bufA, ld, N, h->dsigma_in);
+    load_sigma_kernel<<<h->ntiles, 256, 0, st>>>(h->bufA, h->bufD, ld, N, h->dsigma_in);
     h->launches++;
   } else {
     int smem = 2 * d * TB * 8 + 2 * TB * 4;
-    assemble_sigma_kernel<<<h->ntiles * h->tile_split, 256, smem, st>>>(h->bufA, ld, N, h->dX, h->dpop, h->drhotab,
+    assemble_sigma_kernel<<<h->ntiles * h->tile_split, 256, smem, st>>>(h->bufA, h->bufD, ld, N, h->dX, h->dpop, h->drhotab,
                                                                           h->dparams, h->tile_split);
     h->launches++;
   }
@@ -284,10 +284,10 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
   // --- gradient trace terms + scalar reductions
   {
     const int DC = d <= 8 ? 8 : (d <= 12 ? 12 : (d <= 16 ? 16 : 32));
-    const int smem = (2 * d * TB + 2 * TB + DC + 8 * (DC + 3)) * 8 + 2 * TB * 4;
+    const int smem = (2 * d * TB + 2 * TB + 8 * (DC + 3)) * 8 + 2 * TB * 4;
     const int cs = h->tile_split, grid = h->ntiles * cs;
 #define GPEDM_TRACE(DCV)                                                                                         \
-  grad_trace_kernel<DCV><<<grid, 256, smem, st>>>(h->bufC, ld, N, h->dX, h->dpop, h->drhotab, h->da, h->dparams, \
+  grad_trace_kernel<DCV><<<grid, 256, smem, st>>>(h->bufC, h->bufD, ld, N, h->dX, h->dpop, h->da, h->dparams, \
                                                   h->dtracepart, cs)
     if (DC == 8)
       GPEDM_TRACE(8);

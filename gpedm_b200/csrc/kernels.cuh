@@ -50,7 +50,10 @@ __device__ __forceinline__ double cov_entry(const double* xi, const double* xj, 
 // ranges (csplit > 1 only when there are fewer tiles than SMs).  A thread owns TWO consecutive rows
 // (16-byte loads of the staged predictors, 16-byte stores: one column of the tile is written as 64 x 16
 // contiguous bytes) and every fourth column of its range; the arithmetic per entry is exactly cov_entry's.
-__device__ __forceinline__ void assemble_sigma_body(double* __restrict__ A, size_t ld, int N,
+// `Akeep` receives the same values: Sigma is factored in place, and the gradient trace terms read Cd = Sigma - ve I
+// from this copy instead of recomputing every distance and exponential (the assembly is bound by FP64 issue, not by
+// its stores, so the second stream of stores is free).
+__device__ __forceinline__ void assemble_sigma_body(double* __restrict__ A, double* __restrict__ Akeep, size_t ld, int N,
                                                               const double* __restrict__ X,
                                                               const int* __restrict__ pop,
                                                               const double* __restrict__ rhotab,
@@ -108,14 +111,15 @@ __device__ __forceinline__ void assemble_sigma_body(double* __restrict__ A, size
     if (gj >= N || gi0 >= N) v0 = (gi0 == gj) ? 1.0 : 0.0;          // identity in the padding
     if (gj >= N || gi0 + 1 >= N) v1 = (gi0 + 1 == gj) ? 1.0 : 0.0;
     *reinterpret_cast<double2*>(A + (size_t)gi0 + (size_t)gj * ld) = make_double2(v0, v1);
+    *reinterpret_cast<double2*>(Akeep + (size_t)gi0 + (size_t)gj * ld) = make_double2(v0, v1);
   }
 }
-__global__ void __launch_bounds__(256) assemble_sigma_kernel(double* __restrict__ A, size_t ld, int N,
+__global__ void __launch_bounds__(256) assemble_sigma_kernel(double* __restrict__ A, double* __restrict__ Akeep, size_t ld, int N,
                                                               const double* __restrict__ X,
                                                               const int* __restrict__ pop,
                                                               const double* __restrict__ rhotab,
                                                               const EvalParams* __restrict__ P, int csplit) {
-  assemble_sigma_body(A, ld, N, X, pop, rhotab, P, csplit, (int)blockIdx.x);
+  assemble_sigma_body(A, Akeep, ld, N, X, pop, rhotab, P, csplit, (int)blockIdx.x);
 }
 
 // General rectangular covariance (getcov with X2 != X): out[(row) + (col)*ldo] where
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(256) cov_rect_kernel(double* __restrict__ out,
 // getcovinv on a caller-supplied matrix (reference R/GPfunctions.R:818-830): load the symmetrised lower
 // tiles of Sigma (N x N column-major, "(Sigma + t(Sigma))/2" as the reference does before calling it,
 // :641, :1076) into the padded work matrix, identity in the padding.
-__global__ void __launch_bounds__(256) load_sigma_kernel(double* __restrict__ A, size_t ld, int N,
+__global__ void __launch_bounds__(256) load_sigma_kernel(double* __restrict__ A, double* __restrict__ Akeep, size_t ld, int N,
                                                           const double* __restrict__ S) {
   int ti, tj;
   tri_decode(blockIdx.x, ti, tj);
@@ -195,6 +199,7 @@ __global__ void __launch_bounds__(256) load_sigma_kernel(double* __restrict__ A,
     else
       v = (gi == gj) ? 1.0 : 0.0;
     A[(size_t)gi + (size_t)gj * ld] = v;
+    Akeep[(size_t)gi + (size_t)gj * ld] = v;
   }
 }
 
@@ -387,20 +392,18 @@ __global__ void extract_diag_kernel(const double* __restrict__ S, size_t ld, int
 // Gradient trace terms (reference R/GPfunctions.R:652-709):  with vQ = 0.5 (a a' - Sigma^-1),
 //   T_k   = <vQ, -D_k o Cd>          (dl_k = 0.5 T_k, the reference's extra one half, :663)
 //   T_ve  = <vQ, I>, T_s2 = <vQ, Cd/sigma2>, T_rho = <vQ, Cd o (1-popsame) / rho>
-// Reads Sigma^-1 (lower tiles) once; Cd and the per-coordinate squared distances D_k are
-// recomputed from the staged predictor tiles instead of being stored (the reference keeps d
-// dense N x N matrices, :539-542).  Off-diagonal entries count twice (symmetry).
+// Reads Sigma^-1 (lower tiles) and the kept copy of Sigma (Cd = Sigma off the diagonal, sigma2 on it: exactly the
+// entries the likelihood was built from) once each; the per-coordinate squared distances D_k are recomputed from
+// the staged predictor tiles instead of being stored (the reference keeps d dense N x N matrices, :539-542).
+// Off-diagonal entries count twice (symmetry).  Round 1 also recomputed Cd here (distances + a software exp per
+// entry: ~80 FP64 instructions, FP64-issue-bound at 0.35 ms for N = 8182); with Cd read back it is ~3 per coordinate.
 // tracepart[cta][q], q = 0..d-1 (phi), d (ve), d+1 (sigma2), d+2 (rho).
-// A thread owns two consecutive rows (16-byte loads of Sigma^-1 and of the staged predictors) and every
-// fourth column of the CTA's column range.  Here Cd only weights a sum that is compared at 1e-8, so its
-// squared distance is accumulated as sum_k phi_k (x_ik - x_jk)^2 with FMAs, sharing (x_ik - x_jk)^2 with
-// the D_k terms (the assembly kernel keeps getcov's exact operation order; this one does not need to).
-// The 1/sigma2 and 1/rho factors are applied once per CTA, not per entry.
+// A thread owns two consecutive rows (16-byte loads of both matrices and of the staged predictors) and every
+// fourth column of the CTA's column range.  The 1/sigma2 and 1/rho factors are applied once per CTA, not per entry.
 template <int DC>
-__device__ __forceinline__ void grad_trace_body(const double* __restrict__ S, size_t ld, int N,
+__device__ __forceinline__ void grad_trace_body(const double* __restrict__ S, const double* __restrict__ Sig, size_t ld, int N,
                                                           const double* __restrict__ X,
                                                           const int* __restrict__ pop,
-                                                          const double* __restrict__ rhotab,
                                                           const double* __restrict__ avec,
                                                           const EvalParams* __restrict__ P,
                                                           double* __restrict__ tracepart, int csplit, const int bid) {
@@ -410,8 +413,7 @@ __device__ __forceinline__ void grad_trace_body(const double* __restrict__ S, si
   double* rj = ri + d * TB;         // ... of its columns
   double* ai = rj + d * TB;         // [128]
   double* aj = ai + TB;
-  double* phis = aj + TB;           // [DC]
-  double* red = phis + DC;          // [8][DC+3]
+  double* red = aj + TB;            // [8][DC+3]
   int* pi_s = (int*)(red + 8 * (DC + 3));
   int* pj_s = pi_s + TB;
   int ti, tj;
@@ -431,11 +433,8 @@ __device__ __forceinline__ void grad_trace_body(const double* __restrict__ S, si
     ai[tid] = gi < N ? avec[gi] : 0.0;
     aj[tid] = gj < N ? avec[gj] : 0.0;
   }
-  if (tid < DC) phis[tid] = tid < d ? P->phi[tid] : 0.0;
   __syncthreads();
   const double sigma2 = P->sigma2, rho = P->rho;
-  const int np = P->np;
-  const double* rt = P->use_rhotab ? rhotab : nullptr;
   const int r0 = 2 * (tid & 63), cg = tid >> 6;
   const int gi0 = ti * TB + r0;
   double acc[DC + 3];
@@ -443,47 +442,37 @@ __device__ __forceinline__ void grad_trace_body(const double* __restrict__ S, si
   for (int q = 0; q < DC + 3; ++q) acc[q] = 0.0;
   const double a0 = ai[r0], a1 = ai[r0 + 1];
   const int p0 = pi_s[r0], p1 = pi_s[r0 + 1];
-  const double* Sp = S + (size_t)gi0 + (size_t)tj * TB * ld;
-  // the Sigma^-1 pair of the NEXT column is requested before the current one is processed (the loop is
-  // otherwise bound by the latency of this load: ncu long-scoreboard stalls)
+  const size_t off0 = (size_t)gi0 + (size_t)tj * TB * ld;
+  const double* Sp = S + off0;
+  const double* Cp = Sig + off0;
+  // the pairs of the NEXT column are requested before the current one is processed (the loop is otherwise bound by
+  // the latency of these loads)
   double2 s2n = *reinterpret_cast<const double2*>(Sp + (size_t)(cbeg + cg) * ld);
+  double2 c2n = *reinterpret_cast<const double2*>(Cp + (size_t)(cbeg + cg) * ld);
   for (int c = cbeg + cg; c < cbeg + ncols; c += 4) {
     const int gj = tj * TB + c;
-    const double2 s2 = s2n;
-    if (c + 4 < cbeg + ncols) s2n = *reinterpret_cast<const double2*>(Sp + (size_t)(c + 4) * ld);
+    const double2 s2 = s2n, c2 = c2n;
+    if (c + 4 < cbeg + ncols) {
+      s2n = *reinterpret_cast<const double2*>(Sp + (size_t)(c + 4) * ld);
+      c2n = *reinterpret_cast<const double2*>(Cp + (size_t)(c + 4) * ld);
+    }
     if (gj >= N || gj > gi0 + 1 || gi0 >= N) continue;  // nothing of this column pair lies in the lower triangle
-    double d20[DC], d21[DC];
-    double dist0 = 0.0, dist1 = 0.0;
+    const int pj = pj_s[c];
+    const double ajc = aj[c];
+    const bool ok0 = gj <= gi0, ok1 = gi0 + 1 < N;  // (gj <= gi0 + 1 and gi0 < N hold here)
+    const double q0 = 0.5 * (a0 * ajc - s2.x), q1 = 0.5 * (a1 * ajc - s2.y);
+    // Cd: Sigma off the diagonal, sigma2 on it (Sigma_ii = sigma2 + ve); off-diagonal entries count twice
+    const double qc0 = ok0 ? ((gi0 == gj) ? q0 * sigma2 : 2.0 * q0 * c2.x) : 0.0;
+    const double qc1 = ok1 ? ((gi0 + 1 == gj) ? q1 * sigma2 : 2.0 * q1 * c2.y) : 0.0;
 #pragma unroll
     for (int k = 0; k < DC; ++k) {
       if (k < d) {
         const double2 xr = *reinterpret_cast<const double2*>(ri + k * TB + r0);
         const double xc = rj[k * TB + c];
         const double f0 = xr.x - xc, f1 = xr.y - xc;
-        d20[k] = f0 * f0;
-        d21[k] = f1 * f1;
-        dist0 = fma(phis[k], d20[k], dist0);
-        dist1 = fma(phis[k], d21[k], dist1);
-      } else {
-        d20[k] = d21[k] = 0.0;
+        acc[k] = fma(-qc0, f0 * f0, fma(-qc1, f1 * f1, acc[k]));
       }
     }
-    const int pj = pj_s[c];
-    const double ajc = aj[c];
-    double m0 = 1.0, m1 = 1.0;
-    if (rt != nullptr) {
-      m0 = rt[p0 + pj * np];
-      m1 = rt[(p1 < 0 ? p0 : p1) + pj * np];
-    } else {
-      if (p0 != pj) m0 = rho;
-      if (p1 != pj) m1 = rho;
-    }
-    const bool ok0 = gj <= gi0, ok1 = gi0 + 1 < N;  // (gj <= gi0 + 1 and gi0 < N hold here)
-    const double q0 = 0.5 * (a0 * ajc - s2.x), q1 = 0.5 * (a1 * ajc - s2.y);
-    const double qc0 = ok0 ? ((gi0 == gj) ? 1.0 : 2.0) * q0 * (sigma2 * exp(-dist0) * m0) : 0.0;
-    const double qc1 = ok1 ? ((gi0 + 1 == gj) ? 1.0 : 2.0) * q1 * (sigma2 * exp(-dist1) * m1) : 0.0;
-#pragma unroll
-    for (int k = 0; k < DC; ++k) acc[k] = fma(-qc0, d20[k], fma(-qc1, d21[k], acc[k]));
     if (gi0 == gj) acc[DC] += q0;
     if (gi0 + 1 == gj && ok1) acc[DC] += q1;
     acc[DC + 1] += qc0 + qc1;
@@ -509,14 +498,14 @@ __device__ __forceinline__ void grad_trace_body(const double* __restrict__ S, si
   }
 }
 template <int DC>
-__global__ void __launch_bounds__(256, DC <= 16 ? 2 : 1) grad_trace_kernel(const double* __restrict__ S, size_t ld, int N,
+__global__ void __launch_bounds__(256, DC <= 16 ? 3 : 1) grad_trace_kernel(const double* __restrict__ S, const double* __restrict__ Sig,
+                                                          size_t ld, int N,
                                                           const double* __restrict__ X,
                                                           const int* __restrict__ pop,
-                                                          const double* __restrict__ rhotab,
                                                           const double* __restrict__ avec,
                                                           const EvalParams* __restrict__ P,
                                                           double* __restrict__ tracepart, int csplit) {
-  grad_trace_body<DC>(S, ld, N, X, pop, rhotab, avec, P, tracepart, csplit, (int)blockIdx.x);
+  grad_trace_body<DC>(S, Sig, ld, N, X, pop, avec, P, tracepart, csplit, (int)blockIdx.x);
 }
 
 // Final scalar reductions of one evaluation (single CTA, fixed order => deterministic):

@@ -13,7 +13,7 @@
 namespace gpedm {
 
 struct MidFit {  // device-side description of one fit of the batch
-  double *A, *X, *S;  // Sigma -> L, L^-1, Sigma^-1 (Np x Np, lower tiles)
+  double *A, *X, *S, *D;  // Sigma -> L, L^-1, Sigma^-1, kept copy of Sigma (Np x Np, lower tiles)
   size_t ld;
   int N, nb, ntiles, split, d, pad;
   const double* dX;
@@ -28,7 +28,7 @@ struct MidFit {  // device-side description of one fit of the batch
 __global__ void __launch_bounds__(256) mid_assemble_kernel(const MidFit* __restrict__ fits, const int2* __restrict__ map) {
   const int2 m = map[blockIdx.x];
   const MidFit f = fits[m.x];
-  assemble_sigma_body(f.A, f.ld, f.N, f.dX, f.dpop, f.drhotab, f.P, f.split, m.y);
+  assemble_sigma_body(f.A, f.D, f.ld, f.N, f.dX, f.dpop, f.drhotab, f.P, f.split, m.y);
 }
 __global__ void __launch_bounds__(256) mid_trmv_n_kernel(const MidFit* __restrict__ fits, const int2* __restrict__ map) {
   const int2 m = map[blockIdx.x];
@@ -51,10 +51,10 @@ __global__ void __launch_bounds__(256) mid_extract_diag_kernel(const MidFit* __r
   extract_diag_body(f.S, f.ld, f.N, f.ddiagS, m.y);
 }
 template <int DC>
-__global__ void __launch_bounds__(256, DC <= 16 ? 2 : 1) mid_trace_kernel(const MidFit* __restrict__ fits, const int2* __restrict__ map) {
+__global__ void __launch_bounds__(256, DC <= 16 ? 3 : 1) mid_trace_kernel(const MidFit* __restrict__ fits, const int2* __restrict__ map) {
   const int2 m = map[blockIdx.x];
   const MidFit f = fits[m.x];
-  grad_trace_body<DC>(f.S, f.ld, f.N, f.dX, f.dpop, f.drhotab, f.da, f.P, f.dtracepart, f.split, m.y);
+  grad_trace_body<DC>(f.S, f.D, f.ld, f.N, f.dX, f.dpop, f.da, f.P, f.dtracepart, f.split, m.y);
 }
 // one CTA per active fit
 __global__ void __launch_bounds__(256) mid_final_reduce_kernel(const MidFit* __restrict__ fits, const int* __restrict__ active, int have_S) {
