@@ -411,10 +411,11 @@ def grid_workers(ncells, world):
     """Concurrent fits per GPU in the grid.  The persistent factorisation kernel occupies every SM, so resident fits
     alternate instead of filling each other's gaps (56.4 vs 56.8 evaluations/s with 1 vs 3 resident at N=8182) and
     every extra resident fit stretches each fit: two workers when a GPU has a queue of cells (hides handle set-up /
-    teardown and the host side of the Rprop loop), one when it has only a few, so that the longest fit of the grid
-    (105 iterations, 1.9 s alone) bounds the wall time as little as possible."""
+    teardown and the host side of the Rprop loop), one when it has only a few: two resident fits run at half speed
+    each, which doubles the imbalance the last cells of the queue leave between the GPUs (4 GPUs, 10 cells each:
+    9.2 .. 9.9 s from run to run with two workers) and stretches the longest fit of the grid (105 iterations, 1.9 s alone)."""
     per_gpu = ncells / max(1, world)
-    return 2 if per_gpu >= 8 else 1
+    return 2 if per_gpu >= 16 else 1
 
 
 def run_grid(G, gd, world, rank, local, barrier):

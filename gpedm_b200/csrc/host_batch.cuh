@@ -677,14 +677,15 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
 // single fits).  The persistent factorisation kernel occupies every SM, so two resident fits no longer fill each
 // other's chain-bound stretches - their factorisations simply alternate (N ~ 8190: 56.4 evaluations/s one at a time,
 // 56.8 with three resident) - and every extra resident fit stretches each fit's own duration, which is what bounds
-// a grid spread over several GPUs.  Two workers hide handle creation / teardown and the host side of the Rprop
-// loop when a GPU has a queue of fits; one when it has only a few.
+// a grid spread over several GPUs (two resident fits run at half speed each: twice the imbalance at the end of the
+// queue).  Two workers hide handle creation / teardown and the host side of the Rprop loop when a GPU has a long
+// queue of fits (16 or more); one otherwise.
 static int default_workers_per_gpu(int64_t nmax, int nfits, int ngpus) {
   if (g_batch_workers > 0) return g_batch_workers;
   int w;
   if (nmax > 6144) {
     const double per_gpu = (double)nfits / std::max(1, ngpus);
-    w = per_gpu >= 8 ? 2 : 1;
+    w = per_gpu >= 16 ? 2 : 1;
   } else {
     // Smaller fits that still come through one handle each (gpedm_fit_grid cells, a single mid-size fit next to larger
     // ones): the evaluation is a dozen launches around a chain-bound factorisation and several of them interleave
@@ -964,10 +965,10 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
         }
         std::vector<int> wave(mine.begin() + b, mine.begin() + e2);
         int rcw = fit_batch_mid(devs[g], wave, descs, opts, tmp.data());
-        if (bytes > 8e9) {  // a large arena is not left cached in the pool (other allocations may want the memory)
+        if (bytes > 32e9) {  // a very large arena is not left cached in the pool (other allocations may want the memory)
           cudaMemPool_t pool;
           if (cudaSetDevice(devs[g]) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, devs[g]) == cudaSuccess)
-            cudaMemPoolTrimTo(pool, (size_t)8 << 30);
+            cudaMemPoolTrimTo(pool, (size_t)32 << 30);
           cudaGetLastError();
         }
         if (rcw != 0 && rc == 0) {

@@ -110,7 +110,7 @@ static int ensure_kernel_attrs(int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (device < 64) g_num_sms[device] = prop.multiProcessorCount;
     // Handles are created and destroyed per fit (40 per model-selection grid): keep freed device
-    // memory cached in the stream-ordered pool instead of returning 1.6 GB to the driver each time.
+    // memory cached in the stream-ordered pool instead of returning 2.1 GB to the driver each time.
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
       unsigned long long thr = ~0ull;
