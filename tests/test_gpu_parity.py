@@ -673,6 +673,32 @@ def test_fit_grid_device_prep_equals_host_prep(gpu_lib):
         assert a["R2_insample"] == pytest.approx(b["R2_insample"], rel=1e-9)
 
 
+def test_fit_grid_lockstep_statistics_match_single_handles_and_oracle(gpu_lib):
+    """gpedm_fit_grid on a short series runs its cells through the lockstep batch and reduces the fit statistics on the
+    host from the returned in-sample / leave-one-out means (fit_grid_lockstep, host_lagged.cuh); a single handle
+    reduces them on the device (fit_stats_kernel).  Two populations with local scaling exercise the per-population
+    unscaling; the oracle's fitGP (reference R/GPfunctions.R:221-520, getR2 :1366-1370) is the independent check."""
+    ya, yb = synth.thetalogistic(260, 71, theta=3.0), 3.0 + 2.0 * synth.thetalogistic(260, 72, theta=2.0)
+    y = np.concatenate([ya, yb])
+    pop = np.array(["A"] * 260 + ["B"] * 260, dtype=object)
+    cells = G.fit_grid(y, [2, 3], [1, 2], pop=pop, ngpus=1, scaling="local")
+    assert all(c["status"] == 0 and c["N"] > 256 for c in cells)   # two or more tiles: the lockstep path
+    for c in cells:
+        m = G.GPModel.from_series(y, c["E"], c["tau"], pop=pop, scaling="local")
+        one = m.fit_rprop(batch.default_initparst(c["E"], False))
+        st = m.fit_stats()
+        m.close()
+        assert one["iter"] == c["iter"]
+        assert np.max(np.abs(c["pars"] - one["pars"]) / np.maximum(1, np.abs(one["pars"]))) <= 1e-9
+        for k in ("R2_insample", "R2_loo", "rmse_insample", "rmse_loo"):
+            assert c[k] == pytest.approx(st[k], rel=1e-9), k
+    c = cells[0]
+    o = O.fitGP(data=dict(y=y, pop=pop), y="y", pop="pop", E=c["E"], tau=c["tau"], scaling="local", predictmethod="loo")
+    assert o["iter"] == c["iter"]
+    assert c["R2_insample"] == pytest.approx(o["insampfitstats"]["R2"], rel=1e-8)
+    assert c["R2_loo"] == pytest.approx(o["outsampfitstats"]["R2"], rel=1e-8)
+
+
 def test_getrhomatrix_vs_oracle(gpu_lib, thetalog2pop):
     """getrhomatrix: all pair fits in one gpedm_fit_batch call (one-CTA-per-fit kernel for pairs with <= 128
     rows) against the oracle's loop of two-population fitGP calls (R/rhomatrix.R:169-182), plus the K1 pin."""
