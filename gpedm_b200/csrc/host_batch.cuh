@@ -865,6 +865,8 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
                                const gpedm_rprop_options* opts, gpedm_result* results) {
   if (nfits < 0 || (nfits > 0 && (!descs || !results))) return set_err(GPEDM_ERR_ARG, "bad arguments");
   if (nfits == 0) return 0;
+  for (int i = 0; i < nfits; ++i)
+    if (descs[i].np >= 1 && check_rhomat(descs[i].np, descs[i].rhomat)) return GPEDM_ERR_ARG;
   int ndev = gpedm_device_count();
   if (ndev == 0) return set_err(GPEDM_ERR_CUDA, "no CUDA device available (libgpedm_b200 has no CPU fallback)");
   if (ngpus < 1 || ngpus > ndev) return set_err(GPEDM_ERR_ARG, "ngpus=%d out of range (have %d devices)", ngpus, ndev);

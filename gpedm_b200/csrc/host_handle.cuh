@@ -451,10 +451,23 @@ static int alloc_handle(int device, int64_t N, int32_t d, int32_t np, bool has_r
   return 0;
 }
 
+// A rhomatrix is a between-population correlation matrix: its diagonal must be 1.  The closed forms of the
+// leave-out variances (1/S_ii - ve = Cd_ii - c' S^-1 c against the reference's sigma2 - c' S^-1 c, :1080) and the
+// diagonal of Cd in the gradient trace terms (sigma2) rely on Cd_ii = sigma2, i.e. on rhomat[p, p] = 1, which is what
+// getrhomatrix produces (R/rhomatrix.R:183-186); anything else is refused rather than silently answered differently.
+static int check_rhomat(int32_t np, const double* rhomat) {
+  if (!rhomat) return 0;
+  for (int32_t p = 0; p < np; ++p)
+    if (!(fabs(rhomat[(size_t)p * (np + 1)] - 1.0) <= 1e-12))
+      return set_err(GPEDM_ERR_ARG, "rhomatrix must have a unit diagonal (entry %d is %.17g)", p, rhomat[(size_t)p * (np + 1)]);
+  return 0;
+}
+
 static int gpedm_create_impl(int device, int64_t N, int32_t d, int32_t np, const double* X, const double* Y,
                             const int32_t* pop, const double* rhomat, gpedm_handle* out) {
   if (!out) return set_err(GPEDM_ERR_ARG, "out handle is NULL");
   *out = nullptr;
+  if (np >= 1 && check_rhomat(np, rhomat)) return GPEDM_ERR_ARG;
   if (N < 1 || N > (1 << 20)) return set_err(GPEDM_ERR_ARG, "N=%lld out of range", (long long)N);
   if (np < 1) return set_err(GPEDM_ERR_ARG, "np=%d must be >= 1", np);
   if (!X || !Y || !pop) return set_err(GPEDM_ERR_ARG, "X, Y and pop must be non-NULL");

@@ -60,6 +60,7 @@ static int create_from_series(const LagSeries& S, int32_t E, int32_t tau, int32_
   if (E < 1 || E > GPEDM_MAX_D) return set_err(GPEDM_ERR_ARG, "E=%d out of range 1..%d", E, GPEDM_MAX_D);
   if (tau < 1) return set_err(GPEDM_ERR_ARG, "tau=%d must be >= 1", tau);
   if (scaling < GPEDM_SCALE_NONE || scaling > GPEDM_SCALE_LOCAL) return set_err(GPEDM_ERR_ARG, "unknown scaling %d", scaling);
+  if (check_rhomat(S.np, rhomat)) return GPEDM_ERR_ARG;
   CU(cudaSetDevice(S.device));
   const int G = scaling == GPEDM_SCALE_LOCAL ? S.np : 1;
   const size_t nstat = (size_t)(E + 1) * G;

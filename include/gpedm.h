@@ -83,7 +83,8 @@ void gpedm_default_rprop_options(gpedm_rprop_options* opts);
 /* ---- model state --------------------------------------------------------------------- */
 /* Upload the training set of one fit: what fitGP hands to fmingrad_Rprop
  * (reference R/GPfunctions.R:447-454): Y (N), X (N x d, column-major), Pop as codes
- * 0..np-1 in order of first appearance, optional rhomatrix (np x np column-major, ordered
+ * 0..np-1 in order of first appearance, optional rhomatrix (np x np column-major with a UNIT diagonal - a
+ * between-population correlation matrix as getrhomatrix returns it; anything else is GPEDM_ERR_ARG -, ordered
  * like the codes; NULL = single rho).  N >= 1, 1 <= d <= GPEDM_MAX_D. */
 int gpedm_create(int device, int64_t N, int32_t d, int32_t np, const double* X, const double* Y,
                  const int32_t* pop, const double* rhomat, gpedm_handle* out);

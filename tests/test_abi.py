@@ -70,6 +70,10 @@ def test_argument_validation(L):
     bad = np.array([0, 0, 3, 0], dtype=np.int32)
     assert L.gpedm_create(0, 4, 2, 2, dp(X), dp(Y), ip(bad), None, C.byref(h)) == -1      # pop code out of range
     assert b"pop[2]" in L.gpedm_last_error()
+    pop2 = np.array([0, 1, 0, 1], dtype=np.int32)
+    Rbad = np.array([[1.0, 0.3], [0.3, 0.9]], order="F")                                     # rhomatrix diagonal != 1
+    assert L.gpedm_create(0, 4, 2, 2, dp(X), dp(Y), ip(pop2), dp(Rbad), C.byref(h)) == -1
+    assert b"unit diagonal" in L.gpedm_last_error()
     assert L.gpedm_likegrad(None, None, 1.0, None, float("nan"), 0, None) == -1
     assert L.gpedm_fit_batch(-1, None, 1, None, None, None) == -1
     assert L.gpedm_create_lagged(0, 10, dp(np.zeros(10)), None, 1, 2, 1, 1, None, None) == -1   # NULL out handle
