@@ -373,7 +373,8 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
   cudaStream_t st = stg.s;
   PoolBuf arena(st), dFits(st), dDag(st), dTasks(st), dMapTS(st), dMapT(st), dMapV(st), dActive(st);
   PinnedBuf pParams, pScal, pInfo;
-  cudaError_t e = arena.alloc(tot);
+  static const bool test_alloc_fail = getenv("GPEDM_TEST_MID_ALLOC_FAIL") != nullptr;  // exercises the caller's fallback
+  cudaError_t e = test_alloc_fail ? cudaErrorMemoryAllocation : arena.alloc(tot);
   if (e != cudaSuccess) return set_err(GPEDM_ERR_CUDA, "mid-size batch: allocation of %zu bytes failed: %s", tot, cudaGetErrorString(e));
   char* base = (char*)arena.p;
   // ---- per-fit descriptors, static per-fit task lists, uploads
@@ -967,6 +968,15 @@ static int gpedm_fit_batch_impl(int32_t nfits, const gpedm_fit_desc* descs, int3
         }
         std::vector<int> wave(mine.begin() + b, mine.begin() + e2);
         int rcw = fit_batch_mid(devs[g], wave, descs, opts, tmp.data());
+        if (rcw == GPEDM_ERR_CUDA && strstr(gpedm_last_error(), "mid-size batch: allocation of") != nullptr) {
+          // no room for the arena of this wave (other work holds the memory): one fit at a time through handles
+          cudaGetLastError();
+          rcw = 0;
+          for (int i : wave) {
+            const int r1 = run_one_fit(devs[g], descs[i], opts, &tmp[i]);
+            if (r1 != 0 && rcw == 0) rcw = r1;
+          }
+        }
         if (bytes > 32e9) {  // a very large arena is not left cached in the pool (other allocations may want the memory)
           cudaMemPool_t pool;
           if (cudaSetDevice(devs[g]) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, devs[g]) == cudaSuccess)

@@ -102,6 +102,35 @@ def test_lockstep_batch_of_larger_fits_matches_single_fits(gpu_lib):
         m.close()
 
 
+def test_lockstep_falls_back_to_single_handles_when_its_arena_cannot_be_allocated(gpu_lib):
+    """No room for the arena of a lockstep wave (other work holds the device memory): the fits go one at a time through
+    handles instead of failing the batch.  The allocation failure is forced in a child process
+    (GPEDM_TEST_MID_ALLOC_FAIL is read at library load)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = """
+import json, sys
+sys.path.insert(0, %r)
+import gpedm_b200 as G
+from gpedm_b200 import batch, synth
+probs = []
+for n, E, seed in [(300, 2, 91), (520, 3, 92)]:
+    Y, X = synth.embed(synth.ricker(n, seed), E, 1)
+    probs.append(dict(Y=Y, X=X, initparst=batch.default_initparst(E, True)))
+res = G.fit_batch(probs, ngpus=1, want_loo=True)
+print(json.dumps([dict(status=int(r["status"]), iter=int(r["iter"]), nll=float(r["nllpost"]).hex(), loo0=float(r["loo_mean"][0]).hex()) for r in res]))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for extra in ({}, {"GPEDM_TEST_MID_ALLOC_FAIL": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **extra), timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert all(o["status"] == 0 for o in outs[1])
+    assert outs[0] == outs[1]   # same kernels, same per-tile arithmetic: the two paths agree to the last bit at these sizes
+
+
 def test_mid_batch_reports_non_positive_definite_fit(gpu_lib):
     """One poisoned fit (NaN predictor) must be reported with its pivot and must not disturb the others."""
     probs = _problems()[:3]
