@@ -318,6 +318,8 @@ def run_ours(args):
                                       "nccl_gather_status_note": "0 = the library's ncclAllGather of the records ran and matched "
                                                                  "the host-delivered records; <0 = NCCL unavailable (records "
                                                                  "delivered from host memory)"}
+                except Exception as exc:  # an extra measurement must not take the bench line down (e.g. a launcher
+                    grid["inproc"] = {"error": repr(exc)}  # that shows each rank only its own device)
                 finally:  # never leave the other ranks waiting
                     store.set("gpedm_inproc_done", "1")
             else:
