@@ -48,7 +48,7 @@ constexpr int DAG_SMEM_BYTES = DAG_BAR_OFF + 2 * DAG_NS * 8;
 
 static_assert(DagCfg::MT == 8 && DagCfg::NT == 4, "the triangular variants below assume 64 x 32 warp tiles");
 enum DagTaskType { DAG_DIAG = 0, DAG_POTRF = 1, DAG_TRTRI = 2, DAG_LAUUM = 3 };
-constexpr int DAG_NFLAG = 5;  // flag arrays per fit (see DagFit::flags)
+constexpr int DAG_NFLAG = 6;  // flag arrays per fit (see DagFit::flags)
 
 // One factorisation problem.  A launch may carry the task lists of MANY independent fits (the lockstep
 // batch of mid-size fits, host_batch.cuh): their tasks are interleaved in one list, so a CTA that would
@@ -60,7 +60,8 @@ struct DagFit {
                   // partial sums of TRTRI tiles that are computed in pieces
   size_t ld;
   int nb, n_valid;
-  int* flags;     // DAG_NFLAG nb*nb int arrays: L final, X final, pieces done of L tile / X tile / S tile (zeroed per evaluation)
+  int* flags;     // DAG_NFLAG nb*nb int arrays: L final, X final, pieces done of L tile / X tile / S tile, column strips
+                  // stored of the chain tiles L(c+1, c) (zeroed per evaluation)
   double* logdet_part;
   int* info;
 };
@@ -70,6 +71,7 @@ struct DagArgs {
   const int4* tasks;  // {type | fit << 4, i, j, kt0 | kt1 << 10 | piece << 20 | last << 30}: k tiles [kt0, kt1) of the tile
   int ntasks;
   int* counter;       // next task to claim (zeroed per evaluation)
+  int strips;         // 1: the chain tile L(c+1, c) is handed to DIAG(c+1) in 32-column strips (see dag_strips_ready)
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -80,6 +82,15 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Strip hand-off on the Cholesky chain.  L(c+1, c) = T D_c^T is lower-triangular in D, so its 32-column strip s is
+// complete once the epilogue has consumed the D slabs k < 32 (s + 1): the two warps that own the strip store it and
+// add 1 to byte s of one packed counter, and DIAG(c+1) - whose last k tile is exactly this tile, as both operands -
+// streams k slabs 2 s, 2 s + 1 as soon as byte s reads 2.  The epilogue of the producer, the store of the tile and
+// the consumer's last k tile overlap instead of running one after the other (about a sixth of the chain step).
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool dag_strips_ready(const int* p, int shift) { return ((ld_acquire(p) >> shift) & 0xff) >= 2; }
 // One lane polls, the warp follows (__syncwarp orders the other lanes' later reads after the acquire).
 #ifdef GPEDM_TIMELINE
 #define DAG_TL(...) __VA_ARGS__
@@ -183,7 +194,7 @@ template <bool A_KMAJOR, bool B_KMAJOR, bool TRI = false>
 __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][2], DagRing& ring, double* sA, double* sB,
                                           const double* __restrict__ Ap, const double* __restrict__ Bp, size_t ld,
                                           int nkt, const int* fa, int fsa, const int* fb, int fsb, bool active,
-                                          int tid, int m0, int n0 DAG_TL(, unsigned long long& tl_wait, int tl_col = -1)) {
+                                          int tid, int m0, int n0, const int* strip DAG_TL(, unsigned long long& tl_wait, int tl_col = -1)) {
   using Cfg = DagCfg;
   constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, PREF = NS - 2;
   constexpr int SLAB_A = Cfg::SLAB_A, SLAB_B = Cfg::SLAB_B;
@@ -236,17 +247,37 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
     while (issued < want) {
       if (issued >= ready_slabs) {
         const int ktile = issued / SPT;
-        if (issued > kt) {
-          int ok = 0;
-          if (lane == 0) ok = ld_acquire(fa + ktile * fsa) & ld_acquire(fb + ktile * fsb);
-          ok = __shfl_sync(0xffffffffu, ok, 0);  // (also orders the other lanes' operand reads after the acquire)
-          if (!ok) break;
+        if (TRI && strip != nullptr && ktile == nkt - 1) {
+          // the chain tile, strip by strip (two slabs per 32-column strip); same peek / block rule as for whole tiles
+          const int sh = ((issued % SPT) >> 1) << 3;
+          if (issued > kt) {
+            int ok = 0;
+            if (lane == 0) ok = dag_strips_ready(strip, sh);
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            if (!ok) break;
+          } else {
+            if (lane == 0 && !dag_strips_ready(strip, sh)) {
+              DAG_TL(const unsigned long long w0 = tl_now();)
+              while (!dag_strips_ready(strip, sh)) __nanosleep(32);
+              DAG_TL(tl_wait += tl_now() - w0;)
+            }
+            __syncwarp();
+            DAG_TL(if (tl_col >= 0 && (issued % SPT) == 0) tl_mark(tl_now(), 20, tl_col);)
+          }
+          ready_slabs = (issued & ~1) + 2;
         } else {
-          warp_wait_flag(fa + ktile * fsa, lane DAG_TL(, tl_wait));
-          warp_wait_flag(fb + ktile * fsb, lane DAG_TL(, tl_wait));
-          DAG_TL(if (tl_col >= 0 && ktile == nkt - 1) tl_mark(tl_now(), 20, tl_col);)
+          if (issued > kt) {
+            int ok = 0;
+            if (lane == 0) ok = ld_acquire(fa + ktile * fsa) & ld_acquire(fb + ktile * fsb);
+            ok = __shfl_sync(0xffffffffu, ok, 0);  // (also orders the other lanes' operand reads after the acquire)
+            if (!ok) break;
+          } else {
+            warp_wait_flag(fa + ktile * fsa, lane DAG_TL(, tl_wait));
+            warp_wait_flag(fb + ktile * fsb, lane DAG_TL(, tl_wait));
+            DAG_TL(if (tl_col >= 0 && ktile == nkt - 1) tl_mark(tl_now(), 20, tl_col);)
+          }
+          ready_slabs = (ktile + 1) * SPT;
         }
-        ready_slabs = (ktile + 1) * SPT;
       }
       issue(issued);
       ++issued;
@@ -348,6 +379,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
     int* flagX = flagL + nb * nb;
     int* progL = flagX + nb * nb;
     int* progX = progL + nb * nb;
+    int* stripL = progX + 2 * nb * nb;  // (behind the S-tile piece counts)
     const int kt0 = tk.w & 1023, kt1 = (tk.w >> 10) & 1023, piece = (tk.w >> 20) & 1023;
     const bool last = (tk.w >> 30) & 1;
     DAG_TL(const unsigned long long tl_t0 = tl_now(); unsigned long long tl_wait = 0;)
@@ -399,7 +431,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       }
       DAG_TL(if (tl_ph) tl_mark(tl_now(), 30, type);)
       dag_kloop<true, true>(acc, ring, sA, sB, LAp, LBp, ld, kt1 - kt0, flagX + r0 * nb + ti, nb, flagX + r0 * nb + tj, nb, act,
-                            tid, m0, n0 DAG_TL(, tl_wait));
+                            tid, m0, n0, nullptr DAG_TL(, tl_wait));
       DAG_TL(if (tl_ph) tl_mark(tl_now(), 31, type);)
       if (act) {
 #pragma unroll
@@ -478,12 +510,14 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     }
     DAG_TL(if (tl_ph) tl_mark(tl_now(), 30, type);)
-    if (type == DAG_DIAG)
-      dag_kloop<false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, tid, km0, kn0 DAG_TL(, tl_wait, last ? tj : -1));
-    else if (!is_trtri)
-      dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0 DAG_TL(, tl_wait));
+    if (type == DAG_DIAG) {
+      // the last k tile of the last piece is the chain tile L(tj, tj - 1): taken strip by strip as its producer stores it
+      const int* strip = (a.strips && last && kt1 == tj && nkt > 0) ? stripL + tj * nb + (tj - 1) : nullptr;
+      dag_kloop<false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, tid, km0, kn0, strip DAG_TL(, tl_wait, last ? tj : -1));
+    } else if (!is_trtri)
+      dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, nullptr DAG_TL(, tl_wait));
     else
-      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0 DAG_TL(, tl_wait));
+      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, nullptr DAG_TL(, tl_wait));
     DAG_TL(if (tl_ph) tl_mark(tl_now(), 31, type);)
     if (!is_trtri) {  // back from the negated accumulation
 #pragma unroll
@@ -611,6 +645,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
     const int em0 = is_trtri ? m0t : m0, en0 = is_trtri ? n0 : n0p;  // balanced warp tile maps of the epilogue
     const int dblk = is_trtri ? ti : tj;
     const double* Dg = f.X + (size_t)dblk * TB * (ld + 1);
+    // chain tile: every warp stores its 32-column strip as soon as the D slabs that reach it are consumed (dag_strips_ready)
+    const bool chain_strips = a.strips && !is_trtri && ti == tj + 1;
     warp_wait_flag(flagX + dblk * nb + dblk, lane DAG_TL(, tl_wait));
     DAG_TL(if (!is_trtri && ti == tj + 1) tl_mark(tl_now(), 11, tj);)
     auto issue_e = [&](int j) {
@@ -679,16 +715,31 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       __syncwarp();
       if (lane == 0) mbar_arrive_s(ring.empty(s));
       ring.gc++;
+      if (chain_strips && kt == (en0 >> 4) + 1) {  // columns [en0, en0 + 32) take D slabs k < en0 + 32 only
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Cg[(size_t)(em0 + 8 * i + g) + (size_t)(en0 + 8 * j + 2 * t + e) * ld] = acc[i][j][e];
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          red_release_add(stripL + ti * nb + tj, 1 << ((en0 >> 5) << 3));
+        }
+      }
     }
     DAG_TL(if (!is_trtri && ti == tj + 1) tl_mark(tl_now(), 12, tj);)
     DAG_TL(if (tl_ph) tl_mark(tl_now(), 33, type);)
+    if (!chain_strips) {
 #pragma unroll
-    for (int i = 0; i < MT; ++i)
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
-      for (int j = 0; j < NT; ++j)
+        for (int j = 0; j < NT; ++j)
 #pragma unroll
-        for (int e = 0; e < 2; ++e)  // TRTRI: X_ij = -(D_i T), the sign applied here instead of on every D fragment
-          Cg[(size_t)(em0 + 8 * i + g) + (size_t)(en0 + 8 * j + 2 * t + e) * ld] = is_trtri ? -acc[i][j][e] : acc[i][j][e];
+          for (int e = 0; e < 2; ++e)  // TRTRI: X_ij = -(D_i T), the sign applied here instead of on every D fragment
+            Cg[(size_t)(em0 + 8 * i + g) + (size_t)(en0 + 8 * j + 2 * t + e) * ld] = is_trtri ? -acc[i][j][e] : acc[i][j][e];
+    }
     __syncthreads();  // all stores of the tile issued; T is free again for the next task's ring
     if (tid == 0) {
       __threadfence();

@@ -81,6 +81,8 @@ static const bool g_no_dag = getenv("GPEDM_NO_DAG") != nullptr && atoi(getenv("G
 static const int g_dag_lead = getenv("GPEDM_DAG_LEAD") ? std::max(0, atoi(getenv("GPEDM_DAG_LEAD"))) : 1;
 // k tiles per piece of a long tile (512 = never split)
 static const int g_dag_chunk = getenv("GPEDM_DAG_CHUNK") ? std::min(512, std::max(1, atoi(getenv("GPEDM_DAG_CHUNK")))) : 512;
+// chain tile L(c+1, c) handed to DIAG(c+1) in 32-column strips (dag_factor.cuh); GPEDM_DAG_NO_STRIPS=1: whole tile + flag
+static const bool g_dag_strips = !(getenv("GPEDM_DAG_NO_STRIPS") != nullptr && atoi(getenv("GPEDM_DAG_NO_STRIPS")) != 0);
 static const int g_dag_lag = getenv("GPEDM_DAG_LAG") ? std::max(1, atoi(getenv("GPEDM_DAG_LAG"))) : 2;
 // Sigma^-1 = X^T X tiles summed in pieces of this many block rows, interleaved with the factorisation (0 = whole
 // tiles after it, the default: interleaved pieces were measured SLOWER at every size - 4086 rows 3.38 -> 3.66 ms

@@ -1,0 +1,31 @@
+#!/bin/bash
+# A/B of the strip hand-off on the Cholesky chain (dag_factor.cuh) and of the epilogue prefetch depth, one B200:
+# evaluation time per size with the results' bits, chain timeline, parity subset, lockstep batch rate.
+O=gpurun_out
+SIZES="512 1024 2048 3072 4096 6144 8192"
+for cfg in "" "GPEDM_DAG_NO_STRIPS=1" "GPEDM_DAG_EPREF=3" "GPEDM_DAG_NO_STRIPS=1 GPEDM_DAG_EPREF=3"; do
+  env $cfg timeout -k 5 150 python tools/dag_sweep.py $SIZES; echo "sweep [$cfg] rc=$?"
+done > $O/r02h_strips_sweep.jsonl 2>&1
+cut -c1-140 $O/r02h_strips_sweep.jsonl
+python - <<'PY'
+import json
+ref = {}
+for l in open('profiles/r02_size_sweep_v5.jsonl'):
+    if l.startswith('{'):
+        r = json.loads(l); ref[r['N']] = r
+bad = 0
+for l in open('gpurun_out/r02h_strips_sweep.jsonl'):
+    if l.startswith('{'):
+        r = json.loads(l); o = ref.get(r['N'])
+        if o is not None and (o['nll'], o['g0']) != (r['nll'], r['g0']):
+            bad += 1; print('DIFFERENT BITS', r['env'], r['N'])
+print('bit check vs r02_size_sweep_v5: %d differences' % bad)
+PY
+timeout -k 5 120 python tools/dag_timeline.py 4096 256 > $O/r02h_dag_timeline_n4086_strips.txt 2>&1; echo "timeline rc=$?"; tail -22 $O/r02h_dag_timeline_n4086_strips.txt
+timeout -k 5 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_midbatch.py -m gpu -x -q -k "likegrad or K1 or mid or lockstep or sequential" 2>&1 | tail -4
+for cfg in "" "GPEDM_DAG_NO_STRIPS=1"; do
+  env $cfg timeout -k 5 120 python tools/mid_batch_bench.py 1000 128 | sed "s/^{/{\"cfg\": \"$cfg\", /"
+  env $cfg timeout -k 5 120 python tools/mid_batch_bench.py 3000 24 | sed "s/^{/{\"cfg\": \"$cfg\", /"
+done > $O/r02h_mid_batch_strips.jsonl 2>&1
+cut -c1-260 $O/r02h_mid_batch_strips.jsonl
+echo done
