@@ -72,6 +72,8 @@ struct DagArgs {
   int ntasks;
   int* counter;       // next task to claim (zeroed per evaluation)
   int strips;         // 1: the chain tile L(c+1, c) is handed to DIAG(c+1) in 32-column strips (see dag_strips_ready)
+  int trsm;           // t > 0 (needs strips): the tiles L(c+1 .. c+t, c) are SOLVED against the block columns of L_cc as DIAG(c)
+                      // publishes them (dag_trsm_chain) instead of multiplied by D_c = L_cc^-1 once that is complete
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -100,6 +102,15 @@ __device__ __forceinline__ bool dag_strips_ready(const int* p, int shift) { retu
 #ifdef GPEDM_TIMELINE
 // chain marks: extra timeline records {time, time, smid, 150 | mark << 8 | column << 20} logged by thread 0 of the
 // two chain tasks of a block column (DIAG(c), POTRF(c+1, c)); tools/dag_timeline.py prints the per-step breakdown
+__device__ __forceinline__ void tl_mark_any(unsigned long long t, int mark, int col) {
+  const unsigned int i = atomicAdd(&g_tl_count, 1u);
+  if (i < TL_MAX) {
+    g_tl_rec[4 * i] = t;
+    g_tl_rec[4 * i + 1] = t;
+    g_tl_rec[4 * i + 2] = tl_smid();
+    g_tl_rec[4 * i + 3] = 150ull | ((unsigned long long)mark << 8) | ((unsigned long long)col << 20);
+  }
+}
 __device__ __forceinline__ void tl_mark(unsigned long long t, int mark, int col) {
   if (threadIdx.x == 0) {
     const unsigned int i = atomicAdd(&g_tl_count, 1u);
@@ -183,6 +194,141 @@ __device__ __forceinline__ void load_slab_s(uint32_t s, const double* __restrict
   }
 }
 
+// DIAG(c) side of the chain solve: block column q of L_cc (rows >= 32 q, 32 columns, upper part of the diagonal block
+// zeroed) goes to the L tile in global memory as soon as it is final, and `prog` counts the block columns published.
+struct DagPublishL {
+  const double* T;
+  double* Lg;
+  size_t ld;
+  int* prog;
+  bool on;
+  int col;
+  __device__ __forceinline__ void copy(int q, int first, int nthr) const {
+    for (int idx = first; idx < (4 - q) * 512; idx += nthr) {
+      const int b = idx >> 9, e = idx & 511;
+      const int r = 32 * (q + b) + 2 * (e & 15), c = 32 * q + (e >> 4);
+      double2 v = *reinterpret_cast<const double2*>(&T[r + c * DG_LD]);
+      if (b == 0) {
+        if (r < c) v.x = 0.0;
+        if (r + 1 < c) v.y = 0.0;
+      }
+      *reinterpret_cast<double2*>(&Lg[(size_t)r + (size_t)c * ld]) = v;
+    }
+  }
+  // warps 1 .. 7, while warp 0 factors the next diagonal block: store, meet at a named barrier, one thread flags
+  __device__ __forceinline__ void background(int q) const {
+    if (!on) return;
+    DAG_TL(if (threadIdx.x == 32) tl_mark_any(tl_now(), 40 + q, col);)
+    copy(q, (int)threadIdx.x - 32, DAG_THREADS - 32);
+    asm volatile("bar.sync 1, %0;" ::"n"(DAG_THREADS - 32) : "memory");
+    if (threadIdx.x == 32) {
+      st_release(prog, q + 1);
+      DAG_TL(tl_mark_any(tl_now(), 44 + q, col);)
+    }
+  }
+  __device__ __forceinline__ void store(int q) const {
+    if (!on) return;
+    DAG_TL(tl_mark(tl_now(), 40 + q, col);)
+    copy(q, (int)threadIdx.x, DAG_THREADS);
+  }
+  __device__ __forceinline__ void flag(int q) const {  // (after a CTA barrier that follows store(q))
+    if (on && threadIdx.x == 0) {
+      st_release(prog, q + 1);
+      DAG_TL(tl_mark(tl_now(), 44 + q, col);)
+    }
+  }
+};
+
+// POTRF(c+1, c) side: L(c+1, c) = T L_cc^-T by blocked forward substitution, one 32-column strip per block column of
+// L_cc, each started as soon as DIAG(c) has published that block column - so the tile is complete one 32-wide solve
+// after the Cholesky of L_cc instead of after its inverse, the store of D_c and a 128^3 product.  (Same operation as
+// LAPACK dtrsm; the other tiles of the column are off the chain and keep the product with D_c.)
+//   T   resident tile in shared memory (128 x DG_LD), overwritten with L(c+1, c)
+//   Lq  scratch for the staged block column (128 x 32, stride DG_LD) + 32 reciprocals
+// Every strip is stored and counted for DIAG(c+1) as it completes (dag_strips_ready).
+__device__ __noinline__ void dag_trsm_chain(double* T, double* Lq, const double* Lcc, size_t ld, double* Cg, const int* prog, int* strip, int col) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  double* rdv = Lq + 32 * DG_LD;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    const int base = 32 * q;
+    if (lane == 0) {
+      while (ld_acquire(prog) <= q) __nanosleep(32);
+    }
+    __syncwarp();
+    DAG_TL(if (col >= 0 && q == 0) tl_mark(tl_now(), 50 + q, col);)
+    for (int idx = tid; idx < (4 - q) * 512; idx += DAG_THREADS) {
+      const int b = idx >> 9, e = idx & 511;
+      const int r = base + 32 * b + 2 * (e & 15), c = e >> 4;
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(Lcc + (size_t)r + (size_t)(base + c) * ld));
+      *reinterpret_cast<double2*>(&Lq[r + c * DG_LD]) = v;
+    }
+    __syncthreads();
+    if (tid < 32) rdv[tid] = 1.0 / Lq[(base + tid) + tid * DG_LD];
+    __syncthreads();
+    if (warp < 4) {  // forward substitution, lane = row (as the panel step of diag_cholesky_smem)
+      const int row = 32 * warp + lane;
+      double a[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = T[row + (base + c) * DG_LD];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const double x = a[c] * rdv[c];
+        a[c] = x;
+        const double* lcol = Lq + base + c * DG_LD;  // column c of the diagonal block, contiguous
+#pragma unroll
+        for (int c2 = ((c + 1) & ~1); c2 < 32; c2 += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(lcol + c2);
+          if (c2 > c) a[c2] = fma(-x, v.x, a[c2]);
+          a[c2 + 1] = fma(-x, v.y, a[c2 + 1]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) T[row + (base + c) * DG_LD] = a[c];
+    }
+    __syncthreads();
+    // strip q is final: to global memory for DIAG(c+1) and everybody else
+    for (int idx = tid; idx < 4 * 512; idx += DAG_THREADS) {
+      const int r = 2 * (idx & 63), c = base + (idx >> 6);
+      *reinterpret_cast<double2*>(&Cg[(size_t)r + (size_t)c * ld]) = *reinterpret_cast<const double2*>(&T[r + c * DG_LD]);
+    }
+    // columns right of the strip: T[:, n] -= X_q L_cc[n, strip]^T, 32 x 8 pieces (four DMMA chains per warp)
+    for (int u = warp; u < 16 * (3 - q); u += DAG_THREADS / 32) {
+      const int row0 = 32 * (u & 3), col0 = base + 32 + 8 * (u >> 2);
+      double c[4][2];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double* cp = T + (row0 + 8 * r + g) + (col0 + 2 * t) * DG_LD;
+        c[r][0] = cp[0];
+        c[r][1] = cp[DG_LD];
+      }
+      const double* ap = T + (row0 + g) + (base + t) * DG_LD;
+      const double* bp = Lq + (col0 + g) + t * DG_LD;
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        const double b = bp[0];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) dmma884(c[r][0], c[r][1], -ap[8 * r], b);
+        ap += 4 * DG_LD;
+        bp += 4 * DG_LD;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        double* cp = T + (row0 + 8 * r + g) + (col0 + 2 * t) * DG_LD;
+        cp[0] = c[r][0];
+        cp[DG_LD] = c[r][1];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      red_release_add(strip, 2 << (8 * q));
+      DAG_TL(if (col >= 0) tl_mark(tl_now(), 58 + q, col);)
+    }
+  }
+}
+
 // The k loop of one task: acc (+)= (+/-) sum over `nkt` 128-wide k tiles of A B, operands streamed through the
 // mbarrier ring (see gemm_tile_mb in dgemm_tile.cuh).  A is MN-major; B is MN-major (Cholesky) or K-major
 // (inverse).  Operand tile kt is final once fa[kt] / fb[kt * fsb] are set.  Most of them already are when
@@ -190,11 +336,11 @@ __device__ __forceinline__ void load_slab_s(uint32_t s, const double* __restrict
 // the first unset flag are polled as the loop reaches them - the ones right behind the chain.
 // TRI (diagonal tiles of the Cholesky): the warp tile sits at (m0, n0) of a symmetric tile of which only the lower
 // part is used, so the 8 x 8 blocks strictly above the diagonal are skipped.
-template <bool A_KMAJOR, bool B_KMAJOR, bool TRI = false>
+template <bool A_KMAJOR, bool B_KMAJOR, bool TRI = false, bool STRIPS = false>
 __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][2], DagRing& ring, double* sA, double* sB,
                                           const double* __restrict__ Ap, const double* __restrict__ Bp, size_t ld,
                                           int nkt, const int* fa, int fsa, const int* fb, int fsb, bool active,
-                                          int tid, int m0, int n0, const int* strip DAG_TL(, unsigned long long& tl_wait, int tl_col = -1)) {
+                                          int tid, int m0, int n0, const int* stripa, const int* stripb DAG_TL(, unsigned long long& tl_wait, int tl_col = -1)) {
   using Cfg = DagCfg;
   constexpr int MT = Cfg::MT, NT = Cfg::NT, BK = Cfg::BK, NS = Cfg::NSTAGE, PREF = NS - 2;
   constexpr int SLAB_A = Cfg::SLAB_A, SLAB_B = Cfg::SLAB_B;
@@ -247,18 +393,18 @@ __device__ __forceinline__ void dag_kloop(double (&acc)[DagCfg::MT][DagCfg::NT][
     while (issued < want) {
       if (issued >= ready_slabs) {
         const int ktile = issued / SPT;
-        if (TRI && strip != nullptr && ktile == nkt - 1) {
-          // the chain tile, strip by strip (two slabs per 32-column strip); same peek / block rule as for whole tiles
+        if (STRIPS && stripa != nullptr && ktile == nkt - 1) {
+          // tiles that are produced strip by strip (two slabs per 32-column strip); same peek / block rule as for whole tiles
           const int sh = ((issued % SPT) >> 1) << 3;
           if (issued > kt) {
             int ok = 0;
-            if (lane == 0) ok = dag_strips_ready(strip, sh);
+            if (lane == 0) ok = dag_strips_ready(stripa, sh) && dag_strips_ready(stripb, sh);
             ok = __shfl_sync(0xffffffffu, ok, 0);
             if (!ok) break;
           } else {
-            if (lane == 0 && !dag_strips_ready(strip, sh)) {
+            if (lane == 0 && !(dag_strips_ready(stripa, sh) && dag_strips_ready(stripb, sh))) {
               DAG_TL(const unsigned long long w0 = tl_now();)
-              while (!dag_strips_ready(strip, sh)) __nanosleep(32);
+              while (!(dag_strips_ready(stripa, sh) && dag_strips_ready(stripb, sh))) __nanosleep(32);
               DAG_TL(tl_wait += tl_now() - w0;)
             }
             __syncwarp();
@@ -431,7 +577,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       }
       DAG_TL(if (tl_ph) tl_mark(tl_now(), 30, type);)
       dag_kloop<true, true>(acc, ring, sA, sB, LAp, LBp, ld, kt1 - kt0, flagX + r0 * nb + ti, nb, flagX + r0 * nb + tj, nb, act,
-                            tid, m0, n0, nullptr DAG_TL(, tl_wait));
+                            tid, m0, n0, nullptr, nullptr DAG_TL(, tl_wait));
       DAG_TL(if (tl_ph) tl_mark(tl_now(), 31, type);)
       if (act) {
 #pragma unroll
@@ -510,14 +656,18 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     }
     DAG_TL(if (tl_ph) tl_mark(tl_now(), 30, type);)
+    // The last k tile (block column tj - 1) of a Cholesky task is taken strip by strip when its operand tiles are
+    // produced that way: the chain tile L(tj, tj - 1) with the strips on, L(ti, tj - 1) if it is solved (dag_trsm_chain).
+    const bool last_col = last && kt1 == tj && nkt > 0;
     if (type == DAG_DIAG) {
-      // the last k tile of the last piece is the chain tile L(tj, tj - 1): taken strip by strip as its producer stores it
-      const int* strip = (a.strips && last && kt1 == tj && nkt > 0) ? stripL + tj * nb + (tj - 1) : nullptr;
-      dag_kloop<false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, tid, km0, kn0, strip DAG_TL(, tl_wait, last ? tj : -1));
-    } else if (!is_trtri)
-      dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, nullptr DAG_TL(, tl_wait));
-    else
-      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, nullptr DAG_TL(, tl_wait));
+      const int* strip = (a.strips && last_col) ? stripL + tj * nb + (tj - 1) : nullptr;
+      dag_kloop<false, false, true, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, tid, km0, kn0, strip, strip DAG_TL(, tl_wait, last ? tj : -1));
+    } else if (!is_trtri) {
+      const bool by_strips = last_col && ti - (tj - 1) <= a.trsm;
+      dag_kloop<false, false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0,
+                                           by_strips ? stripL + ti * nb + (tj - 1) : nullptr, by_strips ? stripL + tj * nb + (tj - 1) : nullptr DAG_TL(, tl_wait));
+    } else
+      dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, nullptr, nullptr DAG_TL(, tl_wait));
     DAG_TL(if (tl_ph) tl_mark(tl_now(), 31, type);)
     if (!is_trtri) {  // back from the negated accumulation
 #pragma unroll
@@ -564,7 +714,9 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       double* dvec = rdiag + TB;
       double* colbuf = dvec + TB;
       DAG_TL(tl_mark(tl_now(), 1, tj);)
-      diag_cholesky_smem<DAG_THREADS>(T, rdiag, dvec, colbuf, tj, f.n_valid, f.info);
+      const bool trsm = a.trsm != 0;  // the next panel tile is solved against the block columns of L_jj as they complete
+      const DagPublishL pub{T, Cg, ld, stripL + tj * nb + tj, trsm, tj};
+      diag_cholesky_smem<DAG_THREADS, DagPublishL>(T, rdiag, dvec, colbuf, tj, f.n_valid, f.info, pub);
       DAG_TL(tl_mark(tl_now(), 2, tj);)
       auto lower_block_elem = [](int idx, int& r, int& c, bool& on_diag) {
         const int b = idx >> 9, e = idx & 511;
@@ -578,21 +730,24 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       // the flag is released; L_jj and the log-determinant part follow off the critical path.
       constexpr int LPT = 10 * 512 / DAG_THREADS;  // double2 per thread: the 10 lower 32 x 32 blocks
       double2 lreg[LPT];
+      if (!trsm) {
 #pragma unroll
-      for (int q = 0; q < LPT; ++q) {
-        int r, c;
-        bool dg;
-        lower_block_elem(tid + q * DAG_THREADS, r, c, dg);
-        double2 v = *reinterpret_cast<const double2*>(&T[r + c * DG_LD]);
-        if (dg) {
-          if (r < c) v.x = 0.0;
-          if (r + 1 < c) v.y = 0.0;
+        for (int q = 0; q < LPT; ++q) {
+          int r, c;
+          bool dg;
+          lower_block_elem(tid + q * DAG_THREADS, r, c, dg);
+          double2 v = *reinterpret_cast<const double2*>(&T[r + c * DG_LD]);
+          if (dg) {
+            if (r < c) v.x = 0.0;
+            if (r + 1 < c) v.y = 0.0;
+          }
+          lreg[q] = v;
         }
-        lreg[q] = v;
       }
-      double lv = 0.0;
-      if (tid < TB && tj * TB + tid < f.n_valid) lv = log(dvec[tid]);
       __syncthreads();
+      pub.flag(3);  // (the last block column was stored before this barrier)
+      double lv = 0.0;  // (dvec is not touched by the inverse)
+      if (tid < TB && tj * TB + tid < f.n_valid) lv = log(dvec[tid]);
       DAG_TL(tl_mark(tl_now(), 3, tj);)
       diag_invert_smem<DAG_THREADS>(T, w, rdiag);
       DAG_TL(tl_mark(tl_now(), 4, tj);)
@@ -615,12 +770,14 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
         st_release(flagX + tj * nb + tj, 1);
       }
       DAG_TL(tl_mark(tl_now(), 5, tj);)
+      if (!trsm) {  // (published block column by block column otherwise)
 #pragma unroll
-      for (int q = 0; q < LPT; ++q) {
-        int r, c;
-        bool dg;
-        lower_block_elem(tid + q * DAG_THREADS, r, c, dg);
-        *reinterpret_cast<double2*>(&Cg[(size_t)r + (size_t)c * ld]) = lreg[q];
+        for (int q = 0; q < LPT; ++q) {
+          int r, c;
+          bool dg;
+          lower_block_elem(tid + q * DAG_THREADS, r, c, dg);
+          *reinterpret_cast<double2*>(&Cg[(size_t)r + (size_t)c * ld]) = lreg[q];
+        }
       }
       if (tid < TB) {
 #pragma unroll
@@ -638,6 +795,15 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       continue;
     }
 
+    if (!is_trtri && ti - tj <= a.trsm) {
+      // ---------------- chain tile (and the tiles right below it, which the next column's chain tile needs first):
+      // solved against L_jj block column by block column (dag_trsm_chain), handed on strip by strip
+      dag_trsm_chain(T, sE, f.A + (size_t)tj * TB * (ld + 1), ld, Cg, stripL + tj * nb + tj, stripL + ti * nb + tj, ti == tj + 1 ? tj : -1);
+      if (tid == 0) st_release(flagL + ti * nb + tj, 1);  // (behind the barrier and fence of the last strip)
+      DAG_TL(tl_mark(tl_now(), 13, tj);)
+      DAG_TL(tl_log(tl_t0, (200 + type) | ((long long)ti << 8) | ((long long)tj << 20) | ((long long)nkt << 32) | ((long long)(tl_wait > 0xfffff ? 0xfffff : tl_wait) << 44));)
+      continue;
+    }
     // ---------------- epilogue product against the diagonal-block inverse
     //   POTRF: C = T D_j^T   (A operand = T resident, B operand = D_j streamed, B[k][n] = D_j[n][k])
     //   TRTRI: C = -D_i T    (A operand = D_i streamed,  B operand = T resident)

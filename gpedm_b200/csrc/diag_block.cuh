@@ -192,9 +192,19 @@ __device__ __noinline__ void chol32_warp(double* s, double* rdiag, double* dvec,
 // the part above the diagonal is left undefined except inside the 32x32 diagonal blocks, which are
 // zeroed).  rdiag <- 1/L_jj, dvec <- L_jj.  All NTHR threads of the CTA must call it (NTHR = 512 in the
 // standalone diagonal-block / small-fit kernels, 256 inside the persistent factorisation kernel).
-template <int NTHR = DG_THREADS>
+// `pub` lets the caller hand block columns of L on as they become final (the persistent factorisation kernel
+// publishes them to the CTAs that solve the next panel tiles against them).  Block column q < 3 (rows >= 32 q, 32
+// columns) is final when phase B of step q starts: pub.background(q) is called there by warps 1 .. NW-1 only, so the
+// stores, the fence and the flag never sit in front of warp 0, which factors the next diagonal block meanwhile.
+// pub.store(3) is called by ALL threads at the end; the caller raises the flag after its next CTA barrier.
+struct DiagNoPublish {
+  __device__ __forceinline__ void background(int) const {}
+  __device__ __forceinline__ void store(int) const {}
+  __device__ __forceinline__ void flag(int) const {}
+};
+template <int NTHR = DG_THREADS, class Pub = DiagNoPublish>
 __device__ __forceinline__ void diag_cholesky_smem(double* s, double* rdiag, double* dvec, double* colbuf, int kblock,
-                                                   int n_valid, int* info) {
+                                                   int n_valid, int* info, const Pub pub = Pub()) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   constexpr int NW = NTHR / 32;
@@ -244,6 +254,7 @@ __device__ __forceinline__ void diag_cholesky_smem(double* s, double* rdiag, dou
     if (warp == 0) {
       chol32_warp(s, rdiag, dvec, colbuf, base + 32, lane, kblock, n_valid, info);
     } else {
+      pub.background(kb);
       const int m = 2 - kb;                     // block rows below the next diagonal block
       const int nblk = m * (m + 3) / 2;         // blocks (bi, bj), bi in 1..m, bj in 0..bi  (relative to kb+1)
       for (int q = warp - 1; q < nblk * 16; q += NW - 1) {
@@ -262,7 +273,7 @@ __device__ __forceinline__ void diag_cholesky_smem(double* s, double* rdiag, dou
     __syncthreads();
     DG_TS(5 + 3 * kb);
   }
-
+  pub.store(3);
 }
 
 // In-place inverse of the lower-triangular factor held in `s` (needs rdiag from diag_cholesky_smem):

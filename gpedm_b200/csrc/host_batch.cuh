@@ -532,6 +532,7 @@ static int fit_batch_mid(int device, const std::vector<int>& idx, const gpedm_fi
     da.ntasks = (int)tasks.size();
     da.counter = (int*)(base + counter_off);
     da.strips = g_dag_strips ? 1 : 0;
+    da.trsm = g_dag_trsm;
     dag_factor_kernel<<<std::min(sms, da.ntasks), DAG_THREADS, DAG_SMEM_BYTES, st>>>(da);
     mid_trmv_n_kernel<<<(unsigned)mapT.size(), 256, 0, st>>>(F, (const int2*)dMapT.p);
     mid_reduce_kernel<<<(unsigned)mapV.size(), 256, 0, st>>>(F, (const int2*)dMapV.p, 0);

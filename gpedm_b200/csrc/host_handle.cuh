@@ -83,6 +83,11 @@ static const int g_dag_lead = getenv("GPEDM_DAG_LEAD") ? std::max(0, atoi(getenv
 static const int g_dag_chunk = getenv("GPEDM_DAG_CHUNK") ? std::min(512, std::max(1, atoi(getenv("GPEDM_DAG_CHUNK")))) : 512;
 // chain tile L(c+1, c) handed to DIAG(c+1) in 32-column strips (dag_factor.cuh); GPEDM_DAG_NO_STRIPS=1: whole tile + flag
 static const bool g_dag_strips = !(getenv("GPEDM_DAG_NO_STRIPS") != nullptr && atoi(getenv("GPEDM_DAG_NO_STRIPS")) != 0);
+// Tiles L(c+1 .. c+t, c) are SOLVED against the block columns of L_cc as DIAG(c) publishes them (dag_trsm_chain) instead of
+// multiplied by D_c once the inverse is complete, and handed on strip by strip.  GPEDM_DAG_TRSM=t; 0: product with D_c
+// everywhere.  Measured (profiles/r02_trsm_depth.jsonl): the gain saturates at t = 6 .. 8 (N = 2038: 1.074 ms with 0,
+// 0.893 with 2, 0.826 with 4, 0.813 with 6 and beyond); N >= 8182 is indifferent to t.
+static const int g_dag_trsm = !g_dag_strips ? 0 : (getenv("GPEDM_DAG_TRSM") ? std::max(0, atoi(getenv("GPEDM_DAG_TRSM"))) : 6);
 static const int g_dag_lag = getenv("GPEDM_DAG_LAG") ? std::max(1, atoi(getenv("GPEDM_DAG_LAG"))) : 2;
 // Sigma^-1 = X^T X tiles summed in pieces of this many block rows, interleaved with the factorisation (0 = whole
 // tiles after it, the default: interleaved pieces were measured SLOWER at every size - 4086 rows 3.38 -> 3.66 ms

@@ -143,6 +143,7 @@ static int enqueue_eval_raw(gpedm_fit_s* h, bool full, bool through_z_only) {
     da.ntasks = through_z_only ? h->ntasks_factor : h->ntasks;
     da.counter = h->dsync;
     da.strips = g_dag_strips ? 1 : 0;
+    da.trsm = g_dag_trsm;
     dag_factor_kernel<<<std::min(h->num_sms, da.ntasks), DAG_THREADS, DAG_SMEM_BYTES, st>>>(da);
     h->launches++;
     CU(record_phase_event(h->ev[2], st));

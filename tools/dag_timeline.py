@@ -79,7 +79,7 @@ for k in range(4):
               % (names[k], msk.sum(), coef[0], coef[1], np.sqrt((resid ** 2).mean()), coef[0] * (typ == k).sum() * 1e-3, coef[1] * nkt[typ == k].sum() * 1e-3))
 # phase marks (every 4th task, thread 0): 30 k loop entered, 31 k loop left, 32 resident tile in smem, 33 epilogue
 # product done; matched to the task record of the same SM that encloses them
-pm = marks[((marks[:, 3] >> 8) & 0xff) >= 30]
+pm = marks[(((marks[:, 3] >> 8) & 0xff) >= 30) & (((marks[:, 3] >> 8) & 0xff) < 40)]
 if len(pm):
     ph = {}
     by_sm = {}
@@ -144,3 +144,14 @@ if len(marks):
             if not label.startswith("  "):
                 tot += float(np.median(v))
     print("  %-42s %7.2f" % ("sum of medians", tot))
+
+# ---- raw chain marks of one block column (DAG_TL_DUMP=c): every mark of columns c and c + 1, relative to the first
+if os.environ.get("DAG_TL_DUMP") and len(marks):
+    c0 = int(os.environ["DAG_TL_DUMP"])
+    rows = [((tm - t0) * 1e-3, int((cd >> 20) & 0xfff), int((cd >> 8) & 0xff)) for tm, _, _, cd in marks
+            if int((cd >> 20) & 0xfff) in (c0, c0 + 1) and int((cd >> 8) & 0xff) < 30 or
+            (int((cd >> 20) & 0xfff) in (c0, c0 + 1) and 40 <= int((cd >> 8) & 0xff) < 64)]
+    rows.sort()
+    print("\nmarks of columns %d, %d (us after the first; column, mark):" % (c0, c0 + 1))
+    for tm, c, m_ in rows:
+        print("  %8.2f  c=%d  mark %d" % (tm - rows[0][0], c, m_))
