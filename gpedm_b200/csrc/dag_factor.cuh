@@ -246,7 +246,7 @@ struct DagPublishL {
 //   T   resident tile in shared memory (128 x DG_LD), overwritten with L(c+1, c)
 //   Lq  scratch for the staged block column (128 x 32, stride DG_LD) + 32 reciprocals
 // Every strip is stored and counted for DIAG(c+1) as it completes (dag_strips_ready).
-__device__ __noinline__ void dag_trsm_chain(double* T, double* Lq, const double* Lcc, size_t ld, double* Cg, const int* prog, int* strip, int col) {
+__device__ __forceinline__ void dag_trsm_chain(double* T, double* Lq, const double* Lcc, size_t ld, double* Cg, const int* prog, int* strip, int col) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   double* rdv = Lq + 32 * DG_LD;
@@ -663,9 +663,12 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       const int* strip = (a.strips && last_col) ? stripL + tj * nb + (tj - 1) : nullptr;
       dag_kloop<false, false, true, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, active, tid, km0, kn0, strip, strip DAG_TL(, tl_wait, last ? tj : -1));
     } else if (!is_trtri) {
-      const bool by_strips = last_col && ti - (tj - 1) <= a.trsm;
-      dag_kloop<false, false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0,
-                                           by_strips ? stripL + ti * nb + (tj - 1) : nullptr, by_strips ? stripL + tj * nb + (tj - 1) : nullptr DAG_TL(, tl_wait));
+      // (two instances: the strip logic stays out of the loop that all the other Cholesky tiles run)
+      if (last_col && ti - (tj - 1) <= a.trsm)
+        dag_kloop<false, false, false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0,
+                                             stripL + ti * nb + (tj - 1), stripL + tj * nb + (tj - 1) DAG_TL(, tl_wait));
+      else
+        dag_kloop<false, false>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, nullptr, nullptr DAG_TL(, tl_wait));
     } else
       dag_kloop<false, true>(acc, ring, sA, sB, Ap, Bp, ld, nkt, fa, fsa, fb, fsb, true, tid, km0, kn0, nullptr, nullptr DAG_TL(, tl_wait));
     DAG_TL(if (tl_ph) tl_mark(tl_now(), 31, type);)
@@ -729,25 +732,26 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) dag_factor_kernel(const DagArg
       // diagonal tile of L): L_jj is parked in registers, the in-place inverse and the store of D_j go first and
       // the flag is released; L_jj and the log-determinant part follow off the critical path.
       constexpr int LPT = 10 * 512 / DAG_THREADS;  // double2 per thread: the 10 lower 32 x 32 blocks
-      double2 lreg[LPT];
-      if (!trsm) {
-#pragma unroll
-        for (int q = 0; q < LPT; ++q) {
-          int r, c;
-          bool dg;
-          lower_block_elem(tid + q * DAG_THREADS, r, c, dg);
-          double2 v = *reinterpret_cast<const double2*>(&T[r + c * DG_LD]);
-          if (dg) {
-            if (r < c) v.x = 0.0;
-            if (r + 1 < c) v.y = 0.0;
-          }
-          lreg[q] = v;
-        }
-      }
       __syncthreads();
       pub.flag(3);  // (the last block column was stored before this barrier)
-      double lv = 0.0;  // (dvec is not touched by the inverse)
+      // (L_jj is parked in either mode: making this conditional moves the array to local memory and costs the k loops
+      // of every task type registers - measured in the SASS, 576 -> 613 instructions per slab in the X^T X loop)
+      double2 lreg[LPT];
+#pragma unroll
+      for (int q = 0; q < LPT; ++q) {
+        int r, c;
+        bool dg;
+        lower_block_elem(tid + q * DAG_THREADS, r, c, dg);
+        double2 v = *reinterpret_cast<const double2*>(&T[r + c * DG_LD]);
+        if (dg) {
+          if (r < c) v.x = 0.0;
+          if (r + 1 < c) v.y = 0.0;
+        }
+        lreg[q] = v;
+      }
+      double lv = 0.0;
       if (tid < TB && tj * TB + tid < f.n_valid) lv = log(dvec[tid]);
+      __syncthreads();
       DAG_TL(tl_mark(tl_now(), 3, tj);)
       diag_invert_smem<DAG_THREADS>(T, w, rdiag);
       DAG_TL(tl_mark(tl_now(), 4, tj);)
