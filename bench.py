@@ -164,8 +164,8 @@ def run_reference(args):
 
 
 def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the lauum launch from the committed ncu --set full
-    capture of the dominant kernel (profiles/r02_dag_factor_kernel_ncu.txt); None when the summary is absent."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dag_factor_kernel launch from the committed ncu --set full
+    capture of that kernel at the headline size (profiles/r02_dag_factor_kernel_ncu.txt); None when the summary is absent."""
     try:
         tot = 0.0
         for line in open(os.path.join(ROOT, "profiles", "r02_dag_factor_kernel_ncu.txt")):
