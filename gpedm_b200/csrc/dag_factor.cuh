@@ -25,6 +25,10 @@
 // long been final.
 // Results are bit-reproducible: each tile's summation order is fixed (k ascending), scheduling
 // only decides when a tile is computed, never how.
+// The serial chain DIAG(c) -> L(c+1, c) -> DIAG(c+1) bounds every factorisation below ~6000 rows; two hand-off rules
+// shorten it: tiles next to the diagonal are handed on in 32-column STRIPS (dag_strips_ready),
+// and the POTRF tiles L(c+1 .. c+t, c) are SOLVED against the block columns of L_cc as DIAG(c) publishes them
+// (DagPublishL / dag_trsm_chain) instead of waiting for D_c.  Which tiles are solved depends on their position only.
 #pragma once
 #include "dgemm_tile.cuh"
 #include "diag_block.cuh"

@@ -1,6 +1,7 @@
 #!/bin/bash
-# A/B of the strip hand-off on the Cholesky chain (dag_factor.cuh) and of the epilogue prefetch depth, one B200:
-# evaluation time per size with the results' bits, chain timeline, parity subset, lockstep batch rate.
+# A/B of the hand-off variants on the Cholesky chain (dag_factor.cuh: GPEDM_DAG_NO_STRIPS, GPEDM_DAG_TRSM), one B200:
+# evaluation time per size with the results' bits against the committed sweep, chain timeline with the raw marks of one
+# block column, parity subset, lockstep batch rate.
 O=gpurun_out
 SIZES="512 1024 2048 4096 8192"
 for cfg in "" "GPEDM_DAG_TRSM=3" "GPEDM_DAG_TRSM=4" "GPEDM_DAG_TRSM=1" "GPEDM_DAG_TRSM=0"; do
