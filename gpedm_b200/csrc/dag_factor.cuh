@@ -243,13 +243,14 @@ struct DagPublishL {
   }
 };
 
-// POTRF(c+1, c) side: L(c+1, c) = T L_cc^-T by blocked forward substitution, one 32-column strip per block column of
-// L_cc, each started as soon as DIAG(c) has published that block column - so the tile is complete one 32-wide solve
-// after the Cholesky of L_cc instead of after its inverse, the store of D_c and a 128^3 product.  (Same operation as
-// LAPACK dtrsm; the other tiles of the column are off the chain and keep the product with D_c.)
+// POTRF(i, c) side, i = c+1 .. c+t: L(i, c) = T L_cc^-T by blocked forward substitution, one 32-column strip per block
+// column of L_cc, each started as soon as DIAG(c) has published that block column - so the tile is complete one 32-wide
+// solve after the Cholesky of L_cc instead of after its inverse, the store of D_c and a 128^3 product.  (Same operation
+// as LAPACK dtrsm; the tiles further down the column are off the chain and keep the product with D_c.)
 //   T   resident tile in shared memory (128 x DG_LD), overwritten with L(c+1, c)
 //   Lq  scratch for the staged block column (128 x 32, stride DG_LD) + 32 reciprocals
-// Every strip is stored and counted for DIAG(c+1) as it completes (dag_strips_ready).
+// Every strip is stored and counted as it completes, for the Cholesky tasks of column c+1 whose last k tile this is
+// (dag_strips_ready).
 __device__ __forceinline__ void dag_trsm_chain(double* T, double* Lq, const double* Lcc, size_t ld, double* Cg, const int* prog, int* strip, int col) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
